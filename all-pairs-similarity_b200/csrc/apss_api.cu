@@ -1,0 +1,460 @@
+// apss_api.cu -- host engine + C ABI (include/apss.h) of the B200 all-pairs similarity scorer.
+// One handle = one index worker on one GPU (replaces IndexingWorkerActor, IWA:21-149).
+#include "apss.h"
+#include "apss_kernels.cuh"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace apss;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  // grow to >= n elements, preserving the first `keep` elements
+  cudaError_t reserve(size_t n, size_t keep, cudaStream_t s) {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = std::max(n, cap + cap / 2);
+    ncap = (ncap + 255) & ~size_t(255);
+    T* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p && keep) { e = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s); if (e != cudaSuccess) { cudaFree(np); return e; } }
+    if (p) { cudaStreamSynchronize(s); cudaFree(p); }
+    p = np; cap = ncap;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  size_t bytes() const { return cap * sizeof(T); }
+};
+
+}  // namespace
+
+struct apss_handle {
+  apss_config cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  int CR = 0, WARPS = 0, variant = 0;
+  size_t smem_bytes = 0;
+  std::string err;
+  bool frozen = false, custom_keys = false;
+  int64_t next_id = 0;
+  int max_nnz_seen = 0;
+
+  // shard
+  int64_t n_local = 0, nnz = 0, n_post = 0;
+  int64_t ntiles = 0;
+  DevBuf<int64_t> fwd_ptr; DevBuf<int32_t> fwd_idx; DevBuf<double> fwd_val; DevBuf<int32_t> gid; DevBuf<int64_t> key;
+  DevBuf<uint2> post; DevBuf<int32_t> dir; DevBuf<int64_t> tile_base;
+  DevBuf<double> maxw;
+  // batch staging
+  DevBuf<int64_t> b_ptr; DevBuf<int32_t> b_idx; DevBuf<double> b_val; DevBuf<int64_t> b_key; DevBuf<int32_t> b_first;
+  DevBuf<int32_t> q_cnt, q_ptr, q_dim; DevBuf<double> q_val; DevBuf<float> q_w; DevBuf<uint8_t> q_status;
+  // build scratch
+  DevBuf<unsigned long long> s_keys_in, s_keys_out, s_vals_in; DevBuf<int64_t> s_tile_start; DevBuf<char> cub_tmp;
+  // outputs
+  DevBuf<int32_t> pf_q, pf_c; DevBuf<float> pf_est;
+  DevBuf<int32_t> out_q, out_c; DevBuf<double> out_sim;
+  unsigned long long* d_counters = nullptr;
+  unsigned long long* h_counters = nullptr;   // pinned
+  int32_t* h_total = nullptr;                 // pinned
+  cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
+
+  // last batch
+  int32_t last_n = -1; int64_t last_pairs = 0;
+  std::vector<uint8_t> last_status; bool status_fetched = false;
+  // totals
+  int64_t tot_postings = 0, tot_cands = 0, tot_pairs = 0, tot_pf = 0, score_launches = 0, kernel_launches = 0;
+  double tot_score_ms = 0;
+
+  int32_t fail(int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return h->fail(e_ == cudaErrorMemoryAllocation ? APSS_E_NOMEM : APSS_E_CUDA, \
+                                          "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+template <int WARPS, int UNROLL>
+static cudaError_t launch_score_t(apss_handle* h, const ScoreArgs& a, bool dup) {
+  auto kern = dup ? k_score<WARPS, UNROLL, true> : k_score<WARPS, UNROLL, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  if (e != cudaSuccess) return e;
+  kern<<<h->sm_count, WARPS * 32, h->smem_bytes, h->stream>>>(a);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_score(apss_handle* h, const ScoreArgs& a, bool dup) {
+  const int unroll = (h->variant & 0xff);
+  switch (h->WARPS) {
+    case 8: return unroll == 8 ? launch_score_t<8, 8>(h, a, dup) : launch_score_t<8, 4>(h, a, dup);
+    case 16: return unroll == 8 ? launch_score_t<16, 8>(h, a, dup) : (unroll == 2 ? launch_score_t<16, 2>(h, a, dup) : launch_score_t<16, 4>(h, a, dup));
+    case 32: return unroll == 8 ? launch_score_t<32, 8>(h, a, dup) : launch_score_t<32, 4>(h, a, dup);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+extern "C" int32_t apss_abi_version(void) { return APSS_ABI_VERSION; }
+
+extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
+  if (!cfg || !out || cfg->struct_size != (int32_t)sizeof(apss_config)) return APSS_E_INVALID;
+  *out = nullptr;
+  if (cfg->dim <= 0 || !(cfg->index_threshold >= 0.0) || (cfg->semantics != APSS_SEM_R1 && cfg->semantics != APSS_SEM_R0)) return APSS_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) { cudaGetLastError(); return APSS_E_NO_DEVICE; }
+  apss_handle* h = new apss_handle();
+  h->cfg = *cfg; h->cfg.max_weight = nullptr; h->device = cfg->device;
+  auto bail = [&](int32_t rc) { apss_destroy(h); return rc; };
+  if (cudaSetDevice(h->device) != cudaSuccess) return bail(APSS_E_NO_DEVICE);
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return bail(APSS_E_NO_DEVICE);
+  h->sm_count = prop.multiProcessorCount;
+  const size_t max_smem = prop.sharedMemPerBlockOptin;
+  int CR = cfg->tile_vectors > 0 ? cfg->tile_vectors : 3584;
+  CR = (CR + 127) / 128 * 128;
+  // warps per CTA: as many accumulator rows as fit in shared memory, from {32, 16, 8}
+  int warps = 0;
+  for (int w : {32, 16, 8}) if ((size_t)w * CR * sizeof(float) + 1024 <= max_smem) { warps = w; break; }
+  if (!warps) return bail(APSS_E_INVALID);
+  if ((cfg->kernel_variant >> 8) & 0xff) { int w = (cfg->kernel_variant >> 8) & 0xff; if ((w == 8 || w == 16 || w == 32) && (size_t)w * CR * sizeof(float) + 1024 <= max_smem) warps = w; }
+  h->CR = CR; h->WARPS = warps; h->variant = cfg->kernel_variant; h->smem_bytes = (size_t)warps * CR * sizeof(float);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(APSS_E_CUDA);
+  if (cudaMalloc(&h->d_counters, C_COUNT * sizeof(unsigned long long)) != cudaSuccess) return bail(APSS_E_NOMEM);
+  if (cudaMallocHost(&h->h_counters, C_COUNT * sizeof(unsigned long long)) != cudaSuccess) return bail(APSS_E_NOMEM);
+  if (cudaMallocHost(&h->h_total, sizeof(int32_t) * 4) != cudaSuccess) return bail(APSS_E_NOMEM);
+  cudaEventCreate(&h->ev_b0); cudaEventCreate(&h->ev_b1); cudaEventCreate(&h->ev_s0); cudaEventCreate(&h->ev_s1);
+  if (cfg->max_weight) {
+    if (h->maxw.reserve(cfg->dim, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+    if (cudaMemcpyAsync(h->maxw.p, cfg->max_weight, sizeof(double) * cfg->dim, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return bail(APSS_E_CUDA);
+  }
+  if (cfg->reserve_vectors > 0) {
+    int64_t nv = cfg->reserve_vectors, nt = (nv + CR - 1) / CR;
+    if (h->fwd_ptr.reserve(nv + 1, 0, h->stream) != cudaSuccess || h->gid.reserve(nv, 0, h->stream) != cudaSuccess ||
+        h->key.reserve(nv, 0, h->stream) != cudaSuccess || h->dir.reserve((size_t)nt * ((size_t)cfg->dim + 1), 0, h->stream) != cudaSuccess ||
+        h->tile_base.reserve(nt + 1, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+  }
+  if (cfg->reserve_nnz > 0) {
+    if (h->fwd_idx.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess || h->fwd_val.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess ||
+        h->post.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+  }
+  {
+    size_t np = cfg->reserve_pairs > 0 ? (size_t)cfg->reserve_pairs : (size_t)1 << 20;
+    if (h->pf_q.reserve(np, 0, h->stream) != cudaSuccess || h->pf_c.reserve(np, 0, h->stream) != cudaSuccess || h->pf_est.reserve(np, 0, h->stream) != cudaSuccess ||
+        h->out_q.reserve(np, 0, h->stream) != cudaSuccess || h->out_c.reserve(np, 0, h->stream) != cudaSuccess || h->out_sim.reserve(np, 0, h->stream) != cudaSuccess)
+      return bail(APSS_E_NOMEM);
+  }
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(APSS_E_CUDA);
+  *out = h;
+  return APSS_OK;
+}
+
+extern "C" void apss_destroy(apss_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->fwd_ptr.release(); h->fwd_idx.release(); h->fwd_val.release(); h->gid.release(); h->key.release();
+  h->post.release(); h->dir.release(); h->tile_base.release(); h->maxw.release();
+  h->b_ptr.release(); h->b_idx.release(); h->b_val.release(); h->b_key.release(); h->b_first.release();
+  h->q_cnt.release(); h->q_ptr.release(); h->q_dim.release(); h->q_val.release(); h->q_w.release(); h->q_status.release();
+  h->s_keys_in.release(); h->s_keys_out.release(); h->s_vals_in.release(); h->s_tile_start.release(); h->cub_tmp.release();
+  h->pf_q.release(); h->pf_c.release(); h->pf_est.release(); h->out_q.release(); h->out_c.release(); h->out_sim.release();
+  if (h->d_counters) cudaFree(h->d_counters);
+  if (h->h_counters) cudaFreeHost(h->h_counters);
+  if (h->h_total) cudaFreeHost(h->h_total);
+  if (h->ev_b0) cudaEventDestroy(h->ev_b0);
+  if (h->ev_b1) cudaEventDestroy(h->ev_b1);
+  if (h->ev_s0) cudaEventDestroy(h->ev_s0);
+  if (h->ev_s1) cudaEventDestroy(h->ev_s1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+// IWA:61-71 on the GPU: append the batch's pruned vectors to the forward store and (re)build the
+// index tiles they fall into: at most the last, partially filled tile plus the new ones.
+static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const int64_t* d_ext_keys) {
+  cudaStream_t s = h->stream;
+  const int CR = h->CR; const int D = h->cfg.dim;
+  const int64_t n_old = h->n_local, n_new = n_old + n, nnz_old = h->nnz, nnz_new = nnz_old + batch_nnz;
+  CK(h->fwd_ptr.reserve(n_new + 1, n_old ? n_old + 1 : 0, s));
+  CK(h->gid.reserve(n_new, n_old, s));
+  CK(h->key.reserve(n_new, n_old, s));
+  CK(h->fwd_idx.reserve(std::max<int64_t>(nnz_new, 1), nnz_old, s));
+  CK(h->fwd_val.reserve(std::max<int64_t>(nnz_new, 1), nnz_old, s));
+  k_append_rows<<<cdiv(n, 256), 256, 0, s>>>(n, h->q_ptr.p, nnz_old, n_old, h->next_id, d_ext_keys, h->fwd_ptr.p, h->gid.p, h->key.p);
+  CK(cudaGetLastError()); h->kernel_launches++;
+  if (batch_nnz) {
+    CK(cudaMemcpyAsync(h->fwd_idx.p + nnz_old, h->q_dim.p, sizeof(int32_t) * batch_nnz, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->fwd_val.p + nnz_old, h->q_val.p, sizeof(double) * batch_nnz, cudaMemcpyDeviceToDevice, s));
+  }
+  // tiles to (re)build: [tile0, tile1)
+  const int64_t tile0 = n_old / CR, tile1 = (n_new + CR - 1) / CR;
+  const int ntiles_aff = (int)(tile1 - tile0);
+  const int64_t row_lo = tile0 * CR;
+  // first stored component of row_lo: the open tile's postings are rewritten in place
+  int64_t nnz_lo = nnz_old;
+  if (row_lo < n_old) {
+    CK(cudaMemcpyAsync(h->h_counters + C_COUNT - 1, h->fwd_ptr.p + row_lo, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    nnz_lo = (int64_t)h->h_counters[C_COUNT - 1];
+  }
+  const int64_t m = nnz_new - nnz_lo;
+  const int64_t post_base = nnz_lo;   // postings are stored in the same order of tiles as the forward store
+  CK(h->post.reserve(std::max<int64_t>(nnz_new, 1), post_base, s));
+  CK(h->dir.reserve((size_t)tile1 * ((size_t)D + 1), (size_t)tile0 * ((size_t)D + 1), s));
+  CK(h->tile_base.reserve(tile1 + 1, tile0, s));
+  CK(h->s_tile_start.reserve(ntiles_aff + 1, 0, s));
+  int dimbits = 1; while ((1LL << dimbits) < (int64_t)D + 1) ++dimbits;
+  int tilebits = 1; while ((1LL << tilebits) < ntiles_aff) ++tilebits;
+  if (m > 0) {
+    CK(h->s_keys_in.reserve(m, 0, s)); CK(h->s_keys_out.reserve(m, 0, s)); CK(h->s_vals_in.reserve(m, 0, s));
+    k_emit_postings<<<cdiv(m, 256), 256, 0, s>>>(nnz_lo, nnz_new, row_lo, n_new, h->fwd_ptr.p, h->fwd_idx.p, h->fwd_val.p, CR, tile0, dimbits,
+                                                  h->s_keys_in.p, h->s_vals_in.p);
+    CK(cudaGetLastError()); h->kernel_launches++;
+    size_t tmp = 0;
+    unsigned long long* vals_out = reinterpret_cast<unsigned long long*>(h->post.p + post_base);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->s_keys_in.p, h->s_keys_out.p, h->s_vals_in.p, vals_out, m, 0, dimbits + tilebits, s));
+    CK(h->cub_tmp.reserve(tmp, 0, s));
+    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, h->s_keys_in.p, h->s_keys_out.p, h->s_vals_in.p, vals_out, m, 0, dimbits + tilebits, s));
+    h->kernel_launches += 4;
+  }
+  k_tile_starts<<<cdiv(ntiles_aff + 1, 128), 128, 0, s>>>(h->s_keys_out.p, m, ntiles_aff, dimbits, post_base, tile0, h->s_tile_start.p, h->tile_base.p);
+  CK(cudaGetLastError());
+  k_build_dir<<<cdiv(((int64_t)D + 1) * ntiles_aff, 256), 256, 0, s>>>(h->s_keys_out.p, m, ntiles_aff, D, dimbits, h->s_tile_start.p, tile0, h->dir.p);
+  CK(cudaGetLastError()); h->kernel_launches += 2;
+  h->n_local = n_new; h->nnz = nnz_new; h->n_post = nnz_new; h->ntiles = tile1;
+  return APSS_OK;
+}
+
+extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* indptr, const int32_t* indices, const double* values,
+                                     const int64_t* ext_keys, const int32_t* first_dim, uint32_t flags, apss_batch_result* out) {
+  if (!h) return APSS_E_INVALID;
+  if (n < 0 || (n > 0 && (!indptr || (!indices && !values)))) return h->fail(APSS_E_INVALID, "null batch arrays");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const bool dev_ptrs = flags & APSS_BATCH_DEVICE_PTRS;
+  const bool query_only = (flags & APSS_BATCH_QUERY_ONLY) || h->frozen;
+  const int D = h->cfg.dim;
+  h->last_n = -1; h->last_pairs = 0;
+  apss_batch_result res{};
+  res.n_vectors = n; res.id_base = h->next_id;
+  if (n == 0) { h->last_n = 0; h->last_status.clear(); if (out) *out = res; return APSS_OK; }
+
+  CK(cudaEventRecord(h->ev_b0, s));
+  // ---- stage the batch on the device
+  const int64_t* d_ptr; const int32_t* d_idx; const double* d_val; const int64_t* d_keys = nullptr; const int32_t* d_first = nullptr;
+  int64_t in_nnz = 0;
+  if (dev_ptrs) {
+    d_ptr = indptr; d_idx = indices; d_val = values; d_keys = ext_keys; d_first = first_dim;
+  } else {
+    in_nnz = indptr[n];
+    if (indptr[0] != 0 || in_nnz < 0) return h->fail(APSS_E_INPUT, "indptr must start at 0 and be non-negative");
+    CK(h->b_ptr.reserve(n + 1, 0, s)); CK(h->b_idx.reserve(std::max<int64_t>(in_nnz, 1), 0, s)); CK(h->b_val.reserve(std::max<int64_t>(in_nnz, 1), 0, s));
+    CK(cudaMemcpyAsync(h->b_ptr.p, indptr, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+    if (in_nnz) {
+      CK(cudaMemcpyAsync(h->b_idx.p, indices, sizeof(int32_t) * in_nnz, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(h->b_val.p, values, sizeof(double) * in_nnz, cudaMemcpyHostToDevice, s));
+    }
+    d_ptr = h->b_ptr.p; d_idx = h->b_idx.p; d_val = h->b_val.p;
+    if (ext_keys) { CK(h->b_key.reserve(n, 0, s)); CK(cudaMemcpyAsync(h->b_key.p, ext_keys, sizeof(int64_t) * n, cudaMemcpyHostToDevice, s)); d_keys = h->b_key.p; }
+    if (first_dim) { CK(h->b_first.reserve(n, 0, s)); CK(cudaMemcpyAsync(h->b_first.p, first_dim, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s)); d_first = h->b_first.p; }
+  }
+  if (h->cfg.semantics == APSS_SEM_R0 && !d_first) return h->fail(APSS_E_INVALID, "semantics R0 needs first_dim[]");
+
+  // ---- K5: validate + admit + prune (count, scan, write)
+  CK(h->q_cnt.reserve(n + 1, 0, s)); CK(h->q_ptr.reserve(n + 1, 0, s)); CK(h->q_status.reserve(n, 0, s));
+  CK(cudaMemsetAsync(h->d_counters, 0, C_COUNT * sizeof(unsigned long long), s));
+  const double admit_thr = (flags & APSS_BATCH_SKIP_ADMIT) ? -INFINITY : h->cfg.similarity_threshold;
+  k_prefilter_count<<<cdiv(n + 1, 128), 128, 0, s>>>(n, d_ptr, d_idx, d_val, D, h->maxw.p, admit_thr, h->cfg.index_threshold,
+                                                     h->q_cnt.p, h->q_status.p, h->d_counters);
+  CK(cudaGetLastError());
+  size_t tmp = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, h->q_cnt.p, h->q_ptr.p, n + 1, s));
+  CK(h->cub_tmp.reserve(tmp, 0, s));
+  CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tmp, h->q_cnt.p, h->q_ptr.p, n + 1, s));
+  h->kernel_launches += 3;
+  CK(cudaMemcpyAsync(h->h_counters, h->d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_total, h->q_ptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  h->last_status.resize(n);
+  CK(cudaMemcpyAsync(h->last_status.data(), h->q_status.p, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (h->h_counters[C_ERR]) {   // all-or-nothing (Q9): the index has not been touched yet
+    return h->fail(APSS_E_INPUT, h->h_counters[C_ERR] == 2 ? "indptr is not monotone / does not start at 0"
+                                                           : "indices must be strictly increasing and < dim (SparseVector.scala:96-108)");
+  }
+  const int32_t batch_nnz = h->h_total[0];
+  res.n_rejected = (int32_t)h->h_counters[C_NREJ]; res.n_empty = (int32_t)h->h_counters[C_NEMPTY]; res.n_active = (int32_t)h->h_counters[C_NACTIVE];
+  h->max_nnz_seen = std::max(h->max_nnz_seen, (int)h->h_counters[C_MAXNNZ]);
+  CK(h->q_dim.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_val.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_w.reserve(std::max(batch_nnz, 1), 0, s));
+  k_prefilter_write<<<cdiv(n, 128), 128, 0, s>>>(n, d_ptr, d_idx, d_val, h->cfg.index_threshold, h->q_status.p, h->q_ptr.p, h->q_dim.p, h->q_val.p, h->q_w.p);
+  CK(cudaGetLastError()); h->kernel_launches++;
+  if (d_keys) h->custom_keys = true;
+
+  // ---- K1: index first, then query (IWA:125-132)
+  int64_t q_local_base = -1;
+  if (!query_only) {
+    q_local_base = h->n_local;
+    int32_t rc = index_append(h, n, batch_nnz, d_keys);
+    if (rc != APSS_OK) return rc;
+    h->next_id += n;
+  }
+
+  // ---- K2/K3: scoring + threshold/compaction, K4: fp64 verify.  Re-run on output overflow.
+  const double t = h->cfg.similarity_threshold;
+  float thr_emit;
+  if (t > 0) {
+    const double band = (double)(h->max_nnz_seen + 8) * std::ldexp(1.0, -23);
+    thr_emit = std::nextafterf((float)(t * (1.0 - band)), -INFINITY);
+  } else thr_emit = -INFINITY;
+  // when keys are supplied, q_key lives in b_key (host path) or the caller's buffer (device path)
+  const int64_t* d_qkey = d_keys;
+  if (h->custom_keys && !d_qkey) return h->fail(APSS_E_INVALID, "ext_keys were supplied for earlier batches: supply them for every batch");
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    ScoreArgs a{};
+    a.q_ptr = h->q_ptr.p; a.q_dim = h->q_dim.p; a.q_w = h->q_w.p; a.q_key = d_qkey;
+    a.post = h->post.p; a.dir = h->dir.p; a.tile_base = h->tile_base.p; a.c_key = h->key.p;
+    a.nq = n; a.ntiles = (int32_t)h->ntiles; a.D = D; a.CR = h->CR; a.q_local_base = q_local_base;
+    a.thr_emit = thr_emit;
+    a.out_q = h->pf_q.p; a.out_c = h->pf_c.p; a.out_est = h->pf_est.p; a.out_cap = h->pf_q.cap;
+    a.counters = h->d_counters;
+    a.total_items = (unsigned long long)h->ntiles * (unsigned long long)n;
+    CK(cudaMemsetAsync(h->d_counters, 0, 7 * sizeof(unsigned long long), s));   // keep the prefilter tallies
+    CK(cudaEventRecord(h->ev_s0, s));
+    if (a.total_items && batch_nnz) { CK(launch_score(h, a, h->custom_keys)); h->score_launches++; h->kernel_launches++; }
+    CK(cudaEventRecord(h->ev_s1, s));
+    CK(h->out_q.reserve(h->pf_q.cap, 0, s)); CK(h->out_c.reserve(h->pf_q.cap, 0, s)); CK(h->out_sim.reserve(h->pf_q.cap, 0, s));
+    if (h->n_local) {
+      k_verify<<<h->sm_count * 4, 256, 0, s>>>(h->d_counters, h->pf_q.cap, h->pf_q.p, h->pf_c.p, h->q_ptr.p, h->q_dim.p, h->q_val.p,
+                                               h->fwd_ptr.p, h->fwd_idx.p, h->fwd_val.p, h->gid.p, t, h->cfg.semantics == APSS_SEM_R0, d_first,
+                                               h->out_q.p, h->out_c.p, h->out_sim.p, h->d_counters);
+      CK(cudaGetLastError()); h->kernel_launches++;
+    }
+    CK(cudaEventRecord(h->ev_b1, s));
+    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h->h_counters[C_PF] <= h->pf_q.cap) break;
+    if (attempt == 2) return h->fail(APSS_E_NOMEM, "pair buffer overflow persisted");
+    const size_t need = (size_t)h->h_counters[C_PF] + 1024;     // grow and replay
+    CK(h->pf_q.reserve(need, 0, s)); CK(h->pf_c.reserve(need, 0, s)); CK(h->pf_est.reserve(need, 0, s));
+  }
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, h->ev_s0, h->ev_s1)); res.score_ms = ms;
+  CK(cudaEventElapsedTime(&ms, h->ev_b0, h->ev_b1)); res.device_ms = ms;
+  res.n_prefilter = (int64_t)h->h_counters[C_PF];
+  res.postings_visited = (int64_t)h->h_counters[C_POSTINGS];
+  res.candidates_unique = (int64_t)h->h_counters[C_CANDS];
+  res.n_pairs = (int64_t)h->h_counters[C_FINAL];
+  res.n_pairs_r1 = (int64_t)h->h_counters[C_R1];
+  res.work_items = (int64_t)((unsigned long long)h->ntiles * (unsigned long long)n);
+  h->last_n = n; h->last_pairs = res.n_pairs;
+  h->tot_postings += res.postings_visited; h->tot_cands += res.candidates_unique; h->tot_pairs += res.n_pairs; h->tot_pf += res.n_prefilter;
+  h->tot_score_ms += res.score_ms;
+  if (out) *out = res;
+  return APSS_OK;
+}
+
+extern "C" int32_t apss_fetch_pairs(apss_handle* h, int32_t* q, int32_t* c, double* sim, int64_t capacity, int64_t* n_out) {
+  if (!h) return APSS_E_INVALID;
+  if (h->last_n < 0) return h->fail(APSS_E_STATE, "no completed batch to fetch from");
+  CK(cudaSetDevice(h->device));
+  const int64_t m = std::min<int64_t>(h->last_pairs, capacity < 0 ? 0 : capacity);
+  if (m > 0) {
+    if (q) CK(cudaMemcpyAsync(q, h->out_q.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, h->stream));
+    if (c) CK(cudaMemcpyAsync(c, h->out_c.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, h->stream));
+    if (sim) CK(cudaMemcpyAsync(sim, h->out_sim.p, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  if (n_out) *n_out = h->last_pairs;
+  return APSS_OK;
+}
+
+extern "C" int32_t apss_pairs_device(apss_handle* h, const int32_t** q, const int32_t** c, const double** sim, int64_t* n) {
+  if (!h) return APSS_E_INVALID;
+  if (h->last_n < 0) return h->fail(APSS_E_STATE, "no completed batch");
+  if (q) *q = h->out_q.p;
+  if (c) *c = h->out_c.p;
+  if (sim) *sim = h->out_sim.p;
+  if (n) *n = h->last_pairs;
+  return APSS_OK;
+}
+
+extern "C" int32_t apss_fetch_status(apss_handle* h, uint8_t* status, int32_t capacity) {
+  if (!h || !status) return APSS_E_INVALID;
+  if (h->last_n < 0) return h->fail(APSS_E_STATE, "no completed batch");
+  const int32_t m = std::min<int32_t>(capacity, (int32_t)h->last_status.size());
+  if (m > 0) std::memcpy(status, h->last_status.data(), m);
+  return APSS_OK;
+}
+
+extern "C" int32_t apss_freeze(apss_handle* h) { if (!h) return APSS_E_INVALID; h->frozen = true; return APSS_OK; }
+
+extern "C" int32_t apss_set_next_id(apss_handle* h, int64_t next_id) {
+  if (!h) return APSS_E_INVALID;
+  if (next_id < 0 || next_id > 0x7fffffffLL) return h->fail(APSS_E_INVALID, "next_id out of int32 range");
+  h->next_id = next_id;
+  return APSS_OK;
+}
+
+extern "C" int32_t apss_get_stats(apss_handle* h, apss_stats* out) {
+  if (!h || !out) return APSS_E_INVALID;
+  apss_stats s{};
+  s.n_vectors = h->n_local; s.n_postings = h->n_post; s.n_tiles = h->ntiles;
+  s.bytes_postings = h->n_post * 8; s.bytes_directory = h->ntiles * ((int64_t)h->cfg.dim + 1) * 4;
+  s.bytes_forward = h->nnz * 12 + (h->n_local + 1) * 8;
+  s.tot_postings_visited = h->tot_postings; s.tot_candidates_unique = h->tot_cands; s.tot_pairs = h->tot_pairs; s.tot_prefilter = h->tot_pf;
+  s.score_launches = h->score_launches; s.kernel_launches = h->kernel_launches; s.tot_score_ms = h->tot_score_ms;
+  s.frozen = h->frozen; s.tile_vectors = h->CR; s.warps_per_cta = h->WARPS; s.sm_count = h->sm_count;
+  *out = s;
+  return APSS_OK;
+}
+
+extern "C" const char* apss_last_error(apss_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" void* apss_stream(apss_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+extern "C" int32_t apss_microbench_accumulators(int32_t device, int32_t mode, int32_t warps, int32_t iters, double* updates_per_sec) {
+  if (!updates_per_sec || warps < 1 || warps > 32) return APSS_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return APSS_E_NO_DEVICE; }
+  cudaSetDevice(device);
+  cudaDeviceProp prop{}; cudaGetDeviceProperties(&prop, device);
+  const int CR = 2048;
+  const size_t smem = (size_t)warps * CR * 4;
+  unsigned* sink = nullptr; cudaMalloc(&sink, 4);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto run = [&](int it) {
+    switch (mode) {
+#define MB(M) case M: cudaFuncSetAttribute(k_microbench<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                      k_microbench<M><<<prop.multiProcessorCount, warps * 32, smem>>>(CR, it, sink); break;
+      MB(0) MB(1) MB(2) MB(3) MB(4) MB(5)
+#undef MB
+      default: break;
+    }
+  };
+  run(8); cudaDeviceSynchronize();
+  cudaEventRecord(e0); run(iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  cudaError_t e = cudaGetLastError();
+  cudaFree(sink); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (e != cudaSuccess) return APSS_E_CUDA;
+  *updates_per_sec = (double)prop.multiProcessorCount * warps * 32.0 * 4.0 * iters / (ms * 1e-3);
+  return APSS_OK;
+}

@@ -1,0 +1,344 @@
+// apss_kernels.cuh -- device code of the B200 (sm_100a) all-pairs similarity scorer.
+//
+// Data layout in HBM (one shard = one GPU):
+//   forward store   fwd_ptr[n+1] (int64), fwd_idx[nnz] (int32), fwd_val[nnz] (fp64): the pruned vectors
+//                   exactly as WWA:193-194 stores them; read only by the fp64 verify kernel.
+//   index tiles     the shard's vectors are cut into tiles of CR consecutive local ids.  Each tile
+//                   owns (a) its postings, sorted by dimension then id, 8 B each:
+//                   (id within tile : int32, weight : fp32)  and (b) a dense directory
+//                   dir[tile][0..D] of int32 offsets into the tile's postings.  Tiles are
+//                   append-only: an insert rebuilds at most the last, partially filled tile.
+//   query batch     q_ptr[nq+1] (int32), q_dim[] (int32), q_w[] (fp32) + q_val[] (fp64 for verify).
+//
+// Reference code replaced (core/src/main/scala/cpslab/deploy/...):
+//   k_prefilter_*   EntryProxyActor.scala:81-93 (admission) + WriteWorkerActor.scala:185-202 (prune)
+//   k_emit_postings / k_build_dir    IndexingWorkerActor.scala:61-71 (buildInvertedIndex)
+//   k_score         IndexingWorkerActor.scala:74-111 + CommonUtils.scala:98-117 (fp32 pre-filter)
+//   k_verify        CommonUtils.scala:98-117 in fp64 + the threshold at IndexingWorkerActor.scala:93
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace apss {
+
+enum Counter : int {
+  C_PF = 0,        // fp32 guard-band survivors (prefilter records)
+  C_POSTINGS = 1,  // postings visited
+  C_CANDS = 2,     // touched accumulators (candidates_unique)
+  C_FINAL = 3,     // pairs reported
+  C_R1 = 4,        // pairs with dot >= t
+  C_ERR = 5,       // validation error code (0 = ok)
+  C_WORK = 6,      // persistent-kernel work cursor
+  C_NREJ = 7, C_NEMPTY = 8, C_NACTIVE = 9, C_MAXNNZ = 10,
+  C_COUNT = 16
+};
+
+static constexpr unsigned FULL = 0xffffffffu;
+static constexpr unsigned NEG0 = 0x80000000u;   // accumulator "never touched" marker (-0.0f)
+
+__device__ __forceinline__ uint2 ld_stream(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+// ------------------------------------------------------------------ K5: admission + value prune
+
+// One thread per input vector.  Validates (SparseVector.scala:96-108: strictly increasing indices,
+// all < size), evaluates the admission predicate of EPA:81-93 on the UN-pruned vector in ascending
+// index order (fp64, separate multiply and add) and counts the components that survive
+// `value > indexThreshold` (strict; WWA:192).
+__global__ void k_prefilter_count(int n, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                  const double* __restrict__ val, int D, const double* __restrict__ maxw,
+                                  double sim_thr, double idx_thr, int32_t* __restrict__ cnt,
+                                  uint8_t* __restrict__ status, unsigned long long* counters) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > n) return;
+  if (v == n) { cnt[n] = 0; return; }
+  int64_t a = ptr[v], b = ptr[v + 1];
+  if (b < a || (v == 0 && a != 0)) { atomicMax(&counters[C_ERR], 2ULL); cnt[v] = 0; status[v] = 0; return; }
+  double s = 0.0; int kept = 0; int prev = -1; bool bad = false;
+  for (int64_t p = a; p < b; ++p) {
+    int d = idx[p]; double x = val[p];
+    if (d <= prev || d >= D) { bad = true; break; }
+    prev = d;
+    double mw = maxw ? maxw[d] : 1.0;
+    s = __dadd_rn(s, __dmul_rn(mw, x));
+    kept += (x > idx_thr);
+  }
+  if (bad) { atomicMax(&counters[C_ERR], 3ULL); cnt[v] = 0; status[v] = 0; return; }
+  uint8_t st;
+  if (!(s >= sim_thr)) { st = 0; kept = 0; atomicAdd(&counters[C_NREJ], 1ULL); }
+  else if (kept == 0) { st = 1; atomicAdd(&counters[C_NEMPTY], 1ULL); }
+  else { st = 2; atomicAdd(&counters[C_NACTIVE], 1ULL); atomicMax(&counters[C_MAXNNZ], (unsigned long long)kept); }
+  status[v] = st; cnt[v] = kept;
+}
+
+__global__ void k_prefilter_write(int n, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                  const double* __restrict__ val, double idx_thr, const uint8_t* __restrict__ status,
+                                  const int32_t* __restrict__ q_ptr, int32_t* __restrict__ q_dim,
+                                  double* __restrict__ q_val, float* __restrict__ q_w) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n || status[v] != 2) return;
+  int o = q_ptr[v];
+  for (int64_t p = ptr[v]; p < ptr[v + 1]; ++p) {
+    double x = val[p];
+    if (x > idx_thr) { q_dim[o] = idx[p]; q_val[o] = x; q_w[o] = (float)x; ++o; }
+  }
+}
+
+// ------------------------------------------------------------------ K1: index append
+
+__global__ void k_append_rows(int n, const int32_t* __restrict__ q_ptr, int64_t nnz_base, int64_t n_local,
+                              int64_t id_base, const int64_t* __restrict__ ext_keys,
+                              int64_t* __restrict__ fwd_ptr, int32_t* __restrict__ gid, int64_t* __restrict__ key) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  if (v == 0 && n_local == 0) fwd_ptr[0] = 0;
+  fwd_ptr[n_local + v + 1] = nnz_base + q_ptr[v + 1];
+  gid[n_local + v] = (int32_t)(id_base + v);
+  key[n_local + v] = ext_keys ? ext_keys[v] : (id_base + v);
+}
+
+// One thread per stored component in [nnz_lo, nnz_hi): find its row, emit (sort key, posting).
+__global__ void k_emit_postings(int64_t nnz_lo, int64_t nnz_hi, int64_t row_lo, int64_t row_hi,
+                                const int64_t* __restrict__ fwd_ptr, const int32_t* __restrict__ fwd_idx,
+                                const double* __restrict__ fwd_val, int CR, int64_t tile0, int dimbits,
+                                unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
+  int64_t p = nnz_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnz_hi) return;
+  int64_t lo = row_lo, hi = row_hi;          // largest row with fwd_ptr[row] <= p
+  while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (fwd_ptr[mid] <= p) lo = mid; else hi = mid; }
+  int64_t row = lo;
+  unsigned long long tile_rel = (unsigned long long)(row / CR - tile0);
+  unsigned in_tile = (unsigned)(row % CR);
+  keys[p - nnz_lo] = (tile_rel << dimbits) | (unsigned)fwd_idx[p];
+  vals[p - nnz_lo] = ((unsigned long long)__float_as_uint((float)fwd_val[p]) << 32) | in_tile;   // uint2{x = id, y = w}
+}
+
+__device__ __forceinline__ int64_t lower_bound_u64(const unsigned long long* __restrict__ a, int64_t n, unsigned long long key) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+__global__ void k_tile_starts(const unsigned long long* __restrict__ keys, int64_t m, int ntiles_aff, int dimbits,
+                              int64_t post_base, int64_t tile0, int64_t* __restrict__ tile_start, int64_t* __restrict__ tile_base) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > ntiles_aff) return;
+  int64_t s = lower_bound_u64(keys, m, (unsigned long long)t << dimbits);
+  tile_start[t] = s;
+  if (t < ntiles_aff) tile_base[tile0 + t] = post_base + s;
+}
+
+__global__ void k_build_dir(const unsigned long long* __restrict__ keys, int64_t m, int ntiles_aff, int D, int dimbits,
+                            const int64_t* __restrict__ tile_start, int64_t tile0, int32_t* __restrict__ dir) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t per = (int64_t)D + 1;
+  if (i >= per * ntiles_aff) return;
+  int t = (int)(i / per); int d = (int)(i - (int64_t)t * per);
+  int64_t lb = lower_bound_u64(keys, m, ((unsigned long long)t << dimbits) + (unsigned long long)d);
+  dir[(tile0 + t) * per + d] = (int32_t)(lb - tile_start[t]);
+}
+
+// ------------------------------------------------------------------ K2 + K3: scoring + threshold/compaction
+
+struct ScoreArgs {
+  const int32_t* q_ptr; const int32_t* q_dim; const float* q_w; const int64_t* q_key;
+  const uint2* post; const int32_t* dir; const int64_t* tile_base; const int64_t* c_key;
+  int32_t nq, ntiles, D, CR;
+  int64_t q_local_base;      // shard-local id of query 0 when the batch was indexed in this call, else -1
+  float thr_emit;            // t * (1 - guard band), rounded down
+  int32_t* out_q; int32_t* out_c; float* out_est; unsigned long long out_cap;
+  unsigned long long* counters;
+  unsigned long long total_items;
+};
+
+// Persistent kernel.  One CTA per SM, WARPS warps per CTA; each warp owns one row of CR fp32
+// accumulators in shared memory and loops over work items (index tile, query) drawn from a global
+// cursor (tile-major, so the warps of all SMs sweep the same tile's postings out of L2 together).
+// For one item the warp walks the query's terms: 32 directory look-ups at a time (one per lane),
+// then for every non-empty posting segment the lanes stream postings with coalesced 8 B loads and
+// do a plain LDS/FFMA/STS update -- no atomics are needed because (a) the row belongs to this warp
+// alone and (b) ids inside one posting list are distinct, so lanes never collide.  The epilogue
+// scans the row once: counts touched accumulators (candidates_unique), emits those >= thr_emit by
+// warp-aggregated atomic compaction, and resets the row to the "untouched" marker -0.0f.
+template <int WARPS, int UNROLL, bool DUPKEYS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_score(const ScoreArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* row = smem + (size_t)warp * a.CR;
+  const float4 neg0 = make_float4(__uint_as_float(NEG0), __uint_as_float(NEG0), __uint_as_float(NEG0), __uint_as_float(NEG0));
+  for (int i = lane * 4; i < a.CR; i += 128) *reinterpret_cast<float4*>(row + i) = neg0;
+  __syncwarp();
+
+  unsigned long long n_post = 0, n_cand = 0;
+  unsigned long long item = 0;
+  if (lane == 0) item = atomicAdd(&a.counters[C_WORK], 1ULL);
+  item = __shfl_sync(FULL, item, 0);
+
+  while (item < a.total_items) {
+    unsigned long long next = 0;
+    if (lane == 0) next = atomicAdd(&a.counters[C_WORK], 1ULL);   // latency hidden behind this item
+    const int tile = (int)(item / (unsigned)a.nq);
+    const int q = (int)(item - (unsigned long long)tile * (unsigned)a.nq);
+    const int ts = __ldg(a.q_ptr + q), te = __ldg(a.q_ptr + q + 1);
+    if (ts < te) {
+      const int32_t* __restrict__ dirt = a.dir + (size_t)tile * ((size_t)a.D + 1);
+      const uint2* __restrict__ pt = a.post + __ldg(a.tile_base + tile);
+      for (int t0 = ts; t0 < te; t0 += 32) {
+        const int t = t0 + lane;
+        int s = 0, e = 0; float wq = 0.f;
+        if (t < te) {
+          const int d = __ldg(a.q_dim + t);
+          wq = __ldg(a.q_w + t);
+          s = __ldg(dirt + d); e = __ldg(dirt + d + 1);
+        }
+        n_post += (unsigned)(e - s);
+        unsigned m = __ballot_sync(FULL, e > s);
+        while (m) {
+          const int j = __ffs(m) - 1; m &= m - 1;
+          const int sj = __shfl_sync(FULL, s, j), ej = __shfl_sync(FULL, e, j);
+          const float wj = __shfl_sync(FULL, wq, j);
+          int p = sj + lane;
+          for (; p + 32 * (UNROLL - 1) < ej; p += 32 * UNROLL) {
+            uint2 pp[UNROLL]; float av[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) pp[u] = ld_stream(pt + p + 32 * u);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) av[u] = row[pp[u].x];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) av[u] = fmaf(wj, __uint_as_float(pp[u].y), av[u]);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) row[pp[u].x] = av[u];
+          }
+          for (; p < ej; p += 32) {
+            const uint2 pp = ld_stream(pt + p);
+            row[pp.x] = fmaf(wj, __uint_as_float(pp.y), row[pp.x]);
+          }
+        }
+      }
+      __syncwarp();
+      // ---- epilogue: count, threshold, compact, reset
+      const long long c0 = (long long)tile * a.CR;
+      const long long self = (a.q_local_base >= 0) ? (a.q_local_base + q - c0) : -1;   // q's own slot in this tile, if any
+      long long qkey = 0;
+      if (DUPKEYS) qkey = __ldg(a.q_key + q);
+      for (int i = lane * 4; i < a.CR; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(row + i);
+        *reinterpret_cast<float4*>(row + i) = neg0;
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        unsigned tm = 0, pm = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool touched = __float_as_uint(vv[k]) != NEG0;
+          tm |= (unsigned)touched << k;
+          pm |= (unsigned)(touched && vv[k] >= a.thr_emit) << k;
+        }
+        if (self >= i && self < i + 4) { const unsigned bit = 1u << (int)(self - i); tm &= ~bit; pm &= ~bit; }
+        if (DUPKEYS && tm) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if ((tm >> k) & 1u) { if (__ldg(a.c_key + c0 + i + k) == qkey) { tm &= ~(1u << k); pm &= ~(1u << k); } }
+        }
+        n_cand += __popc(tm);
+        if (__ballot_sync(FULL, pm != 0)) {
+          const int cnt = __popc(pm);
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+          const int tot = __shfl_sync(FULL, incl, 31);
+          unsigned long long base = 0;
+          if (lane == 31) base = atomicAdd(&a.counters[C_PF], (unsigned long long)tot);
+          base = __shfl_sync(FULL, base, 31);
+          unsigned long long slot = base + (unsigned)(incl - cnt);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if ((pm >> k) & 1u) {
+              if (slot < a.out_cap) { a.out_q[slot] = q; a.out_c[slot] = (int32_t)(c0 + i + k); a.out_est[slot] = vv[k]; }
+              ++slot;
+            }
+        }
+      }
+      __syncwarp();
+    }
+    item = __shfl_sync(FULL, next, 0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_post += __shfl_down_sync(FULL, n_post, o);
+    n_cand += __shfl_down_sync(FULL, n_cand, o);
+  }
+  if (lane == 0) { atomicAdd(&a.counters[C_POSTINGS], n_post); atomicAdd(&a.counters[C_CANDS], n_cand); }
+}
+
+// ------------------------------------------------------------------ K4: fp64 verify
+
+// One thread per pre-filter record: exact sparse dot of the query and the stored candidate in
+// ascending dimension order, fp64, multiply and add rounded separately (CU:98-117; bit-identical to
+// the CPU oracle).  Applies `sim >= similarityThreshold` (IWA:93) and, for the as-built semantics
+// R0, drops pairs whose shared dims all equal first(q) (IWA:89 + IWA:106-107).
+__global__ void k_verify(const unsigned long long* counters, unsigned long long pf_cap,
+                         const int32_t* __restrict__ pf_q, const int32_t* __restrict__ pf_c,
+                         const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim, const double* __restrict__ q_val,
+                         const int64_t* __restrict__ fwd_ptr, const int32_t* __restrict__ fwd_idx, const double* __restrict__ fwd_val,
+                         const int32_t* __restrict__ gid, double thr, int sem_r0, const int32_t* __restrict__ first_dim,
+                         int32_t* __restrict__ out_q, int32_t* __restrict__ out_c, double* __restrict__ out_sim,
+                         unsigned long long* wcounters) {
+  unsigned long long n = counters[C_PF];
+  if (n > pf_cap) n = pf_cap;
+  for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (unsigned long long)gridDim.x * blockDim.x) {
+    const int q = pf_q[r], c = pf_c[r];
+    int i = q_ptr[q]; const int ie = q_ptr[q + 1];
+    int64_t j = fwd_ptr[c]; const int64_t je = fwd_ptr[c + 1];
+    const int fd = (sem_r0 && first_dim) ? first_dim[q] : -1;
+    double s = 0.0; int nonfirst = 0;
+    while (i < ie && j < je) {
+      const int di = q_dim[i], dj = fwd_idx[j];
+      if (di < dj) ++i; else if (di > dj) ++j;
+      else { s = __dadd_rn(s, __dmul_rn(fwd_val[j], q_val[i])); nonfirst += (di != fd); ++i; ++j; }
+    }
+    if (s >= thr) {
+      atomicAdd(&wcounters[C_R1], 1ULL);
+      if (!sem_r0 || nonfirst > 0) {
+        const unsigned long long slot = atomicAdd(&wcounters[C_FINAL], 1ULL);
+        out_q[slot] = q; out_c[slot] = gid[c]; out_sim[slot] = s;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ accumulator micro-benchmark
+
+// mode 0: LDS/FFMA/STS random   1: same, consecutive addresses   2: ATOMS.ADD u32 random
+// 3: ATOMS.ADD u32 consecutive  4: float atomicAdd (CAS loop) random   5: FFMA+F2I+ATOMS.ADD random
+template <int MODE>
+__global__ void k_microbench(int CR, int iters, unsigned* sink) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* row = smem + (size_t)warp * CR;
+  unsigned* urow = reinterpret_cast<unsigned*>(row);
+  for (int i = lane; i < CR; i += 32) row[i] = 0.f;
+  __syncwarp();
+  unsigned x = (blockIdx.x * 1315423911u) ^ (threadIdx.x * 2654435761u) ^ 12345u;
+  const float w = 1.0f + lane * 1e-3f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      x = x * 1664525u + 1013904223u;
+      int idx;   // CR is a power of two here
+      if (MODE == 1 || MODE == 3) idx = (int)((__shfl_sync(FULL, x, 0) >> 8) & (unsigned)(CR - 32)) + lane;   // 32 consecutive slots
+      else idx = (int)((x >> 8) & (unsigned)(CR - 1));                                                         // independent random slots
+      if (MODE == 0 || MODE == 1) row[idx] = fmaf(w, 0.5f, row[idx]);
+      else if (MODE == 2 || MODE == 3) atomicAdd(urow + idx, 3u);
+      else if (MODE == 4) atomicAdd(row + idx, w);
+      else atomicAdd(urow + idx, __float2uint_ru(fmaf(w, 1000.f, 0.5f)));
+    }
+  }
+  __syncwarp();
+  unsigned acc = 0;
+  for (int i = lane; i < CR; i += 32) acc += urow[i];
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
+}  // namespace apss

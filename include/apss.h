@@ -1,0 +1,166 @@
+/*
+ * apss.h -- C ABI of the B200-native inverted-index all-pairs similarity scorer.
+ *
+ * This is the drop-in boundary for ONE path of mcgill-cpslab/all-pairs-similarity: what an
+ * IndexingWorkerActor does with an IndexData message (index the batch, score it against every
+ * indexed vector, threshold, emit similar pairs).  The reference has no FFI of its own; the seam
+ * is its actor message protocol, so each entry point below names the reference code it replaces
+ * (paths relative to core/src/main/scala/cpslab/ in the reference):
+ *
+ *   IWA = deploy/server/IndexingWorkerActor.scala      WWA = deploy/server/WriteWorkerActor.scala
+ *   EPA = deploy/server/EntryProxyActor.scala          CU  = deploy/CommonUtils.scala
+ *
+ * A JVM host binds these through jni/apss_jni.c; this repo's own host side
+ * binds them through ctypes.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Threading: a handle is single-caller but not thread-affine (an Akka actor handles one message at
+ * a time on whatever dispatcher thread; IWA:122).  Every entry point selects the handle's device
+ * itself.  Distinct handles may be used concurrently.
+ *
+ * Errors: every function returns APSS_OK (0) or a negative apss_status; nothing aborts or throws
+ * across the boundary (the reference swallows exceptions per batch, IWA:124-137).  A batch that
+ * fails validation leaves the index untouched (all-or-nothing).
+ */
+#ifndef APSS_H_
+#define APSS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APSS_ABI_VERSION 1
+
+typedef enum apss_status {
+  APSS_OK = 0,
+  APSS_E_INVALID = -1,   /* bad argument / config                                  */
+  APSS_E_CUDA = -2,      /* CUDA runtime error (text in apss_last_error)           */
+  APSS_E_NOMEM = -3,     /* device or host allocation failed                       */
+  APSS_E_INPUT = -4,     /* batch failed validation (SparseVector.scala:96-108)    */
+  APSS_E_STATE = -5,     /* call not valid in this state (e.g. fetch before batch) */
+  APSS_E_NO_DEVICE = -6  /* no usable CUDA device: there is NO CPU fallback        */
+} apss_status;
+
+/* which result set is reported */
+#define APSS_SEM_R1 0 /* specified semantics: every pair sharing >= 1 dim with dot >= t            */
+#define APSS_SEM_R0 1 /* as-built: additionally drop pairs whose shared dims are all first(q)       */
+                      /* (IWA:89 + IWA:106-107); needs first_dim[] from the host                    */
+
+/* apss_insert_batch flags */
+#define APSS_BATCH_QUERY_ONLY 1u  /* score but do not index (frozen index, IWA:125,143-144)         */
+#define APSS_BATCH_DEVICE_PTRS 2u /* indptr/indices/values/ext_keys/first_dim are DEVICE pointers   */
+#define APSS_BATCH_SKIP_ADMIT 4u  /* vectors already passed EPA:81-93 upstream (IndexData carries   */
+                                  /* admitted, pruned vectors): do not re-apply the admission filter */
+
+/* per-input-vector status (apss_fetch_status) */
+#define APSS_ST_REJECTED 0 /* failed the admission filter (EPA:81-93)                               */
+#define APSS_ST_EMPTY 1    /* admitted but value-pruned to nothing (WWA:192-199): stored, never sent */
+#define APSS_ST_ACTIVE 2   /* indexed and queried                                                    */
+
+typedef struct apss_handle apss_handle;
+
+typedef struct apss_config {
+  int32_t struct_size;         /* = sizeof(apss_config)                                              */
+  int32_t dim;                 /* cpslab.allpair.vectorDim            (EPA:25, WWA:31)               */
+  double similarity_threshold; /* cpslab.allpair.similarityThreshold  (IWA:23, EPA:24)               */
+  double index_threshold;      /* cpslab.allpair.indexThreshold       (WWA:35); must be >= 0         */
+  const double *max_weight;    /* dim entries, or NULL = 1.0 for every dim (the stub at EPA:51-57)   */
+  int32_t device;              /* CUDA device ordinal                                                */
+  int32_t semantics;           /* APSS_SEM_R1 / APSS_SEM_R0                                          */
+  int32_t tile_vectors;        /* candidates per index tile; 0 = default (3584)                      */
+  int32_t kernel_variant;      /* 0 = default scoring kernel; other values select experiments        */
+  int64_t reserve_vectors;     /* capacity hints; 0 = grow on demand                                 */
+  int64_t reserve_nnz;
+  int64_t reserve_pairs;
+} apss_config;
+
+typedef struct apss_batch_result {
+  int64_t id_base;           /* internal id of the batch's first vector (IWA:64-65 `currentIdx`)    */
+  int32_t n_vectors;         /* vectors in the call                                                  */
+  int32_t n_rejected;        /* EPA:81-93                                                            */
+  int32_t n_empty;           /* WWA:192-199                                                          */
+  int32_t n_active;
+  int64_t n_pairs;           /* pairs reported (after the R0 post-filter when semantics = R0)        */
+  int64_t n_pairs_r1;        /* pairs with dot >= t before the R0 post-filter                        */
+  int64_t n_prefilter;       /* fp32 guard-band survivors handed to the fp64 verify kernel           */
+  int64_t postings_visited;  /* sum over query terms of visible posting-list lengths (IWA:86)        */
+  int64_t candidates_unique; /* (q, c) with >= 1 shared dim, c.id != q.id: "candidate dot-products"  */
+  int64_t work_items;        /* (query, index tile) items the scoring kernel processed               */
+  double score_ms;           /* CUDA-event time of the scoring kernel(s), on the handle's stream     */
+  double device_ms;          /* CUDA-event time first kernel -> last kernel of the call              */
+} apss_batch_result;
+
+typedef struct apss_stats {
+  int64_t n_vectors;         /* vectors stored in this shard (all statuses)                          */
+  int64_t n_postings;        /* postings resident in HBM                                             */
+  int64_t n_tiles;
+  int64_t bytes_postings;    /* 8 B each                                                             */
+  int64_t bytes_directory;
+  int64_t bytes_forward;     /* fp64 forward store used by the verify kernel                         */
+  int64_t tot_postings_visited;
+  int64_t tot_candidates_unique;
+  int64_t tot_pairs;
+  int64_t tot_prefilter;
+  int64_t score_launches;    /* launches of the scoring kernel so far                                */
+  int64_t kernel_launches;   /* all kernels launched by this handle so far                           */
+  double tot_score_ms;
+  int32_t frozen;
+  int32_t tile_vectors;
+  int32_t warps_per_cta;
+  int32_t sm_count;
+} apss_stats;
+
+int32_t apss_abi_version(void);
+
+/* Construct one index worker on one GPU.  Replaces `new IndexingWorkerActor(conf)` (IWA:21-39,
+ * swap point EPA:116) plus the per-vector filters configured on WWA/EPA.  Fails with
+ * APSS_E_NO_DEVICE when CUDA is unusable. */
+int32_t apss_create(const apss_config *cfg, apss_handle **out);
+void apss_destroy(apss_handle *h);
+
+/* One IndexData message = one call.  Replaces, in order: the admission filter EPA:81-93 (on the
+ * un-pruned vector), the value prune WWA:185-202, buildInvertedIndex IWA:61-71 (skipped when
+ * frozen / APSS_BATCH_QUERY_ONLY), querySimilarItems IWA:74-111 with calculateSimilarity
+ * CU:98-117, and the threshold IWA:93.  Synchronous: results are ready on return.
+ *   indptr[n+1], indices[indptr[n]] strictly increasing per vector and < dim, values fp64:
+ *     the CSR form of Set[(String, SparkSparseVector)] (Message.scala:13); strings stay on the host.
+ *   ext_keys[n] or NULL: one integer per distinct caller id string; vectors with equal keys are
+ *     never paired (the string compare at IWA:91).  NULL = every vector distinct.
+ *   first_dim[n] or NULL: first(q) in Scala Set iteration order, only read when semantics = R0. */
+int32_t apss_insert_batch(apss_handle *h, int32_t n, const int64_t *indptr, const int32_t *indices,
+                          const double *values, const int64_t *ext_keys, const int32_t *first_dim,
+                          uint32_t flags, apss_batch_result *out);
+
+/* Copy the last batch's pairs out: q = index of the query within the batch, c = internal id of the
+ * similar vector, sim = fp64 dot product.  This is SimilarityOutput.output (Message.scala:20-21,
+ * sent at IWA:130) before the host maps ids back to strings.  Writes min(n_pairs, capacity). */
+int32_t apss_fetch_pairs(apss_handle *h, int32_t *q, int32_t *c, double *sim, int64_t capacity, int64_t *n_out);
+
+/* Device-resident view of the same arrays (valid until the next call on the handle). */
+int32_t apss_pairs_device(apss_handle *h, const int32_t **q, const int32_t **c, const double **sim, int64_t *n);
+
+/* Per-vector APSS_ST_* of the last batch (which queries get an output entry, IWA:106). */
+int32_t apss_fetch_status(apss_handle *h, uint8_t *status, int32_t capacity);
+
+/* ReceiveTimeout => stopUpdateIndex (IWA:143-144): every later batch is query-only. */
+int32_t apss_freeze(apss_handle *h);
+
+/* Internal id the next indexed vector will get (default: consecutive from 0).  Used by the shard
+ * dispatcher, which owns the global id space when the index is sharded by id range. */
+int32_t apss_set_next_id(apss_handle *h, int64_t next_id);
+
+int32_t apss_get_stats(apss_handle *h, apss_stats *out);
+const char *apss_last_error(apss_handle *h);
+
+/* The cudaStream_t all work of this handle is enqueued on (for CUDA-event timing by the caller). */
+void *apss_stream(apss_handle *h);
+
+/* Micro-benchmark of shared-memory accumulator update primitives (plain RMW, fixed-point atomics,
+ * float CAS atomics), used to choose the accumulator design; reports updates per second. */
+int32_t apss_microbench_accumulators(int32_t device, int32_t mode, int32_t warps, int32_t iters, double *updates_per_sec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APSS_H_ */

@@ -1,0 +1,246 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on identical
+inputs.  Bit-exact: pair sets, integer counters and fp64 similarities (same summation order)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.helpers import csr_from_dicts, csr_slice, assert_pairs_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def native():
+    import apss_b200
+    return apss_b200.native
+
+
+def gpu_pairs(idx, res):
+    q, c, s = idx.fetch_pairs()
+    return {(int(res.id_base + a), int(b)): float(x) for a, b, x in zip(q, c, s)}
+
+
+def run_both(batches, dim, t, idx_thr=0.0, sem="R1", keys=None, freeze_after=None, query_only=None, **kw):
+    n = native()
+    gsem = n.SEM_R0 if sem == "R0" else n.SEM_R1
+    o = orc.Oracle(dim, t, idx_thr, semantics=orc.R0 if sem == "R0" else orc.R1,
+                   algo=orc.ALGO_FAITHFUL if sem == "R0" else orc.ALGO_FAST, threads=8)
+    g = n.Index(dim, t, idx_thr, semantics=gsem, **kw)
+    out = []
+    for i, csr in enumerate(batches):
+        k = None if keys is None else keys[i]
+        qo = bool(query_only and query_only[i])
+        fd = orc.first_dims(*csr, index_threshold=idx_thr) if sem == "R0" else None
+        ro = o.insert_batch(*csr, keys=k, query_only=qo)
+        rg = g.insert_batch(*csr, ext_keys=k, first_dim=fd, query_only=qo)
+        out.append((ro, rg, gpu_pairs(g, rg), g.fetch_status(len(csr[0]) - 1)))
+        if freeze_after is not None and i == freeze_after:
+            o.freeze(); g.freeze()
+    return o, g, out
+
+
+A = {0: .6, 1: .8}
+B2 = {1: .8, 2: .6}
+
+
+def test_kat_a_b_c():
+    _, _, out = run_both([csr_from_dicts([A]), csr_from_dicts([dict(A)])], 64, 0.5)
+    ro, rg, gp, _ = out[1]
+    assert gp == ro.pair_set() == {(1, 0): .6 * .6 + .8 * .8}
+    assert rg.postings_visited == 4 and rg.candidates_unique == 1
+    _, _, out = run_both([csr_from_dicts([A]), csr_from_dicts([B2])], 64, 0.5, sem="R0")
+    assert out[1][2] == {} and out[1][1].n_pairs_r1 == 1
+    _, _, out = run_both([csr_from_dicts([B2]), csr_from_dicts([A])], 64, 0.5, sem="R0")
+    assert out[1][2] == {(1, 0): .8 * .8}
+    _, _, out = run_both([csr_from_dicts([A, B2])], 64, 0.5)
+    assert out[0][2] == {(0, 1): .8 * .8, (1, 0): .8 * .8} and out[0][1].candidates_unique == 2
+    _, _, out = run_both([csr_from_dicts([A, B2])], 64, 0.5, sem="R0")
+    assert out[0][2] == {(0, 1): .8 * .8}
+
+
+def test_kat_d_e_i_counters_and_filters():
+    a = {0: .5, 1: .5, 2: .5, 3: .5}
+    b = {0: .7, 1: .1, 2: .7, 3: .1}
+    _, _, out = run_both([csr_from_dicts([a]), csr_from_dicts([b])], 64, 0.9)
+    assert out[1][2] == {} and out[1][1].candidates_unique == 1 and out[1][1].postings_visited == 8
+    _, _, out = run_both([csr_from_dicts([{0: .1, 1: .9}]), csr_from_dicts([{1: .9, 5: .2}])], 64, 0.5, idx_thr=0.2)
+    assert out[1][2] == {(1, 0): .9 * .9} and out[1][1].postings_visited == 2
+    _, _, out = run_both([csr_from_dicts([{0: .5}]), csr_from_dicts([{0: 1.0}]), csr_from_dicts([{0: .95}])], 64, 0.9)
+    n = native()
+    assert list(out[0][3]) == [n.ST_REJECTED] and out[0][1].n_rejected == 1
+    assert out[2][2] == {(2, 1): .95}
+    _, _, out = run_both([csr_from_dicts([{0: .2, 1: .9}]), csr_from_dicts([{0: .15, 3: .9}])], 64, 0.1, idx_thr=0.9)
+    assert list(out[1][3]) == [n.ST_EMPTY] and out[1][2] == {}
+
+
+def test_kat_g_frozen_and_query_only():
+    _, g, out = run_both([csr_from_dicts([A]), csr_from_dicts([dict(A), dict(A)])], 64, 0.5, freeze_after=0)
+    assert set(out[1][2]) == {(1, 0), (2, 0)}
+    assert g.stats()["n_vectors"] == 1 and g.stats()["frozen"] == 1
+    _, g, out = run_both([csr_from_dicts([A]), csr_from_dicts([dict(A)]), csr_from_dicts([dict(A)])], 64, 0.5,
+                         query_only=[False, True, False])
+    assert set(out[1][2]) == {(1, 0)} and set(out[2][2]) == {(1, 0)}   # ids continue from the indexed ones
+
+
+def test_kat_h_same_external_id_never_paired():
+    keys = [np.array([42]), np.array([42]), np.array([43])]
+    _, _, out = run_both([csr_from_dicts([A]), csr_from_dicts([dict(A)]), csr_from_dicts([dict(A)])], 64, 0.5, keys=keys)
+    assert out[1][2] == {} and out[1][1].candidates_unique == 0
+    assert set(out[2][2]) == {(2, 0), (2, 1)} and out[2][1].candidates_unique == 2
+
+
+def test_validation_all_or_nothing():
+    n = native()
+    g = n.Index(16, 0.5)
+    g.insert_batch(*csr_from_dicts([{1: 1.0}]))
+    with pytest.raises(n.ApssError) as e:
+        g.insert_batch(np.array([0, 2]), np.array([3, 3]), np.array([.5, .5]))
+    assert e.value.code == -4
+    with pytest.raises(n.ApssError):
+        g.insert_batch(np.array([0, 1]), np.array([16]), np.array([1.0]))
+    assert g.stats()["n_vectors"] == 1
+    r = g.insert_batch(*csr_from_dicts([{1: 1.0}]))
+    assert r.id_base == 1 and gpu_pairs(g, r) == {(1, 0): 1.0}
+
+
+def test_empty_and_ragged_inputs():
+    n = native()
+    g = n.Index(128, 0.3)
+    r = g.insert_batch(np.array([0]), np.zeros(0, np.int32), np.zeros(0))
+    assert r.n_pairs == 0
+    # empty vectors in the middle of a batch; 1-component vectors; a vector spanning many dims
+    vecs = [{}, {5: 1.0}, {}, {i: 1.0 / np.sqrt(100) for i in range(100)}, {5: .7, 6: .7}]
+    csr = csr_from_dicts(vecs)
+    o = orc.Oracle(128, 0.3, algo=orc.ALGO_FAST)
+    ro = o.insert_batch(*csr)
+    rg = g.insert_batch(*csr)
+    assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+    assert rg.candidates_unique == ro.candidates_unique and rg.postings_visited == ro.postings_visited
+
+
+def _synth(N, D, nnz, seed, **kw):
+    import apss_b200
+    return apss_b200.synth.generate(N, D, nnz, seed=seed, **kw).numpy()
+
+
+@pytest.mark.parametrize("tile,batch", [(128, 100), (256, 333), (3584, 1000), (1024, 4096)])
+def test_synthetic_parity_small(tile, batch):
+    """Zipf data, several tile sizes / batch sizes (ragged last tile, tiles spanning batches)."""
+    N, D, t = 6000, 1 << 12, 0.6
+    data = _synth(N, D, 30, seed=11)
+    n = native()
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
+    g = n.Index(D, t, tile_vectors=tile)
+    for lo in range(0, N, batch):
+        hi = min(N, lo + batch)
+        csr = csr_slice(data, lo, hi)
+        ro = o.insert_batch(*csr)
+        rg = g.insert_batch(*csr)
+        assert rg.id_base == lo
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())          # bit-exact sims
+        assert rg.postings_visited == ro.postings_visited
+        assert rg.candidates_unique == ro.candidates_unique
+    assert g.stats()["tot_pairs"] == o.totals()["pairs"] > 0
+
+
+@pytest.mark.parametrize("warps,unroll", [(8, 4), (16, 2), (16, 8), (32, 4)])
+def test_kernel_variants_agree(warps, unroll):
+    N, D, t = 3000, 1 << 11, 0.5
+    data = _synth(N, D, 25, seed=5)
+    n = native()
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
+    g = n.Index(D, t, tile_vectors=1024, kernel_variant=(warps << 8) | unroll)
+    assert g.stats()["warps_per_cta"] == warps
+    for lo in range(0, N, 1000):
+        csr = csr_slice(data, lo, lo + 1000)
+        ro = o.insert_batch(*csr); rg = g.insert_batch(*csr)
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+        assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+
+
+def test_r0_parity_against_faithful_oracle():
+    """As-built semantics (first posting list skipped) through the R0 post-filter; vectors with >= 5
+    components exercise the Scala HashSet iteration order."""
+    N, D, t = 1500, 1 << 9, 0.4
+    data = _synth(N, D, 8, seed=3)
+    n = native()
+    o = orc.Oracle(D, t, semantics=orc.R0, algo=orc.ALGO_FAITHFUL, threads=8)
+    g = n.Index(D, t, semantics=n.SEM_R0, tile_vectors=256)
+    dropped = 0
+    for lo in range(0, N, 500):
+        csr = csr_slice(data, lo, lo + 500)
+        ro = o.insert_batch(*csr)
+        rg = g.insert_batch(*csr, first_dim=orc.first_dims(*csr))
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+        dropped += rg.n_pairs_r1 - rg.n_pairs
+    assert dropped > 0
+
+
+def test_index_threshold_and_unnormalised_values():
+    """Value prune changes what is scored (Q6); inputs need not be unit-norm (Q8)."""
+    N, D, t = 2000, 1 << 10, 0.3
+    ip, ix, v = _synth(N, D, 20, seed=9)
+    v = v * 1.7
+    n = native()
+    o = orc.Oracle(D, t, 0.12, algo=orc.ALGO_FAST, threads=8)
+    g = n.Index(D, t, 0.12, tile_vectors=512)
+    for lo in range(0, N, 700):
+        csr = csr_slice((ip, ix, v), lo, min(N, lo + 700))
+        ro = o.insert_batch(*csr); rg = g.insert_batch(*csr)
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+        assert list(g.fetch_status(len(csr[0]) - 1)) == list(ro.status)
+        assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+
+
+def test_pair_buffer_overflow_grows_and_replays():
+    """Threshold 0 makes every candidate a pair: far more than the initial pair buffer."""
+    N, D = 1500, 1 << 8
+    data = _synth(N, D, 10, seed=2, dup_frac=0.0)
+    n = native()
+    o = orc.Oracle(D, 0.0, algo=orc.ALGO_FAST, threads=8)
+    g = n.Index(D, 0.0, tile_vectors=256, reserve_pairs=1024)
+    ro = o.insert_batch(*data); rg = g.insert_batch(*data)
+    assert rg.n_pairs == len(ro.sim) == ro.candidates_unique > 1024
+    assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+
+
+def test_device_pointer_entry_matches_host_entry():
+    import torch
+    N, D, t = 3000, 1 << 11, 0.5
+    data = _synth(N, D, 25, seed=21)
+    n = native()
+    g1 = n.Index(D, t, tile_vectors=512); g2 = n.Index(D, t, tile_vectors=512)
+    for lo in range(0, N, 1000):
+        csr = csr_slice(data, lo, lo + 1000)
+        r1 = g1.insert_batch(*csr)
+        dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in csr]
+        torch.cuda.synchronize()
+        r2 = g2.insert_batch(dev[0], dev[1], dev[2])
+        assert gpu_pairs(g1, r1) == gpu_pairs(g2, r2)
+        assert (r1.postings_visited, r1.candidates_unique) == (r2.postings_visited, r2.candidates_unique)
+
+
+def test_c2_scale_sampled_parity():
+    """Config C2 shape (2^16 dims, nnz ~50, t=0.8) at 30K vectors: full parity + invariants."""
+    import apss_b200
+    N, D, t, B = 30000, 1 << 16, 0.8, 4096
+    data = apss_b200.synth.generate(N, D, 50, seed=20260102).numpy()
+    n = native()
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=orc.max_threads())
+    g = n.Index(D, t)
+    seen = {}
+    for lo in range(0, N, B):
+        hi = min(N, lo + B)
+        csr = csr_slice(data, lo, hi)
+        ro = o.insert_batch(*csr); rg = g.insert_batch(*csr)
+        gp = gpu_pairs(g, rg)
+        assert_pairs_equal(gp, ro.pair_set())
+        assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+        seen.update(gp)
+    # size-independent properties: symmetry inside the data set (every unordered pair reported once
+    # across batches or twice inside a batch, with identical similarity)
+    for (q, c), s in seen.items():
+        assert q != c and s >= t
+        if (c, q) in seen:
+            assert seen[(c, q)] == s and q // B == c // B
+        else:
+            assert q // B > c // B
