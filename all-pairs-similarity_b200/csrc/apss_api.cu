@@ -436,7 +436,7 @@ extern "C" int32_t apss_microbench_accumulators(int32_t device, int32_t mode, in
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return APSS_E_NO_DEVICE; }
   cudaSetDevice(device);
   cudaDeviceProp prop{}; cudaGetDeviceProperties(&prop, device);
-  const int CR = 2048;
+  const int CR = warps > 16 ? 1024 : 2048;
   const size_t smem = (size_t)warps * CR * 4;
   unsigned* sink = nullptr; cudaMalloc(&sink, 4);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -1,0 +1,186 @@
+"""Shard dispatcher: the index partitioned by vector-id range across the GPUs of one box.
+
+Replaces the reference's "remote router" (EntryProxyActor.scala:37-49,113-122 dimension sharding and
+the Akka cluster-sharding hop, CommonUtils.scala:28-46): instead of copying every vector to each
+shard that owns one of its dimensions, each rank (one process per GPU) owns whole vectors for a
+block-cyclic range of internal ids (block = one insert batch, owner = batch_no mod world).  Per batch:
+
+  1. rank 0 broadcasts the query batch (CSR) to all ranks          -- torch.distributed.broadcast
+  2. every rank scores the batch against its own shard; the owner also indexes it (it alone sees
+     the in-batch pairs, IWA:125-132)                              -- include/apss.h
+  3. per-shard pair lists are gathered back to rank 0              -- all_gather(counts) + gather
+
+Every pair is scored exactly once (a vector lives on exactly one shard).  The dispatcher owns the
+global id space (apss_set_next_id), so shards report global candidate ids.  Backend-agnostic: with
+NCCL the buffers are CUDA tensors handed to the C ABI as device pointers; with gloo (CPU tests of the
+host logic) they are host tensors.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class DispatchResult:
+    id_base: int
+    owner: int
+    n_pairs: int                 # whole job (valid on every rank)
+    postings_visited: int
+    candidates_unique: int
+    q: Optional[np.ndarray]      # rank 0 only: query index within the batch
+    c: Optional[np.ndarray]      #              global candidate id
+    sim: Optional[np.ndarray]
+    local: object                # this rank's native BatchResult
+
+
+class ShardDispatcher:
+    def __init__(self, engine, group=None, device=None):
+        """engine: this rank's index worker (native.Index on the rank's GPU)."""
+        self.engine = engine
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.backend = dist.get_backend(group) if dist.is_initialized() else "none"
+        self.device = torch.device(device) if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu"))
+        self.next_id = 0
+        self.batch_no = 0
+        self.frozen = False
+
+    # ---- helpers
+    def _bcast(self, t, src=0):
+        if self.world > 1:
+            dist.broadcast(t, src=src, group=self.group)
+        return t
+
+    def owner_of(self, batch_no):
+        return batch_no % self.world
+
+    def freeze(self):
+        self.frozen = True
+        self.engine.freeze()
+
+    def preload(self, indptr, indices, values):
+        """Index a batch every rank already holds (bulk load): only the owner touches its shard; no
+        scoring, no collectives.  Ids advance on every rank."""
+        n = int(indptr.numel() if hasattr(indptr, "numel") else len(indptr)) - 1
+        if self.owner_of(self.batch_no) == self.rank:
+            self.engine.set_next_id(self.next_id)
+            self.engine.insert_batch(indptr, indices, values, index_only=True)
+        self.next_id += n
+        self.batch_no += 1
+
+    def insert_batch(self, indptr=None, indices=None, values=None, query_only=False) -> DispatchResult:
+        """One insertNewVector batch.  Rank 0 passes the batch (torch tensors on self.device, or
+        anything torch.as_tensor accepts); other ranks pass nothing."""
+        dev = self.device
+        # 1. broadcast: sizes, then the three CSR arrays
+        hdr = torch.zeros(2, dtype=torch.int64, device=dev)
+        if self.rank == 0:
+            indptr = torch.as_tensor(indptr, dtype=torch.int64).to(dev)
+            indices = torch.as_tensor(indices, dtype=torch.int32).to(dev)
+            values = torch.as_tensor(values, dtype=torch.float64).to(dev)
+            hdr[0] = indptr.numel() - 1
+            hdr[1] = indices.numel()
+        self._bcast(hdr)
+        n, nnz = int(hdr[0]), int(hdr[1])
+        if self.rank != 0:
+            indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+            indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+            values = torch.empty(max(nnz, 1), dtype=torch.float64, device=dev)[:nnz]
+        self._bcast(indptr); self._bcast(indices); self._bcast(values)
+        if dev.type == "cuda":
+            torch.cuda.current_stream().synchronize()      # the engine runs on its own stream
+
+        # 2. local scoring; the owner indexes
+        query_only = query_only or self.frozen
+        owner = self.owner_of(self.batch_no)
+        mine = (owner == self.rank) and not query_only
+        id_base = self.next_id
+        if mine:
+            self.engine.set_next_id(id_base)
+        res = self.engine.insert_batch(indptr, indices, values, query_only=not mine)
+        if not query_only:
+            self.next_id += n
+            self.batch_no += 1
+
+        # 3. gather pair lists to rank 0
+        q, c, s = self._local_pairs(res.n_pairs)
+        tot = torch.tensor([res.n_pairs, res.postings_visited, res.candidates_unique], dtype=torch.int64, device=dev)
+        if self.world > 1:
+            counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
+            dist.all_gather(counts, tot[:1].clone(), group=self.group)
+            counts = [int(x) for x in counts]
+            dist.all_reduce(tot, group=self.group)
+            mx = max(counts)
+            if mx > 0:
+                def pad(t):
+                    out = torch.zeros(mx, dtype=t.dtype, device=dev)
+                    out[:t.numel()] = t
+                    return out
+                bufs = []
+                for t in (q, c, s):
+                    gl = [torch.empty(mx, dtype=t.dtype, device=dev) for _ in range(self.world)] if self.rank == 0 else None
+                    dist.gather(pad(t), gl, dst=0, group=self.group)
+                    bufs.append(gl)
+                if self.rank == 0:
+                    q = torch.cat([b[:k] for b, k in zip(bufs[0], counts)])
+                    c = torch.cat([b[:k] for b, k in zip(bufs[1], counts)])
+                    s = torch.cat([b[:k] for b, k in zip(bufs[2], counts)])
+        if self.rank == 0:
+            qn, cn, sn = q.cpu().numpy(), c.cpu().numpy(), s.cpu().numpy()
+        else:
+            qn = cn = sn = None
+        return DispatchResult(id_base, owner, int(tot[0]), int(tot[1]), int(tot[2]), qn, cn, sn, res)
+
+    def _local_pairs(self, n_pairs):
+        dev = self.device
+        if dev.type == "cuda" and hasattr(self.engine, "pairs_device"):
+            qp, cp, sp, m = self.engine.pairs_device()
+            q = torch.empty(m, dtype=torch.int32, device=dev)
+            c = torch.empty(m, dtype=torch.int32, device=dev)
+            s = torch.empty(m, dtype=torch.float64, device=dev)
+            if m:
+                _copy_from_ptr(q, qp); _copy_from_ptr(c, cp); _copy_from_ptr(s, sp)
+            return q, c, s
+        q, c, s = self.engine.fetch_pairs()
+        return (torch.from_numpy(np.ascontiguousarray(q)).to(dev), torch.from_numpy(np.ascontiguousarray(c)).to(dev),
+                torch.from_numpy(np.ascontiguousarray(s)).to(dev))
+
+
+def _copy_from_ptr(dst: torch.Tensor, src_ptr: int):
+    """device-to-device copy from a raw pointer owned by the C library into a torch tensor"""
+    import ctypes
+    rt = _cudart()
+    nbytes = dst.numel() * dst.element_size()
+    rc = rt.cudaMemcpy(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(src_ptr), ctypes.c_size_t(nbytes), 3)   # cudaMemcpyDeviceToDevice
+    if rc != 0:
+        raise RuntimeError("cudaMemcpy D2D failed: %d" % rc)
+
+
+_rt = None
+
+
+def _cudart():
+    global _rt
+    if _rt is None:
+        import ctypes
+        import glob
+        import os
+        cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*")) + \
+            glob.glob("/usr/local/cuda/lib64/libcudart.so*")
+        for cnd in cands + ["libcudart.so.12", "libcudart.so"]:
+            try:
+                _rt = ctypes.CDLL(cnd)
+                break
+            except OSError:
+                continue
+        if _rt is None:
+            raise RuntimeError("libcudart not found")
+        _rt.cudaMemcpy.restype = ctypes.c_int
+    return _rt
