@@ -318,6 +318,15 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     h->next_id += n;
   }
 
+  if ((flags & APSS_BATCH_INDEX_ONLY) && !query_only) {
+    CK(cudaEventRecord(h->ev_b1, s));
+    CK(cudaStreamSynchronize(s));
+    float ms0 = 0.f; CK(cudaEventElapsedTime(&ms0, h->ev_b0, h->ev_b1)); res.device_ms = ms0;
+    h->last_n = n; h->last_pairs = 0;
+    if (out) *out = res;
+    return APSS_OK;
+  }
+
   // ---- K2/K3: scoring + threshold/compaction, K4: fp64 verify.  Re-run on output overflow.
   const double t = h->cfg.similarity_threshold;
   float thr_emit;

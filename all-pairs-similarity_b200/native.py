@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libapss_b200.so")
 
 ABI_VERSION = 1
 SEM_R1, SEM_R0 = 0, 1
-BATCH_QUERY_ONLY, BATCH_DEVICE_PTRS, BATCH_SKIP_ADMIT = 1, 2, 4
+BATCH_QUERY_ONLY, BATCH_DEVICE_PTRS, BATCH_SKIP_ADMIT, BATCH_INDEX_ONLY = 1, 2, 4, 8
 ST_REJECTED, ST_EMPTY, ST_ACTIVE = 0, 1, 2
 
 _STATUS_NAMES = {0: "APSS_OK", -1: "APSS_E_INVALID", -2: "APSS_E_CUDA", -3: "APSS_E_NOMEM", -4: "APSS_E_INPUT",
@@ -165,7 +165,7 @@ class Index:
             raise ApssError(rc, self._L.apss_last_error(self._h).decode())
 
     def insert_batch(self, indptr, indices, values, ext_keys=None, first_dim=None, query_only=False, n=None,
-                     skip_admit=False) -> BatchResult:
+                     skip_admit=False, index_only=False) -> BatchResult:
         """Host arrays (numpy / pinned torch) or, when all of them are CUDA tensors, device pointers."""
         on_device = hasattr(indptr, "is_cuda") and indptr.is_cuda
         if isinstance(indptr, np.ndarray) or not hasattr(indptr, "data_ptr"):
@@ -178,7 +178,7 @@ class Index:
                 first_dim = np.ascontiguousarray(first_dim, dtype=np.int32)
         nvec = (len(indptr) - 1) if n is None else n
         flags = ((BATCH_QUERY_ONLY if query_only else 0) | (BATCH_DEVICE_PTRS if on_device else 0) |
-                 (BATCH_SKIP_ADMIT if skip_admit else 0))
+                 (BATCH_SKIP_ADMIT if skip_admit else 0) | (BATCH_INDEX_ONLY if index_only else 0))
         self._keep = (indptr, indices, values, ext_keys, first_dim)
         out = BatchResultC()
         self._check(self._L.apss_insert_batch(self._h, nvec, _ptr(indptr), _ptr(indices), _ptr(values), _ptr(ext_keys),

@@ -52,6 +52,8 @@ typedef enum apss_status {
 #define APSS_BATCH_DEVICE_PTRS 2u /* indptr/indices/values/ext_keys/first_dim are DEVICE pointers   */
 #define APSS_BATCH_SKIP_ADMIT 4u  /* vectors already passed EPA:81-93 upstream (IndexData carries   */
                                   /* admitted, pruned vectors): do not re-apply the admission filter */
+#define APSS_BATCH_INDEX_ONLY 8u  /* bulk load: IWA:61-71 only, no scoring (HBase LoadData-style     */
+                                  /* warm start; not a path the reference's IndexData offers)        */
 
 /* per-input-vector status (apss_fetch_status) */
 #define APSS_ST_REJECTED 0 /* failed the admission filter (EPA:81-93)                               */

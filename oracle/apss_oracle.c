@@ -45,6 +45,7 @@
 #define ORC_ALGO_FAITHFUL 0
 #define ORC_ALGO_FAST 1
 #define ORC_FLAG_QUERY_ONLY 1
+#define ORC_FLAG_INDEX_ONLY 2   /* bulk load (IWA:61-71 only); used to build the CPU baseline's index */
 
 #define ORC_ST_REJECTED 0   /* failed EPA:81-93 admission                         */
 #define ORC_ST_EMPTY    1   /* admitted, pruned to zero components (WWA:192-199)  */
@@ -382,6 +383,7 @@ int32_t oracle_insert_batch(oracle_t *o, int32_t n, const int64_t *indptr, const
     }
   }
   int query_only = (flags & ORC_FLAG_QUERY_ONLY) || o->frozen;
+  int index_only = (flags & ORC_FLAG_INDEX_ONLY) && !query_only;
   int64_t base = o->n_vecs;
   o->id_base = base;
   o->n_pairs = 0; o->postings_visited = 0; o->candidates_unique = 0; o->dot_calls_ref = 0;
@@ -438,7 +440,7 @@ int32_t oracle_insert_batch(oracle_t *o, int32_t n, const int64_t *indptr, const
     int dup_keys = 0;
     if (keys) { map64_t seen; map64_init(&seen, n); for (int32_t v = 0; v < n && !dup_keys; v++) { if (map64_find(&seen, keys[v]) >= 0) dup_keys = 1; map64_put(&seen, keys[v], 1); } map64_free(&seen); }
     if (dup_keys) nthreads = 1;
-    for (int32_t w = 0; w < nw; w++) {
+    for (int32_t w = 0; w < nw && !index_only; w++) {
       const oworker_t *wk = &o->workers[w];
       int32_t nq = wn[w];
       if (!nq) continue;
@@ -499,9 +501,9 @@ int32_t oracle_insert_batch(oracle_t *o, int32_t n, const int64_t *indptr, const
     int64_t postings = 0, cands = 0;
     int nthreads = o->threads;
 #ifdef _OPENMP
-#pragma omp parallel num_threads(nthreads) reduction(+:postings, cands)
+#pragma omp parallel num_threads(nthreads) reduction(+:postings, cands) if(!index_only)
 #endif
-    {
+    if (!index_only) {
       double *acc = (double*)calloc((size_t)(nvis ? nvis : 1), sizeof(double));
       uint8_t *touched = (uint8_t*)calloc((size_t)(nvis ? nvis : 1), 1);
       int32_t *tl = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nvis ? nvis : 1));
