@@ -45,7 +45,8 @@ struct apss_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 0;
-  int CR = 0, WARPS = 0, variant = 0;
+  int CR = 0, WARPS = 0, variant = 0, algo = 2, QB = 16;
+  double max_sq = 0.0;   // largest squared norm of any pruned vector seen (stored or query)
   size_t smem_bytes = 0;
   std::string err;
   bool frozen = false, custom_keys = false;
@@ -63,6 +64,8 @@ struct apss_handle {
   DevBuf<int32_t> q_cnt, q_ptr, q_dim; DevBuf<double> q_val; DevBuf<float> q_w; DevBuf<uint8_t> q_status;
   // build scratch
   DevBuf<unsigned long long> s_keys_in, s_keys_out, s_vals_in; DevBuf<int64_t> s_tile_start; DevBuf<char> cub_tmp;
+  // query-block transposition (v2 kernel)
+  DevBuf<unsigned long long> bt_keys_in, bt_keys_out, bt_vals_in, bt_vals_out, ud_key; DevBuf<int32_t> bt_flags, bt_pos, ud_dim, ud_start, bd_ptr;
   // outputs
   DevBuf<int32_t> pf_q, pf_c; DevBuf<float> pf_est;
   DevBuf<int32_t> out_q, out_c; DevBuf<double> out_sim;
@@ -105,11 +108,29 @@ static cudaError_t launch_score_t(apss_handle* h, const ScoreArgs& a, bool dup) 
 }
 
 static cudaError_t launch_score(apss_handle* h, const ScoreArgs& a, bool dup) {
-  const int unroll = (h->variant & 0xff);
+  const int unroll = (h->variant & 0xff) ? (h->variant & 0xff) : 8;
   switch (h->WARPS) {
     case 8: return unroll == 8 ? launch_score_t<8, 8>(h, a, dup) : launch_score_t<8, 4>(h, a, dup);
     case 16: return unroll == 8 ? launch_score_t<16, 8>(h, a, dup) : (unroll == 2 ? launch_score_t<16, 2>(h, a, dup) : launch_score_t<16, 4>(h, a, dup));
     case 32: return unroll == 8 ? launch_score_t<32, 8>(h, a, dup) : launch_score_t<32, 4>(h, a, dup);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int WARPS>
+static cudaError_t launch_blk_t(apss_handle* h, const ScoreArgs& a, const BlockArgs& b, bool dup) {
+  auto kern = dup ? k_score_blk<WARPS, true> : k_score_blk<WARPS, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  if (e != cudaSuccess) return e;
+  kern<<<h->sm_count, WARPS * 32, h->smem_bytes, h->stream>>>(a, b);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_blk(apss_handle* h, const ScoreArgs& a, const BlockArgs& b, bool dup) {
+  switch (h->WARPS) {
+    case 8: return launch_blk_t<8>(h, a, b, dup);
+    case 16: return launch_blk_t<16>(h, a, b, dup);
+    case 32: return launch_blk_t<32>(h, a, b, dup);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -130,14 +151,30 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return bail(APSS_E_NO_DEVICE);
   h->sm_count = prop.multiProcessorCount;
   const size_t max_smem = prop.sharedMemPerBlockOptin;
-  int CR = cfg->tile_vectors > 0 ? cfg->tile_vectors : 3584;
+  // kernel_variant: bits 0-7 unroll (row kernel), 8-15 warps per CTA, 16-23 algorithm (0/2 = query-block
+  // kernel with fixed-point atomics, 1 = warp-per-(query, tile) row kernel), 24-31 queries per block
+  const int algo = ((cfg->kernel_variant >> 16) & 0xff) == 2 ? 2 : 1;   // default: row kernel
+  int QB = (cfg->kernel_variant >> 24) & 0xff; if (QB <= 0) QB = 16;
+  if (QB > 32) QB = 32;   // a dimension's row list is staged one entry per lane
+  const size_t blk_extra = (size_t)LONG_CAP * 16 + (size_t)(LONG_CAP + 1) * 4 + 64;
+  int CR = cfg->tile_vectors;
+  if (CR <= 0) CR = algo == 1 ? 3584 : (int)(((max_smem - blk_extra) / ((size_t)QB * 4)) / 128 * 128);
   CR = (CR + 127) / 128 * 128;
-  // warps per CTA: as many accumulator rows as fit in shared memory, from {32, 16, 8}
   int warps = 0;
-  for (int w : {32, 16, 8}) if ((size_t)w * CR * sizeof(float) + 1024 <= max_smem) { warps = w; break; }
+  const int want = (cfg->kernel_variant >> 8) & 0xff;
+  if (algo == 1) {
+    // one accumulator row per warp: as many rows as fit in shared memory, from {32, 16, 8}
+    for (int w : {32, 16, 8}) if ((size_t)w * CR * sizeof(float) + 1024 <= max_smem) { warps = w; break; }
+    if ((want == 8 || want == 16 || want == 32) && (size_t)want * CR * sizeof(float) + 1024 <= max_smem) warps = want;
+    h->smem_bytes = (size_t)warps * CR * sizeof(float);
+  } else {
+    while (QB > 1 && (size_t)QB * CR * 4 + blk_extra > max_smem) QB >>= 1;   // explicit tile size: shrink the block
+    if ((size_t)QB * CR * 4 + blk_extra > max_smem) return bail(APSS_E_INVALID);
+    warps = (want == 8 || want == 16 || want == 32) ? want : 16;
+    h->smem_bytes = (size_t)QB * CR * 4 + blk_extra;
+  }
   if (!warps) return bail(APSS_E_INVALID);
-  if ((cfg->kernel_variant >> 8) & 0xff) { int w = (cfg->kernel_variant >> 8) & 0xff; if ((w == 8 || w == 16 || w == 32) && (size_t)w * CR * sizeof(float) + 1024 <= max_smem) warps = w; }
-  h->CR = CR; h->WARPS = warps; h->variant = cfg->kernel_variant; h->smem_bytes = (size_t)warps * CR * sizeof(float);
+  h->CR = CR; h->WARPS = warps; h->variant = cfg->kernel_variant; h->algo = algo; h->QB = QB;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(APSS_E_CUDA);
   if (cudaMalloc(&h->d_counters, C_COUNT * sizeof(unsigned long long)) != cudaSuccess) return bail(APSS_E_NOMEM);
   if (cudaMallocHost(&h->h_counters, C_COUNT * sizeof(unsigned long long)) != cudaSuccess) return bail(APSS_E_NOMEM);
@@ -176,6 +213,8 @@ extern "C" void apss_destroy(apss_handle* h) {
   h->post.release(); h->dir.release(); h->tile_base.release(); h->maxw.release();
   h->b_ptr.release(); h->b_idx.release(); h->b_val.release(); h->b_key.release(); h->b_first.release();
   h->q_cnt.release(); h->q_ptr.release(); h->q_dim.release(); h->q_val.release(); h->q_w.release(); h->q_status.release();
+  h->bt_keys_in.release(); h->bt_keys_out.release(); h->bt_vals_in.release(); h->bt_vals_out.release(); h->ud_key.release();
+  h->bt_flags.release(); h->bt_pos.release(); h->ud_dim.release(); h->ud_start.release(); h->bd_ptr.release();
   h->s_keys_in.release(); h->s_keys_out.release(); h->s_vals_in.release(); h->s_tile_start.release(); h->cub_tmp.release();
   h->pf_q.release(); h->pf_c.release(); h->pf_est.release(); h->out_q.release(); h->out_c.release(); h->out_sim.release();
   if (h->d_counters) cudaFree(h->d_counters);
@@ -304,6 +343,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   const int32_t batch_nnz = h->h_total[0];
   res.n_rejected = (int32_t)h->h_counters[C_NREJ]; res.n_empty = (int32_t)h->h_counters[C_NEMPTY]; res.n_active = (int32_t)h->h_counters[C_NACTIVE];
   h->max_nnz_seen = std::max(h->max_nnz_seen, (int)h->h_counters[C_MAXNNZ]);
+  { double sq; std::memcpy(&sq, &h->h_counters[C_MAXSQ], sizeof sq); if (sq > h->max_sq) h->max_sq = sq; }
   CK(h->q_dim.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_val.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_w.reserve(std::max(batch_nnz, 1), 0, s));
   k_prefilter_write<<<cdiv(n, 128), 128, 0, s>>>(n, d_ptr, d_idx, d_val, h->cfg.index_threshold, h->q_status.p, h->q_ptr.p, h->q_dim.p, h->q_val.p, h->q_w.p);
   CK(cudaGetLastError()); h->kernel_launches++;
@@ -337,6 +377,43 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   // when keys are supplied, q_key lives in b_key (host path) or the caller's buffer (device path)
   const int64_t* d_qkey = d_keys;
   if (h->custom_keys && !d_qkey) return h->fail(APSS_E_INVALID, "ext_keys were supplied for earlier batches: supply them for every batch");
+  // ---- query-block transposition for the block kernel: (block, dim)-sorted (row, scaled weight) lists
+  BlockArgs blk{};
+  int F = 0; unsigned thr_int = 0;
+  if (h->algo != 1 && batch_nnz) {
+    // fixed-point scale: every dot product is <= max squared norm (Cauchy-Schwarz); keep 2x headroom
+    const double bound = std::max(h->max_sq, 1e-300) * (1.0 + 1e-6);
+    F = (int)std::floor(std::log2(2147483648.0 / bound));
+    F = std::max(-100, std::min(100, F));
+    const double ts = t * std::ldexp(1.0, F) * (1.0 - std::ldexp(1.0, -20));
+    thr_int = ts <= 0 ? 0u : (ts >= 4294967295.0 ? 0xffffffffu : (unsigned)std::floor(ts));
+    const int QB = h->QB; const int nqb = (n + QB - 1) / QB;
+    int dimbits = 1; while ((1LL << dimbits) < (int64_t)D) ++dimbits;
+    int qbbits = 1; while ((1LL << qbbits) < nqb) ++qbbits;
+    CK(h->bt_keys_in.reserve(batch_nnz, 0, s)); CK(h->bt_keys_out.reserve(batch_nnz, 0, s)); CK(h->bt_vals_in.reserve(batch_nnz, 0, s));
+    CK(h->bt_vals_out.reserve(batch_nnz, 0, s)); CK(h->ud_key.reserve(batch_nnz + 1, 0, s));
+    CK(h->bt_flags.reserve(batch_nnz + 1, 0, s)); CK(h->bt_pos.reserve(batch_nnz + 1, 0, s));
+    CK(h->ud_dim.reserve(batch_nnz + 1, 0, s)); CK(h->ud_start.reserve(batch_nnz + 2, 0, s)); CK(h->bd_ptr.reserve(nqb + 1, 0, s));
+    k_bt_emit<<<cdiv(batch_nnz, 256), 256, 0, s>>>(n, batch_nnz, h->q_ptr.p, h->q_dim.p, h->q_w.p, QB, h->CR, dimbits, (float)std::ldexp(1.0, F),
+                                                   h->bt_keys_in.p, h->bt_vals_in.p);
+    CK(cudaGetLastError());
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits + qbbits, s));
+    CK(h->cub_tmp.reserve(tb, 0, s));
+    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits + qbbits, s));
+    k_bt_heads<<<cdiv(batch_nnz + 1, 256), 256, 0, s>>>(batch_nnz, h->bt_keys_out.p, h->bt_flags.p);
+    CK(cudaGetLastError());
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, h->bt_flags.p, h->bt_pos.p, batch_nnz + 1, s));
+    CK(h->cub_tmp.reserve(tb, 0, s));
+    CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tb, h->bt_flags.p, h->bt_pos.p, batch_nnz + 1, s));
+    k_bt_scatter<<<cdiv(batch_nnz + 1, 256), 256, 0, s>>>(batch_nnz, h->bt_keys_out.p, h->bt_flags.p, h->bt_pos.p, dimbits, h->ud_key.p, h->ud_dim.p, h->ud_start.p);
+    CK(cudaGetLastError());
+    k_bt_blocks<<<cdiv(nqb + 1, 128), 128, 0, s>>>(nqb, h->bt_pos.p, batch_nnz, h->ud_key.p, dimbits, h->bd_ptr.p);
+    CK(cudaGetLastError());
+    h->kernel_launches += 9;
+    blk.ud_dim = h->ud_dim.p; blk.ud_start = h->ud_start.p; blk.bd_ptr = h->bd_ptr.p;
+    blk.bt = reinterpret_cast<const uint2*>(h->bt_vals_out.p); blk.QB = QB; blk.n_qblocks = nqb;
+  }
   for (int attempt = 0; attempt < 3; ++attempt) {
     ScoreArgs a{};
     a.q_ptr = h->q_ptr.p; a.q_dim = h->q_dim.p; a.q_w = h->q_w.p; a.q_key = d_qkey;
@@ -348,7 +425,13 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     a.total_items = (unsigned long long)h->ntiles * (unsigned long long)n;
     CK(cudaMemsetAsync(h->d_counters, 0, 7 * sizeof(unsigned long long), s));   // keep the prefilter tallies
     CK(cudaEventRecord(h->ev_s0, s));
-    if (a.total_items && batch_nnz) { CK(launch_score(h, a, h->custom_keys)); h->score_launches++; h->kernel_launches++; }
+    if (h->algo == 1) {
+      if (a.total_items && batch_nnz) { CK(launch_score(h, a, h->custom_keys)); h->score_launches++; h->kernel_launches++; }
+    } else if (h->ntiles && batch_nnz) {
+      blk.thr_int = thr_int; blk.inv_scale = (float)std::ldexp(1.0, -F);
+      a.total_items = (unsigned long long)h->ntiles * (unsigned long long)blk.n_qblocks;
+      CK(launch_blk(h, a, blk, h->custom_keys)); h->score_launches++; h->kernel_launches++;
+    }
     CK(cudaEventRecord(h->ev_s1, s));
     CK(h->out_q.reserve(h->pf_q.cap, 0, s)); CK(h->out_c.reserve(h->pf_q.cap, 0, s)); CK(h->out_sim.reserve(h->pf_q.cap, 0, s));
     if (h->n_local) {
@@ -373,7 +456,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   res.candidates_unique = (int64_t)h->h_counters[C_CANDS];
   res.n_pairs = (int64_t)h->h_counters[C_FINAL];
   res.n_pairs_r1 = (int64_t)h->h_counters[C_R1];
-  res.work_items = (int64_t)((unsigned long long)h->ntiles * (unsigned long long)n);
+  res.work_items = (int64_t)((unsigned long long)h->ntiles * (unsigned long long)(h->algo == 1 ? n : (n + h->QB - 1) / h->QB));
   h->last_n = n; h->last_pairs = res.n_pairs;
   h->tot_postings += res.postings_visited; h->tot_cands += res.candidates_unique; h->tot_pairs += res.n_pairs; h->tot_pf += res.n_prefilter;
   h->tot_score_ms += res.score_ms;

@@ -30,6 +30,7 @@ enum Counter : int {
   C_ERR = 5,       // validation error code (0 = ok)
   C_WORK = 6,      // persistent-kernel work cursor
   C_NREJ = 7, C_NEMPTY = 8, C_NACTIVE = 9, C_MAXNNZ = 10,
+  C_MAXSQ = 11,    // max squared L2 norm of a pruned vector (bits of a non-negative double)
   C_COUNT = 16
 };
 
@@ -57,20 +58,23 @@ __global__ void k_prefilter_count(int n, const int64_t* __restrict__ ptr, const 
   if (v == n) { cnt[n] = 0; return; }
   int64_t a = ptr[v], b = ptr[v + 1];
   if (b < a || (v == 0 && a != 0)) { atomicMax(&counters[C_ERR], 2ULL); cnt[v] = 0; status[v] = 0; return; }
-  double s = 0.0; int kept = 0; int prev = -1; bool bad = false;
+  double s = 0.0, sq = 0.0; int kept = 0; int prev = -1; bool bad = false;
   for (int64_t p = a; p < b; ++p) {
     int d = idx[p]; double x = val[p];
     if (d <= prev || d >= D) { bad = true; break; }
     prev = d;
     double mw = maxw ? maxw[d] : 1.0;
     s = __dadd_rn(s, __dmul_rn(mw, x));
-    kept += (x > idx_thr);
+    if (x > idx_thr) { ++kept; sq = fma(x, x, sq); }
   }
   if (bad) { atomicMax(&counters[C_ERR], 3ULL); cnt[v] = 0; status[v] = 0; return; }
   uint8_t st;
   if (!(s >= sim_thr)) { st = 0; kept = 0; atomicAdd(&counters[C_NREJ], 1ULL); }
   else if (kept == 0) { st = 1; atomicAdd(&counters[C_NEMPTY], 1ULL); }
-  else { st = 2; atomicAdd(&counters[C_NACTIVE], 1ULL); atomicMax(&counters[C_MAXNNZ], (unsigned long long)kept); }
+  else {
+    st = 2; atomicAdd(&counters[C_NACTIVE], 1ULL); atomicMax(&counters[C_MAXNNZ], (unsigned long long)kept);
+    atomicMax(&counters[C_MAXSQ], (unsigned long long)__double_as_longlong(sq));
+  }
   status[v] = st; cnt[v] = kept;
 }
 
@@ -263,6 +267,237 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score(const ScoreArgs a) {
       __syncwarp();
     }
     item = __shfl_sync(FULL, next, 0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_post += __shfl_down_sync(FULL, n_post, o);
+    n_cand += __shfl_down_sync(FULL, n_cand, o);
+  }
+  if (lane == 0) { atomicAdd(&a.counters[C_POSTINGS], n_post); atomicAdd(&a.counters[C_CANDS], n_cand); }
+}
+
+// ------------------------------------------------------------------ K2b: query-block scoring (fixed-point atomics)
+
+// Per-batch transposition of the query batch into blocks of QB consecutive queries: for every block
+// the distinct dimensions it uses and, per dimension, the (row, weight) list of the queries having it.
+struct BlockArgs {
+  const int32_t* ud_dim;    // distinct (block, dim) entries, block-major, dim ascending
+  const int32_t* ud_start;  // [n_ud + 1] offsets into bt
+  const int32_t* bd_ptr;    // [n_qblocks + 1] ranges of a block in ud_*
+  const uint2* bt;          // (row * CR, weight * 2^F as fp32 bits), grouped by (block, dim)
+  int32_t QB, n_qblocks;
+  unsigned thr_int;         // emit iff acc >= thr_int  (t * 2^F with guard band, rounded down)
+  float inv_scale;          // 2^-F
+};
+
+__global__ void k_bt_emit(int nq, int nnz, const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim,
+                          const float* __restrict__ q_w, int QB, int CR, int dimbits, float scale,
+                          unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nnz) return;
+  int lo = 0, hi = nq;                      // largest q with q_ptr[q] <= t
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (q_ptr[mid] <= t) lo = mid; else hi = mid; }
+  const int q = lo;
+  keys[t] = ((unsigned long long)(q / QB) << dimbits) | (unsigned)q_dim[t];
+  vals[t] = ((unsigned long long)__float_as_uint(q_w[t] * scale) << 32) | (unsigned)((q % QB) * CR);
+}
+
+__global__ void k_bt_heads(int nnz, const unsigned long long* __restrict__ keys, int32_t* __restrict__ flags) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > nnz) return;
+  flags[t] = (t < nnz) && (t == 0 || keys[t] != keys[t - 1]);
+}
+
+__global__ void k_bt_scatter(int nnz, const unsigned long long* __restrict__ keys, const int32_t* __restrict__ flags,
+                             const int32_t* __restrict__ pos, int dimbits, unsigned long long* __restrict__ ud_key,
+                             int32_t* __restrict__ ud_dim, int32_t* __restrict__ ud_start) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > nnz) return;
+  if (t == nnz) { ud_start[pos[nnz]] = nnz; return; }     // pos[nnz] = number of distinct entries
+  if (flags[t]) { const int j = pos[t]; ud_key[j] = keys[t]; ud_dim[j] = (int32_t)(keys[t] & ((1ULL << dimbits) - 1)); ud_start[j] = t; }
+}
+
+__global__ void k_bt_blocks(int n_qblocks, const int32_t* __restrict__ pos, int nnz, const unsigned long long* __restrict__ ud_key,
+                            int dimbits, int32_t* __restrict__ bd_ptr) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_qblocks) return;
+  bd_ptr[b] = (int32_t)lower_bound_u64(ud_key, pos[nnz], (unsigned long long)b << dimbits);
+}
+
+static constexpr int LONG_CAP = 512;     // posting segments longer than one warp chunk, per work item
+
+// Persistent kernel, one CTA per SM.  A work item is (index tile, block of QB queries); the CTA holds
+// QB x CR u32 fixed-point accumulators in shared memory.  Every posting of the tile that belongs to a
+// dimension used by the block is loaded ONCE (coalesced 8 B loads) and applied to every query row that
+// has the dimension: acc[row][id] += ceil(wq * 2^F * wc + 0.5) with a native shared-memory atomic
+// (ATOMS.ADD, ~2x the rate of an LDS/FFMA/STS round trip, order-independent => bit-reproducible).
+// Every contribution is >= 1, so "touched" (a candidate, IWA:86-92) is exactly acc != 0.
+//   phase 1  warps look up 32 directory entries at a time; segments of <= 32 postings are applied
+//            at once, longer ones are queued in shared memory
+//   phase 2  the queued segments are cut into 32-posting chunks, dealt round-robin to the warps
+//   phase 3  scan: count candidates, emit acc >= thr_int by warp-aggregated compaction, clear
+template <int WARPS, bool DUPKEYS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_score_blk(const ScoreArgs a, const BlockArgs b) {
+  extern __shared__ __align__(16) unsigned smem_u[];
+  const int QB = b.QB, CR = a.CR;
+  unsigned* acc = smem_u;
+  int4* longlist = reinterpret_cast<int4*>(acc + (size_t)QB * CR);
+  int* lprefix = reinterpret_cast<int*>(longlist + LONG_CAP);     // [LONG_CAP + 1] chunk prefix
+  __shared__ unsigned long long s_item;
+  __shared__ int s_nlong;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  constexpr int NT = WARPS * 32;
+  const int nacc = QB * CR;
+  for (int i = tid * 4; i < nacc; i += NT * 4) *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
+  unsigned long long n_post = 0, n_cand = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) { s_item = atomicAdd(&a.counters[C_WORK], 1ULL); s_nlong = 0; }
+    __syncthreads();
+    const unsigned long long item = s_item;
+    if (item >= a.total_items) break;
+    const int tile = (int)(item / (unsigned)b.n_qblocks);
+    const int qb = (int)(item - (unsigned long long)tile * (unsigned)b.n_qblocks);
+    const int32_t* __restrict__ dirt = a.dir + (size_t)tile * ((size_t)a.D + 1);
+    const uint2* __restrict__ pt = a.post + __ldg(a.tile_base + tile);
+    const int u0 = __ldg(b.bd_ptr + qb), u1 = __ldg(b.bd_ptr + qb + 1);
+
+    // ---- phase 1
+    for (int ub = u0 + warp * 32; ub < u1; ub += NT) {
+      const int u = ub + lane;
+      int s = 0, e = 0, rs = 0, re = 0;
+      if (u < u1) {
+        const int d = __ldg(b.ud_dim + u);
+        rs = __ldg(b.ud_start + u); re = __ldg(b.ud_start + u + 1);
+        s = __ldg(dirt + d); e = __ldg(dirt + d + 1);
+      }
+      const int len = e - s;
+      n_post += (unsigned long long)(unsigned)len * (unsigned)(re - rs);
+      bool queued = false;
+      if (len > 32) {
+        const int slot = atomicAdd(&s_nlong, 1);
+        if (slot < LONG_CAP) { longlist[slot] = make_int4(s, e, rs, re); queued = true; }
+      }
+      unsigned m = __ballot_sync(FULL, len > 0 && !queued);
+      while (m) {
+        const int j = __ffs(m) - 1; m &= m - 1;
+        const int sj = __shfl_sync(FULL, s, j), ej = __shfl_sync(FULL, e, j);
+        const int rsj = __shfl_sync(FULL, rs, j), nr = __shfl_sync(FULL, re, j) - rsj;    // nr <= QB <= 32 rows
+        uint2 rw = make_uint2(0, 0);
+        if (lane < nr) rw = __ldg(b.bt + rsj + lane);        // the dimension's (row, weight) list, one per lane
+        for (int p0 = sj; p0 < ej; p0 += 32) {               // <= 32 postings unless the queue overflowed
+          const int p = p0 + lane;
+          uint2 pp = make_uint2(0, 0);
+          if (p < ej) pp = ld_stream(pt + p);
+          const float wc = __uint_as_float(pp.y);
+          for (int r = 0; r < nr; ++r) {
+            const unsigned ro = __shfl_sync(FULL, rw.x, r);
+            const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
+            if (p < ej) atomicAdd(acc + ro + pp.x, __float2uint_ru(fmaf(ws, wc, 0.5f)));
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- chunk prefix of the queued segments (warp 0)
+    const int nlong = min(s_nlong, LONG_CAP);
+    if (warp == 0) {
+      int run = 0;
+      for (int k0 = 0; k0 < nlong; k0 += 32) {
+        const int k = k0 + lane;
+        int nc = 0;
+        if (k < nlong) { const int4 L = longlist[k]; nc = (L.y - L.x + 31) >> 5; }
+        int incl = nc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+        if (k < nlong) lprefix[k] = run + incl - nc;
+        run += __shfl_sync(FULL, incl, 31);
+      }
+      if (lane == 0) lprefix[nlong] = run;
+    }
+    __syncthreads();
+    // ---- phase 2: 32-posting chunks, round-robin over the warps, next chunk's loads in flight
+    {
+      const int nchunks = lprefix[nlong];
+      int k = 0;
+      int ch = warp;
+      uint2 pp_n = make_uint2(0, 0), rw_n = make_uint2(0, 0); int nr_n = 0; bool ok_n = false;
+      if (ch < nchunks) {
+        while (lprefix[k + 1] <= ch) ++k;
+        const int4 L = longlist[k];
+        const int p = L.x + ((ch - lprefix[k]) << 5) + lane;
+        nr_n = L.w - L.z; ok_n = p < L.y;
+        if (ok_n) pp_n = ld_stream(pt + p);
+        if (lane < nr_n) rw_n = __ldg(b.bt + L.z + lane);
+      }
+      while (ch < nchunks) {
+        const uint2 pp = pp_n, rw = rw_n; const int nr = nr_n; const bool ok = ok_n;
+        ch += WARPS;
+        if (ch < nchunks) {
+          while (lprefix[k + 1] <= ch) ++k;
+          const int4 L = longlist[k];
+          const int p = L.x + ((ch - lprefix[k]) << 5) + lane;
+          nr_n = L.w - L.z; ok_n = p < L.y;
+          if (ok_n) pp_n = ld_stream(pt + p);
+          if (lane < nr_n) rw_n = __ldg(b.bt + L.z + lane);
+        }
+        const float wc = __uint_as_float(pp.y);
+        unsigned* col = acc + pp.x;
+#pragma unroll 4
+        for (int r = 0; r < nr; ++r) {
+          const unsigned ro = __shfl_sync(FULL, rw.x, r);
+          const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
+          if (ok) atomicAdd(col + ro, __float2uint_ru(fmaf(ws, wc, 0.5f)));
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 3: epilogue
+    {
+      const long long c0 = (long long)tile * CR;
+      const int q0 = qb * QB;
+      const long long self0 = (a.q_local_base >= 0) ? (a.q_local_base + q0 - c0) : (long long)-(1LL << 40);   // self column of row 0
+      for (int i = tid * 4; i < nacc; i += NT * 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(acc + i);
+        const unsigned any = v.x | v.y | v.z | v.w;
+        const unsigned wany = __ballot_sync(FULL, any != 0);
+        if (!wany) continue;
+        if (any) *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
+        const int row = i / CR, col = i - row * CR;
+        const int q = q0 + row;
+        const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+        unsigned tm = 0, pm = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { tm |= (unsigned)(vv[k] != 0) << k; pm |= (unsigned)(vv[k] != 0 && vv[k] >= b.thr_int) << k; }
+        const long long selfc = self0 + row;
+        if (selfc >= col && selfc < col + 4) { const unsigned bit = 1u << (int)(selfc - col); tm &= ~bit; pm &= ~bit; }
+        if (DUPKEYS && tm) {
+          const long long qkey = __ldg(a.q_key + q);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if ((tm >> k) & 1u) { if (__ldg(a.c_key + c0 + col + k) == qkey) { tm &= ~(1u << k); pm &= ~(1u << k); } }
+        }
+        n_cand += __popc(tm);
+        if (__ballot_sync(FULL, pm != 0)) {
+          const int cnt = __popc(pm);
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+          const int tot = __shfl_sync(FULL, incl, 31);
+          unsigned long long base = 0;
+          if (lane == 31) base = atomicAdd(&a.counters[C_PF], (unsigned long long)tot);
+          base = __shfl_sync(FULL, base, 31);
+          unsigned long long slot = base + (unsigned)(incl - cnt);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if ((pm >> k) & 1u) {
+              if (slot < a.out_cap) { a.out_q[slot] = q; a.out_c[slot] = (int32_t)(c0 + col + k); a.out_est[slot] = (float)vv[k] * b.inv_scale; }
+              ++slot;
+            }
+        }
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

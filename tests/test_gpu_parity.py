@@ -122,14 +122,15 @@ def _synth(N, D, nnz, seed, **kw):
     return apss_b200.synth.generate(N, D, nnz, seed=seed, **kw).numpy()
 
 
-@pytest.mark.parametrize("tile,batch", [(128, 100), (256, 333), (3584, 1000), (1024, 4096)])
-def test_synthetic_parity_small(tile, batch):
+@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("tile,batch", [(128, 100), (256, 333), (3584, 1000), (1024, 4096), (0, 2500)])
+def test_synthetic_parity_small(tile, batch, algo):
     """Zipf data, several tile sizes / batch sizes (ragged last tile, tiles spanning batches)."""
     N, D, t = 6000, 1 << 12, 0.6
     data = _synth(N, D, 30, seed=11)
     n = native()
     o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
-    g = n.Index(D, t, tile_vectors=tile)
+    g = n.Index(D, t, tile_vectors=tile, kernel_variant=algo << 16)
     for lo in range(0, N, batch):
         hi = min(N, lo + batch)
         csr = csr_slice(data, lo, hi)
@@ -142,13 +143,19 @@ def test_synthetic_parity_small(tile, batch):
     assert g.stats()["tot_pairs"] == o.totals()["pairs"] > 0
 
 
-@pytest.mark.parametrize("warps,unroll", [(8, 4), (16, 2), (16, 8), (32, 4)])
-def test_kernel_variants_agree(warps, unroll):
+def variant(algo=0, warps=0, unroll=0, qb=0):
+    return (qb << 24) | (algo << 16) | (warps << 8) | unroll
+
+
+@pytest.mark.parametrize("algo,warps,unroll,qb", [(1, 8, 4, 0), (1, 16, 2, 0), (1, 16, 8, 0), (1, 32, 4, 0),
+                                                  (2, 16, 0, 16), (2, 8, 0, 4), (2, 32, 0, 32), (2, 16, 0, 1), (2, 16, 0, 7)])
+def test_kernel_variants_agree(algo, warps, unroll, qb):
+    """row kernel (fp32 plain RMW) and query-block kernel (fixed-point atomics) give identical results"""
     N, D, t = 3000, 1 << 11, 0.5
     data = _synth(N, D, 25, seed=5)
     n = native()
     o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
-    g = n.Index(D, t, tile_vectors=1024, kernel_variant=(warps << 8) | unroll)
+    g = n.Index(D, t, tile_vectors=1024, kernel_variant=variant(algo, warps, unroll, qb))
     assert g.stats()["warps_per_cta"] == warps
     for lo in range(0, N, 1000):
         csr = csr_slice(data, lo, lo + 1000)
