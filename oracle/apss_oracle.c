@@ -46,6 +46,7 @@
 #define ORC_ALGO_FAST 1
 #define ORC_FLAG_QUERY_ONLY 1
 #define ORC_FLAG_INDEX_ONLY 2   /* bulk load (IWA:61-71 only); used to build the CPU baseline's index */
+#define ORC_FLAG_SKIP_ADMIT 4   /* IndexData carries vectors that already passed EPA:81-93 upstream     */
 
 #define ORC_ST_REJECTED 0   /* failed EPA:81-93 admission                         */
 #define ORC_ST_EMPTY    1   /* admitted, pruned to zero components (WWA:192-199)  */
@@ -396,7 +397,7 @@ int32_t oracle_insert_batch(oracle_t *o, int32_t n, const int64_t *indptr, const
     int32_t nn = (int32_t)(indptr[v + 1] - indptr[v]);
     ovec_t *ov = &o->vecs[base + v];
     ov->key = keys ? keys[v] : base + v;
-    if (!admit_vector(o, idx, val, nn)) { o->status[v] = ORC_ST_REJECTED; ov->nnz = 0; ov->idx = NULL; ov->val = NULL; continue; }
+    if (!(flags & ORC_FLAG_SKIP_ADMIT) && !admit_vector(o, idx, val, nn)) { o->status[v] = ORC_ST_REJECTED; ov->nnz = 0; ov->idx = NULL; ov->val = NULL; continue; }
     prune_vector(o, idx, val, nn, ov);
     o->status[v] = ov->nnz ? ORC_ST_ACTIVE : ORC_ST_EMPTY;
   }

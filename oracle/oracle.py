@@ -20,6 +20,7 @@ R1, R0 = 0, 1
 ALGO_FAITHFUL, ALGO_FAST = 0, 1
 FLAG_QUERY_ONLY = 1
 FLAG_INDEX_ONLY = 2
+FLAG_SKIP_ADMIT = 4
 ST_REJECTED, ST_EMPTY, ST_ACTIVE = 0, 1, 2
 SET_ORDER_SCALA, SET_ORDER_ASCENDING = 0, 1
 
@@ -125,14 +126,15 @@ class Oracle:
     def n_vectors(self):
         return int(self._L.oracle_n_vectors(self._h))
 
-    def insert_batch(self, indptr, indices, values, keys=None, query_only=False, index_only=False) -> BatchResult:
+    def insert_batch(self, indptr, indices, values, keys=None, query_only=False, index_only=False, skip_admit=False) -> BatchResult:
         indptr = np.ascontiguousarray(indptr, dtype=np.int64)
         indices = np.ascontiguousarray(indices, dtype=np.int32)
         values = np.ascontiguousarray(values, dtype=np.float64)
         n = len(indptr) - 1
         k = None if keys is None else np.ascontiguousarray(keys, dtype=np.int64)
         rc = self._L.oracle_insert_batch(self._h, n, _p(indptr), _p(indices), _p(values), _p(k),
-                                         (FLAG_QUERY_ONLY if query_only else 0) | (FLAG_INDEX_ONLY if index_only else 0))
+                                         (FLAG_QUERY_ONLY if query_only else 0) | (FLAG_INDEX_ONLY if index_only else 0) |
+                                         (FLAG_SKIP_ADMIT if skip_admit else 0))
         if rc != 0:
             raise ValueError("oracle: %s (rc=%d)" % (self._L.oracle_last_error(self._h).decode(), rc))
         m = int(self._L.oracle_n_pairs(self._h))

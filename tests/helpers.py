@@ -41,3 +41,54 @@ def assert_pairs_equal(got, want, rel=0.0):
             assert got[k] == want[k], (k, got[k], want[k])
         else:
             assert abs(got[k] - want[k]) <= rel * abs(want[k]), (k, got[k], want[k])
+
+
+class OracleEngine:
+    """Test double with the interface of apss_b200.native.Index, backed by the CPU oracle.  Lives in
+    tests/ on purpose: the product never routes through the oracle; this only lets the host-side logic
+    (message mirror, shard dispatcher) be exercised on a box without a GPU."""
+
+    def __init__(self, dim, similarity_threshold, index_threshold=0.0, as_built=False):
+        from oracle import oracle as orc
+        self._orc = orc
+        self.o = orc.Oracle(dim, similarity_threshold, index_threshold, semantics=orc.R0 if as_built else orc.R1,
+                            algo=orc.ALGO_FAITHFUL if as_built else orc.ALGO_FAST, threads=2)
+        self.gid = []              # oracle ordinal -> global id
+        self.next_id = 0
+        self.last = None
+
+    def set_next_id(self, next_id):
+        self.next_id = int(next_id)
+
+    def freeze(self):
+        self.o.freeze()
+
+    def insert_batch(self, indptr, indices, values, ext_keys=None, first_dim=None, query_only=False, skip_admit=False,
+                     index_only=False, n=None):
+        import types
+        a = [x.numpy() if hasattr(x, "numpy") else np.asarray(x) for x in (indptr, indices, values)]
+        nvec = len(a[0]) - 1
+        keys = ext_keys
+        if keys is None:           # default key = global id
+            keys = np.arange(self.next_id, self.next_id + nvec, dtype=np.int64)
+        r = self.o.insert_batch(a[0], a[1], a[2], keys=keys, query_only=query_only, index_only=index_only, skip_admit=skip_admit)
+        id_base = self.next_id
+        if not query_only:
+            self.gid.extend(range(self.next_id, self.next_id + nvec))
+            self.next_id += nvec
+        self.last = r
+        return types.SimpleNamespace(id_base=id_base, n_vectors=nvec, n_pairs=len(r.sim), n_pairs_r1=len(r.sim), n_prefilter=len(r.sim),
+                                     postings_visited=r.postings_visited, candidates_unique=max(r.candidates_unique, 0),
+                                     work_items=0, score_ms=0.0, device_ms=0.0,
+                                     n_rejected=int((r.status == 0).sum()), n_empty=int((r.status == 1).sum()), n_active=int((r.status == 2).sum()))
+
+    def fetch_pairs(self):
+        r = self.last
+        c = np.array([self.gid[int(x)] for x in r.c], np.int32)
+        return r.q.astype(np.int32), c, r.sim.copy()
+
+    def fetch_status(self, n):
+        return self.last.status[:n]
+
+    def stats(self):
+        return {"n_vectors": self.o.n_vectors}
