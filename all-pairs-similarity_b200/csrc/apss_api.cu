@@ -52,6 +52,7 @@ struct apss_handle {
   bool frozen = false, custom_keys = false;
   int64_t next_id = 0;
   int max_nnz_seen = 0;
+  int64_t phase_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // last batch, dense kernel: setup, phase 1, Wq, dense, tasks, epilogue
 
   // shard
   int64_t n_local = 0, nnz = 0, n_post = 0;
@@ -64,6 +65,9 @@ struct apss_handle {
   DevBuf<int32_t> q_cnt, q_ptr, q_dim; DevBuf<double> q_val; DevBuf<float> q_w; DevBuf<uint8_t> q_status;
   // build scratch
   DevBuf<unsigned long long> s_keys_in, s_keys_out, s_vals_in; DevBuf<int64_t> s_tile_start; DevBuf<char> cub_tmp;
+  // dense-head tiles (algo 3)
+  DevBuf<int32_t> dn_cnt, dn_dim, dn_len, tile_cnt; DevBuf<int2> dn_hash; DevBuf<float> dn_w; DevBuf<unsigned long long> s_vals_out;
+  int dense_shift = 2, COLS = 4;
   // query-block transposition (v2 kernel)
   DevBuf<unsigned long long> bt_keys_in, bt_keys_out, bt_vals_in, bt_vals_out, ud_key; DevBuf<int32_t> bt_flags, bt_pos, ud_dim, ud_start, bd_ptr;
   // outputs
@@ -135,6 +139,29 @@ static cudaError_t launch_blk(apss_handle* h, const ScoreArgs& a, const BlockArg
   }
 }
 
+template <int QB, int WARPS, int COLS>
+static cudaError_t launch_dense_t(apss_handle* h, const ScoreArgs& a, const BlockArgs& b, const DenseTiles& d, bool dup) {
+  auto kern = dup ? k_score_dense<QB, WARPS, COLS, true> : k_score_dense<QB, WARPS, COLS, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  if (e != cudaSuccess) return e;
+  kern<<<h->sm_count, WARPS * 32, h->smem_bytes, h->stream>>>(a, b, d);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_dense(apss_handle* h, const ScoreArgs& a, const BlockArgs& b, const DenseTiles& d, bool dup) {
+  const int key = h->QB * 10000 + h->WARPS * 100 + h->COLS;
+  switch (key) {
+    case 321602: return launch_dense_t<32, 16, 2>(h, a, b, d, dup);
+    case 321202: return launch_dense_t<32, 12, 2>(h, a, b, d, dup);
+    case 320802: return launch_dense_t<32, 8, 2>(h, a, b, d, dup);
+    case 161602: return launch_dense_t<16, 16, 2>(h, a, b, d, dup);
+    case 161604: return launch_dense_t<16, 16, 4>(h, a, b, d, dup);
+    case 160804: return launch_dense_t<16, 8, 4>(h, a, b, d, dup);
+    case 81604: return launch_dense_t<8, 16, 4>(h, a, b, d, dup);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 extern "C" int32_t apss_abi_version(void) { return APSS_ABI_VERSION; }
 
 extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
@@ -153,12 +180,20 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   const size_t max_smem = prop.sharedMemPerBlockOptin;
   // kernel_variant: bits 0-7 unroll (row kernel), 8-15 warps per CTA, 16-23 algorithm (0/2 = query-block
   // kernel with fixed-point atomics, 1 = warp-per-(query, tile) row kernel), 24-31 queries per block
-  const int algo = ((cfg->kernel_variant >> 16) & 0xff) == 2 ? 2 : 1;   // default: row kernel
+  int algo = (cfg->kernel_variant >> 16) & 0xff;   // 0 = default
+  if (algo != 1 && algo != 2 && algo != 3) algo = 3;   // default: dense-head kernel
   int QB = (cfg->kernel_variant >> 24) & 0xff; if (QB <= 0) QB = 16;
+  const bool qb_given = ((cfg->kernel_variant >> 24) & 0xff) != 0;
   if (QB > 32) QB = 32;   // a dimension's row list is staged one entry per lane
-  const size_t blk_extra = (size_t)LONG_CAP * 16 + (size_t)(LONG_CAP + 1) * 4 + 64;
+  if (algo == 3 && QB != 8 && QB != 16 && QB != 32) QB = qb_given ? 32 : 16;
+  size_t blk_extra = (size_t)LONG_CAP * 16 + (size_t)(LONG_CAP + 1) * 4 + 64;
+  if (algo == 3) blk_extra = (size_t)SEG_CAP * 16 + 64 + (size_t)KD * QB * 4 + (size_t)KD * 16 + (size_t)HS * 8;
+  const size_t acc_bytes = algo == 3 ? 2 : 4;   // u16 packed (dense-head kernel) or u32 / fp32
   int CR = cfg->tile_vectors;
-  if (CR <= 0) CR = algo == 1 ? 3584 : (int)(((max_smem - blk_extra) / ((size_t)QB * 4)) / 128 * 128);
+  if (CR <= 0) {
+    CR = algo == 1 ? 3584 : (int)(((max_smem - blk_extra) / ((size_t)QB * acc_bytes)) / 128 * 128);
+    if (algo == 3 && CR >= 1024) CR = CR / 1024 * 1024;   // whole passes of the dense phase
+  }
   CR = (CR + 127) / 128 * 128;
   int warps = 0;
   const int want = (cfg->kernel_variant >> 8) & 0xff;
@@ -168,10 +203,21 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
     if ((want == 8 || want == 16 || want == 32) && (size_t)want * CR * sizeof(float) + 1024 <= max_smem) warps = want;
     h->smem_bytes = (size_t)warps * CR * sizeof(float);
   } else {
-    while (QB > 1 && (size_t)QB * CR * 4 + blk_extra > max_smem) QB >>= 1;   // explicit tile size: shrink the block
-    if ((size_t)QB * CR * 4 + blk_extra > max_smem) return bail(APSS_E_INVALID);
-    warps = (want == 8 || want == 16 || want == 32) ? want : 16;
-    h->smem_bytes = (size_t)QB * CR * 4 + blk_extra;
+    while (QB > (algo == 3 ? 8 : 1) && (size_t)QB * CR * acc_bytes + blk_extra > max_smem) {   // explicit tile size: shrink the block
+      if (algo == 3) blk_extra -= (size_t)KD * (QB / 2) * 4;
+      QB >>= 1;
+    }
+    if ((size_t)QB * CR * acc_bytes + blk_extra > max_smem) return bail(APSS_E_INVALID);
+    warps = (want == 8 || want == 12 || want == 16 || want == 32) ? want : 16;
+    h->smem_bytes = (size_t)QB * CR * acc_bytes + blk_extra;
+    if (algo == 3) {
+      h->COLS = (cfg->kernel_variant & 0xff) == 2 ? 2 : 4;
+      if (QB == 32) { h->COLS = 2; if (warps != 8 && warps != 12 && warps != 16) warps = 16; }
+      else if (QB == 16) { if (h->COLS == 2) warps = 16; else if (warps != 8) warps = 16; }
+      else { h->COLS = 4; warps = 16; }
+      const char* ds = getenv("APSS_DENSE_SHIFT");
+      if (ds && atoi(ds) >= 0 && atoi(ds) <= 10) h->dense_shift = atoi(ds);
+    }
   }
   if (!warps) return bail(APSS_E_INVALID);
   h->CR = CR; h->WARPS = warps; h->variant = cfg->kernel_variant; h->algo = algo; h->QB = QB;
@@ -215,6 +261,7 @@ extern "C" void apss_destroy(apss_handle* h) {
   h->q_cnt.release(); h->q_ptr.release(); h->q_dim.release(); h->q_val.release(); h->q_w.release(); h->q_status.release();
   h->bt_keys_in.release(); h->bt_keys_out.release(); h->bt_vals_in.release(); h->bt_vals_out.release(); h->ud_key.release();
   h->bt_flags.release(); h->bt_pos.release(); h->ud_dim.release(); h->ud_start.release(); h->bd_ptr.release();
+  h->dn_cnt.release(); h->dn_dim.release(); h->dn_len.release(); h->tile_cnt.release(); h->dn_hash.release(); h->dn_w.release(); h->s_vals_out.release();
   h->s_keys_in.release(); h->s_keys_out.release(); h->s_vals_in.release(); h->s_tile_start.release(); h->cub_tmp.release();
   h->pf_q.release(); h->pf_c.release(); h->pf_est.release(); h->out_q.release(); h->out_c.release(); h->out_sim.release();
   if (h->d_counters) cudaFree(h->d_counters);
@@ -258,7 +305,7 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
   }
   const int64_t m = nnz_new - nnz_lo;
   const int64_t post_base = nnz_lo;   // postings are stored in the same order of tiles as the forward store
-  CK(h->post.reserve(std::max<int64_t>(nnz_new, 1), post_base, s));
+  CK(h->post.reserve(std::max<int64_t>(nnz_new, 1), h->algo == 3 ? nnz_old : post_base, s));
   CK(h->dir.reserve((size_t)tile1 * ((size_t)D + 1), (size_t)tile0 * ((size_t)D + 1), s));
   CK(h->tile_base.reserve(tile1 + 1, tile0, s));
   CK(h->s_tile_start.reserve(ntiles_aff + 1, 0, s));
@@ -271,6 +318,7 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
     CK(cudaGetLastError()); h->kernel_launches++;
     size_t tmp = 0;
     unsigned long long* vals_out = reinterpret_cast<unsigned long long*>(h->post.p + post_base);
+    if (h->algo == 3) { CK(h->s_vals_out.reserve(m, 0, s)); vals_out = h->s_vals_out.p; }
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->s_keys_in.p, h->s_keys_out.p, h->s_vals_in.p, vals_out, m, 0, dimbits + tilebits, s));
     CK(h->cub_tmp.reserve(tmp, 0, s));
     CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, h->s_keys_in.p, h->s_keys_out.p, h->s_vals_in.p, vals_out, m, 0, dimbits + tilebits, s));
@@ -280,6 +328,27 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
   CK(cudaGetLastError());
   k_build_dir<<<cdiv(((int64_t)D + 1) * ntiles_aff, 256), 256, 0, s>>>(h->s_keys_out.p, m, ntiles_aff, D, dimbits, h->s_tile_start.p, tile0, h->dir.p);
   CK(cudaGetLastError()); h->kernel_launches += 2;
+  if (h->algo == 3) {
+    // dense-head extraction: pick each tile's dense dims, move their postings into dense fp32 rows,
+    // compact the remaining postings and fix the directory
+    CK(h->dn_cnt.reserve(tile1, tile0, s)); CK(h->tile_cnt.reserve(tile1, tile0, s));
+    CK(h->dn_dim.reserve((size_t)tile1 * KD, (size_t)tile0 * KD, s)); CK(h->dn_len.reserve((size_t)tile1 * KD, (size_t)tile0 * KD, s));
+    CK(h->dn_hash.reserve((size_t)tile1 * HS, (size_t)tile0 * HS, s));
+    CK(h->dn_w.reserve((size_t)tile1 * KD * CR, (size_t)tile0 * KD * CR, s));
+    k_dense_select<<<ntiles_aff, 256, 0, s>>>(D, CR, tile0, n_new, h->dense_shift, h->dir.p, h->dn_cnt.p, h->dn_dim.p, h->dn_len.p, h->dn_hash.p, h->tile_cnt.p);
+    CK(cudaGetLastError());
+    k_tile_bases<<<1, 32, 0, s>>>(tile0, ntiles_aff, h->tile_cnt.p, h->tile_base.p);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(h->dn_w.p + (size_t)tile0 * KD * CR, 0, (size_t)ntiles_aff * KD * CR * sizeof(float), s));
+    if (m > 0) {
+      k_post_scatter<<<cdiv(m, 256), 256, 0, s>>>(m, h->s_keys_out.p, h->s_vals_out.p, dimbits, tile0, CR, h->s_tile_start.p, h->tile_base.p,
+                                                   h->dn_cnt.p, h->dn_dim.p, h->dn_len.p, h->dn_hash.p, h->dn_w.p,
+                                                   reinterpret_cast<unsigned long long*>(h->post.p), (long long)h->post.cap);
+      CK(cudaGetLastError());
+    }
+    k_dir_fix<<<cdiv(((int64_t)D + 1) * ntiles_aff, 256), 256, 0, s>>>(ntiles_aff, D, tile0, h->dn_cnt.p, h->dn_dim.p, h->dn_len.p, h->dir.p);
+    CK(cudaGetLastError()); h->kernel_launches += 4;
+  }
   h->n_local = n_new; h->nnz = nnz_new; h->n_post = nnz_new; h->ntiles = tile1;
   return APSS_OK;
 }
@@ -383,10 +452,12 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   if (h->algo != 1 && batch_nnz) {
     // fixed-point scale: every dot product is <= max squared norm (Cauchy-Schwarz); keep 2x headroom
     const double bound = std::max(h->max_sq, 1e-300) * (1.0 + 1e-6);
-    F = (int)std::floor(std::log2(2147483648.0 / bound));
+    // (dense-head kernel: u16 accumulators, sums stay below 2^15 + one quantum per shared dim)
+    F = (int)std::floor(std::log2((h->algo == 3 ? 32768.0 : 2147483648.0) / bound));
     F = std::max(-100, std::min(100, F));
-    const double ts = t * std::ldexp(1.0, F) * (1.0 - std::ldexp(1.0, -20));
-    thr_int = ts <= 0 ? 0u : (ts >= 4294967295.0 ? 0xffffffffu : (unsigned)std::floor(ts));
+    const double ts = t * std::ldexp(1.0, F) * (1.0 - std::ldexp(1.0, h->algo == 3 ? -16 : -20));
+    const double tmax = h->algo == 3 ? 65535.0 : 4294967295.0;
+    thr_int = ts <= 0 ? 0u : (ts >= tmax ? (unsigned)tmax : (unsigned)std::floor(ts));
     const int QB = h->QB; const int nqb = (n + QB - 1) / QB;
     int dimbits = 1; while ((1LL << dimbits) < (int64_t)D) ++dimbits;
     int qbbits = 1; while ((1LL << qbbits) < nqb) ++qbbits;
@@ -394,7 +465,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     CK(h->bt_vals_out.reserve(batch_nnz, 0, s)); CK(h->ud_key.reserve(batch_nnz + 1, 0, s));
     CK(h->bt_flags.reserve(batch_nnz + 1, 0, s)); CK(h->bt_pos.reserve(batch_nnz + 1, 0, s));
     CK(h->ud_dim.reserve(batch_nnz + 1, 0, s)); CK(h->ud_start.reserve(batch_nnz + 2, 0, s)); CK(h->bd_ptr.reserve(nqb + 1, 0, s));
-    k_bt_emit<<<cdiv(batch_nnz, 256), 256, 0, s>>>(n, batch_nnz, h->q_ptr.p, h->q_dim.p, h->q_w.p, QB, h->CR, dimbits, (float)std::ldexp(1.0, F),
+    k_bt_emit<<<cdiv(batch_nnz, 256), 256, 0, s>>>(n, batch_nnz, h->q_ptr.p, h->q_dim.p, h->q_w.p, QB, h->algo == 3 ? h->CR / 2 : h->CR, dimbits, (float)std::ldexp(1.0, F),
                                                    h->bt_keys_in.p, h->bt_vals_in.p);
     CK(cudaGetLastError());
     size_t tb = 0;
@@ -422,15 +493,21 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     a.thr_emit = thr_emit;
     a.out_q = h->pf_q.p; a.out_c = h->pf_c.p; a.out_est = h->pf_est.p; a.out_cap = h->pf_q.cap;
     a.counters = h->d_counters;
+    a.tile_cnt = h->algo == 3 ? h->tile_cnt.p : nullptr; a.post_cap = (long long)h->post.cap;
     a.total_items = (unsigned long long)h->ntiles * (unsigned long long)n;
     CK(cudaMemsetAsync(h->d_counters, 0, 7 * sizeof(unsigned long long), s));   // keep the prefilter tallies
+    CK(cudaMemsetAsync(h->d_counters + C_PHASE, 0, 8 * sizeof(unsigned long long), s));
     CK(cudaEventRecord(h->ev_s0, s));
     if (h->algo == 1) {
       if (a.total_items && batch_nnz) { CK(launch_score(h, a, h->custom_keys)); h->score_launches++; h->kernel_launches++; }
     } else if (h->ntiles && batch_nnz) {
       blk.thr_int = thr_int; blk.inv_scale = (float)std::ldexp(1.0, -F);
       a.total_items = (unsigned long long)h->ntiles * (unsigned long long)blk.n_qblocks;
-      CK(launch_blk(h, a, blk, h->custom_keys)); h->score_launches++; h->kernel_launches++;
+      if (h->algo == 3) {
+        DenseTiles dtl{h->dn_cnt.p, h->dn_dim.p, h->dn_len.p, h->dn_hash.p, h->dn_w.p};
+        CK(launch_dense(h, a, blk, dtl, h->custom_keys));
+      } else CK(launch_blk(h, a, blk, h->custom_keys));
+      h->score_launches++; h->kernel_launches++;
     }
     CK(cudaEventRecord(h->ev_s1, s));
     CK(h->out_q.reserve(h->pf_q.cap, 0, s)); CK(h->out_c.reserve(h->pf_q.cap, 0, s)); CK(h->out_sim.reserve(h->pf_q.cap, 0, s));
@@ -442,6 +519,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     }
     CK(cudaEventRecord(h->ev_b1, s));
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_counters + C_PHASE, h->d_counters + C_PHASE, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (h->h_counters[C_PF] <= h->pf_q.cap) break;
     if (attempt == 2) return h->fail(APSS_E_NOMEM, "pair buffer overflow persisted");
@@ -456,6 +534,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   res.candidates_unique = (int64_t)h->h_counters[C_CANDS];
   res.n_pairs = (int64_t)h->h_counters[C_FINAL];
   res.n_pairs_r1 = (int64_t)h->h_counters[C_R1];
+  for (int k = 0; k < 8; ++k) h->phase_cycles[k] = (int64_t)h->h_counters[C_PHASE + k];
   res.work_items = (int64_t)((unsigned long long)h->ntiles * (unsigned long long)(h->algo == 1 ? n : (n + h->QB - 1) / h->QB));
   h->last_n = n; h->last_pairs = res.n_pairs;
   h->tot_postings += res.postings_visited; h->tot_cands += res.candidates_unique; h->tot_pairs += res.n_pairs; h->tot_pf += res.n_prefilter;
@@ -514,6 +593,7 @@ extern "C" int32_t apss_get_stats(apss_handle* h, apss_stats* out) {
   s.bytes_forward = h->nnz * 12 + (h->n_local + 1) * 8;
   s.tot_postings_visited = h->tot_postings; s.tot_candidates_unique = h->tot_cands; s.tot_pairs = h->tot_pairs; s.tot_prefilter = h->tot_pf;
   s.score_launches = h->score_launches; s.kernel_launches = h->kernel_launches; s.tot_score_ms = h->tot_score_ms;
+  for (int k = 0; k < 8; ++k) s.phase_cycles[k] = h->phase_cycles[k];
   s.frozen = h->frozen; s.tile_vectors = h->CR; s.warps_per_cta = h->WARPS; s.sm_count = h->sm_count;
   *out = s;
   return APSS_OK;

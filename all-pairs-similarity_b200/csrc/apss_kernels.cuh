@@ -16,8 +16,16 @@
 //   k_score         IndexingWorkerActor.scala:74-111 + CommonUtils.scala:98-117 (fp32 pre-filter)
 //   k_verify        CommonUtils.scala:98-117 in fp64 + the threshold at IndexingWorkerActor.scala:93
 #pragma once
+#include <cassert>
 #include <cstdint>
 #include <cuda_runtime.h>
+
+// APSS_DEBUG builds (libapss_b200_dbg.so) bounds-check every indexed access with device asserts.
+#ifdef APSS_DEBUG
+#define DBG_ASSERT(c) assert(c)
+#else
+#define DBG_ASSERT(c) ((void)0)
+#endif
 
 namespace apss {
 
@@ -31,11 +39,15 @@ enum Counter : int {
   C_WORK = 6,      // persistent-kernel work cursor
   C_NREJ = 7, C_NEMPTY = 8, C_NACTIVE = 9, C_MAXNNZ = 10,
   C_MAXSQ = 11,    // max squared L2 norm of a pruned vector (bits of a non-negative double)
-  C_COUNT = 16
+  C_PHASE = 16,    // 8 per-phase cycle totals of the dense kernel (thread 0 of every CTA)
+  C_COUNT = 24
 };
 
 static constexpr unsigned FULL = 0xffffffffu;
 static constexpr unsigned NEG0 = 0x80000000u;   // accumulator "never touched" marker (-0.0f)
+// fp32 weights are clamped to >= 2^-60 so that the product of any two is a positive normal float: a
+// shared dimension always leaves a non-zero trace in the accumulator (exact candidate counts).
+#define W_MIN 8.6736173798840355e-19f
 
 __device__ __forceinline__ uint2 ld_stream(const uint2* p) {
   uint2 r;
@@ -87,7 +99,7 @@ __global__ void k_prefilter_write(int n, const int64_t* __restrict__ ptr, const 
   int o = q_ptr[v];
   for (int64_t p = ptr[v]; p < ptr[v + 1]; ++p) {
     double x = val[p];
-    if (x > idx_thr) { q_dim[o] = idx[p]; q_val[o] = x; q_w[o] = (float)x; ++o; }
+    if (x > idx_thr) { q_dim[o] = idx[p]; q_val[o] = x; q_w[o] = fmaxf((float)x, W_MIN); ++o; }
   }
 }
 
@@ -117,7 +129,7 @@ __global__ void k_emit_postings(int64_t nnz_lo, int64_t nnz_hi, int64_t row_lo, 
   unsigned long long tile_rel = (unsigned long long)(row / CR - tile0);
   unsigned in_tile = (unsigned)(row % CR);
   keys[p - nnz_lo] = (tile_rel << dimbits) | (unsigned)fwd_idx[p];
-  vals[p - nnz_lo] = ((unsigned long long)__float_as_uint((float)fwd_val[p]) << 32) | in_tile;   // uint2{x = id, y = w}
+  vals[p - nnz_lo] = ((unsigned long long)__float_as_uint(fmaxf((float)fwd_val[p], W_MIN)) << 32) | in_tile;   // uint2{x = id, y = w}
 }
 
 __device__ __forceinline__ int64_t lower_bound_u64(const unsigned long long* __restrict__ a, int64_t n, unsigned long long key) {
@@ -156,6 +168,8 @@ struct ScoreArgs {
   int32_t* out_q; int32_t* out_c; float* out_est; unsigned long long out_cap;
   unsigned long long* counters;
   unsigned long long total_items;
+  const int32_t* tile_cnt;   // debug builds: sparse postings per tile (bounds checks)
+  long long post_cap;        // debug builds: capacity of post[]
 };
 
 // Persistent kernel.  One CTA per SM, WARPS warps per CTA; each warp owns one row of CR fp32
@@ -505,6 +519,436 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_blk(const ScoreArgs a, 
     n_cand += __shfl_down_sync(FULL, n_cand, o);
   }
   if (lane == 0) { atomicAdd(&a.counters[C_POSTINGS], n_post); atomicAdd(&a.counters[C_CANDS], n_cand); }
+}
+
+// ------------------------------------------------------------------ K1b/K2c: dense-head tiles + FFMA scoring
+
+// On power-law data almost all posting visits fall on a few dozen near-ubiquitous dimensions.  A tile
+// therefore stores the dimensions present in >= 1/2^dense_shift of its vectors ("dense dims", at most
+// KD per tile) as dense fp32 rows dense_w[tile][slot][id] (0 = absent) instead of postings; the
+// scoring kernel handles them with register-tiled FFMAs (1 instruction per 32 updates instead of ~12
+// on the sparse path) and everything else with the sparse path of k_score_blk.
+static constexpr int KD = 64;      // dense slots per tile
+static constexpr int HS = 128;     // open-addressing hash (dim -> slot) per tile
+
+struct DenseTiles {
+  const int32_t* cnt;      // [ntiles]
+  const int32_t* dim;      // [ntiles][KD] ascending
+  const int32_t* len;      // [ntiles][KD] true posting-list length of the dim in the tile
+  const int2* hash;        // [ntiles][HS] (dim, slot); dim = -1 empty
+  const float* w;          // [ntiles][KD][CR]
+};
+
+__device__ __forceinline__ unsigned dense_hash_fn(int d) { return ((unsigned)d * 2654435761u) >> 25; }   // 7 bits
+
+// one CTA per affected tile: pick the dense dims (ascending dim order, first KD that qualify)
+__global__ void k_dense_select(int D, int CR, int64_t tile0, int64_t n_local, int dense_shift, const int32_t* __restrict__ dir,
+                               int32_t* __restrict__ d_cnt, int32_t* __restrict__ d_dim, int32_t* __restrict__ d_len,
+                               int2* __restrict__ d_hash, int32_t* __restrict__ tile_cnt) {
+  const int64_t tile = tile0 + blockIdx.x;
+  const int32_t* dirt = dir + (size_t)tile * ((size_t)D + 1);
+  __shared__ int s_run, s_warp[32], s_removed;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int64_t nt = min((int64_t)CR, n_local - tile * CR);
+  const int thr = max(8, (int)((nt + (1 << dense_shift) - 1) >> dense_shift));
+  if (tid == 0) { s_run = 0; s_removed = 0; }
+  for (int h = tid; h < HS; h += blockDim.x) d_hash[tile * HS + h] = make_int2(-1, -1);
+  __syncthreads();
+  for (int d0 = 0; d0 < D; d0 += blockDim.x) {
+    const int d = d0 + tid;
+    int len = 0;
+    if (d < D) len = dirt[d + 1] - dirt[d];
+    const bool q = len >= thr;
+    const unsigned bal = __ballot_sync(FULL, q);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_run;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const int slot = before + __popc(bal & ((1u << lane) - 1));
+    if (q && slot < KD) {
+      d_dim[tile * KD + slot] = d; d_len[tile * KD + slot] = len;
+      atomicAdd(&s_removed, len);
+      unsigned h = dense_hash_fn(d);
+      while (atomicCAS(&d_hash[tile * HS + h].x, -1, d) != -1) h = (h + 1) & (HS - 1);
+      d_hash[tile * HS + h].y = slot;
+    }
+    __syncthreads();
+    if (tid == 0) { int t = s_run; for (int w = 0; w < nw; ++w) t += s_warp[w]; s_run = t; }
+    __syncthreads();
+    if (s_run >= KD) break;
+  }
+  if (tid == 0) { d_cnt[tile] = min(s_run, KD); tile_cnt[tile] = dirt[D] - s_removed; }
+}
+
+__global__ void k_tile_bases(int64_t tile0, int ntiles_aff, const int32_t* __restrict__ tile_cnt, int64_t* __restrict__ tile_base) {
+  if (blockIdx.x || threadIdx.x) return;
+  int64_t b = tile0 == 0 ? 0 : tile_base[tile0 - 1] + tile_cnt[tile0 - 1];
+  for (int t = 0; t < ntiles_aff; ++t) { tile_base[tile0 + t] = b; b += tile_cnt[tile0 + t]; }
+}
+
+__device__ __forceinline__ int dense_lookup(const int2* __restrict__ hash, int d) {
+  unsigned h = dense_hash_fn(d);
+  for (;;) { const int2 e = hash[h]; if (e.x == d) return e.y; if (e.x < 0) return -1; h = (h + 1) & (HS - 1); }
+}
+
+// thread per sorted posting: dense dims go to dense_w, the rest are compacted into the tile's postings
+__global__ void k_post_scatter(int64_t m, const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ vals,
+                               int dimbits, int64_t tile0, int CR, const int64_t* __restrict__ tile_start,
+                               const int64_t* __restrict__ tile_base, const int32_t* __restrict__ d_cnt, const int32_t* __restrict__ d_dim,
+                               const int32_t* __restrict__ d_len, const int2* __restrict__ d_hash, float* __restrict__ d_w,
+                               unsigned long long* __restrict__ post, long long post_cap) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const unsigned long long key = keys[i], val = vals[i];
+  const int trel = (int)(key >> dimbits); const int d = (int)(key & ((1ULL << dimbits) - 1));
+  const int64_t tile = tile0 + trel;
+  const int slot = dense_lookup(d_hash + tile * HS, d);
+  DBG_ASSERT(trel >= 0 && (unsigned)(val & 0xffffffffu) < (unsigned)CR && slot < KD);
+  if (slot >= 0) { d_w[((size_t)tile * KD + slot) * CR + (unsigned)(val & 0xffffffffu)] = __uint_as_float((unsigned)(val >> 32)); return; }
+  int removed = 0;
+  const int n = d_cnt[tile];
+  for (int k = 0; k < n; ++k) { if (d_dim[tile * KD + k] < d) removed += d_len[tile * KD + k]; else break; }
+  DBG_ASSERT((i - tile_start[trel]) - removed >= 0 && tile_base[tile] + (i - tile_start[trel]) - removed < post_cap);
+  post[tile_base[tile] + (i - tile_start[trel]) - removed] = val;
+}
+
+__global__ void k_dir_fix(int ntiles_aff, int D, int64_t tile0, const int32_t* __restrict__ d_cnt, const int32_t* __restrict__ d_dim,
+                          const int32_t* __restrict__ d_len, int32_t* __restrict__ dir) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)D + 1;
+  if (i >= per * ntiles_aff) return;
+  const int64_t tile = tile0 + i / per; const int d = (int)(i % per);
+  int removed = 0;
+  const int n = d_cnt[tile];
+  for (int k = 0; k < n; ++k) { if (d_dim[tile * KD + k] < d) removed += d_len[tile * KD + k]; else break; }
+  dir[tile * per + d] -= removed;
+}
+
+// Scoring kernel for dense-head tiles.  Same work items, fixed-point accumulators, sparse phases and
+// epilogue as k_score_blk; in addition the dimensions of the query block that are dense in the tile
+// are applied by FFMA: thread = COLS adjacent candidates x all QB query rows in registers.
+static constexpr int SEG_CAP = 1280;    // sparse segments longer than SPLIT, per work item (shared memory)
+static constexpr int SPLIT = 8;         // segments up to this length are walked by the lane that looked them up
+static constexpr int SEG_PIECE = 512;   // queued segments are cut into pieces of at most this many postings
+
+// Accumulators of the dense-head kernel are u16 fixed point, two per 32-bit word: word (row*CR + c)/2,
+// half c & 1 (CR is even).  An update is one native shared atomic add of (value << 16*(c&1)); halves
+// cannot carry into each other because every sum is < 2^16 by the choice of the scale.
+__device__ __forceinline__ void acc_add16(unsigned* acc, unsigned rowoff_words, unsigned c, float ws, float wc) {
+  atomicAdd(acc + rowoff_words + (c >> 1), __float2uint_ru(ws * wc) << ((c & 1u) << 4));
+}
+
+// apply postings [p, pe) (<= SPLIT of them) of one sparse segment to the rows [rs, rs+nr) of the block:
+// one LANE per segment; collisions between lanes are safe (atomics)
+__device__ __forceinline__ void lane_walk(unsigned* acc, const uint2* __restrict__ pt, const uint2* __restrict__ bt,
+                                          int p, int pe, int rs, int nr, uint2 rw0, int nwords, int CR) {
+  DBG_ASSERT(p >= 0 && pe >= p && pe - p <= SPLIT);
+  while (__any_sync(FULL, p < pe)) {
+    uint2 pp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (p + u < pe) pp[u] = ld_stream(pt + p + u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (p + u < pe) {
+        const float wc = __uint_as_float(pp[u].y);
+        DBG_ASSERT(pp[u].x < (unsigned)CR && rw0.x + (pp[u].x >> 1) < (unsigned)nwords);
+        acc_add16(acc, rw0.x, pp[u].x, __uint_as_float(rw0.y), wc);
+        for (int r = 1; r < nr; ++r) {
+          const uint2 rw = __ldg(bt + rs + r);
+          acc_add16(acc, rw.x, pp[u].x, __uint_as_float(rw.y), wc);
+        }
+      }
+    p += 4;
+  }
+}
+
+// Scoring kernel for dense-head tiles.  Persistent, one CTA per SM; a work item is (index tile, block
+// of QB queries); QB x CR u16 accumulators live in shared memory.  Per item:
+//   phase 1  32 directory look-ups per warp step.  Dims that are dense in the tile go to the dense list;
+//            sparse segments of <= SPLIT postings are walked at once, one lane per segment; longer ones
+//            are queued
+//   phase D  dense dims by FFMA: thread = COLS adjacent candidates x all QB query rows in registers,
+//            result added to the accumulators (exclusive phase, plain read-modify-write)
+//   phase L  queued segments, one warp per segment: coalesced 8 B posting loads (next chunk in flight),
+//            the dimension's (row, weight) list held one entry per lane and broadcast by shuffle
+//   phase 3  epilogue: count candidates (non-zero halves), emit those >= thr by warp-aggregated
+//            compaction, clear
+// bt entries for this kernel hold (row * CR / 2, weight * 2^F).
+template <int QB, int WARPS, int COLS, bool DUPKEYS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_score_dense(const ScoreArgs a, const BlockArgs b, const DenseTiles dt) {
+  extern __shared__ __align__(16) unsigned smem_u[];
+  const int CR = a.CR;
+  const int RW = CR >> 1;                                               // words per accumulator row
+  unsigned* acc = smem_u;                                               // [QB][RW]
+  float* Wq = reinterpret_cast<float*>(acc + (size_t)QB * RW);          // [KD][QB] scaled query weights, by dense entry
+  int4* dl = reinterpret_cast<int4*>(Wq + KD * QB);                     // [KD] (slot, rs, nr, -)
+  int2* hsh = reinterpret_cast<int2*>(dl + KD);                         // [HS]
+  int4* segs = reinterpret_cast<int4*>(hsh + HS);                       // [SEG_CAP] (s, e, rs, nr)
+  __shared__ unsigned long long s_item;
+  __shared__ int s_nseg, s_segvalid, s_ndense;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  constexpr int NT = WARPS * 32;
+  const int nwords = QB * RW;
+  for (int i = tid * 4; i < nwords; i += NT * 4) *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
+  unsigned long long n_post = 0, n_cand = 0;
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tc = clock64();
+#define PHASE_MARK(k) do { if (tid == 0) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; } } while (0)
+  const unsigned thr_hi = b.thr_int << 16;   // high half >= thr  <=>  word >= thr << 16
+
+  for (;;) {
+    __syncthreads();
+    PHASE_MARK(5);
+    if (tid == 0) { s_item = atomicAdd(&a.counters[C_WORK], 1ULL); s_nseg = 0; s_segvalid = SEG_CAP; s_ndense = 0; }
+    __syncthreads();
+    const unsigned long long item = s_item;
+    if (item >= a.total_items) break;
+    const int tile = (int)(item / (unsigned)b.n_qblocks);
+    const int qb = (int)(item - (unsigned long long)tile * (unsigned)b.n_qblocks);
+    const int32_t* __restrict__ dirt = a.dir + (size_t)tile * ((size_t)a.D + 1);
+    const uint2* __restrict__ pt = a.post + __ldg(a.tile_base + tile);
+    const int u0 = __ldg(b.bd_ptr + qb), u1 = __ldg(b.bd_ptr + qb + 1);
+    const int ndt = __ldg(dt.cnt + tile);
+    const int tcnt = a.tile_cnt ? __ldg(a.tile_cnt + tile) : 0x7fffffff;
+    DBG_ASSERT(tile >= 0 && tile < a.ntiles && qb < b.n_qblocks && ndt >= 0 && ndt <= KD && u0 <= u1);
+    DBG_ASSERT(!a.tile_cnt || __ldg(a.tile_base + tile) + tcnt <= a.post_cap);
+    for (int h = tid; h < HS; h += NT) hsh[h] = __ldg(dt.hash + (size_t)tile * HS + h);
+    for (int i = tid; i < KD * QB; i += NT) Wq[i] = 0.f;
+    __syncthreads();
+    PHASE_MARK(0);
+
+    // ---- phase 1
+    for (int ub = u0 + warp * 32; ub < u1; ub += NT) {
+      const int u = ub + lane;
+      int s = 0, e = 0, rs = 0, nr = 0;
+      uint2 rw0 = make_uint2(0, 0);
+      if (u < u1) {
+        const int d = __ldg(b.ud_dim + u);
+        rs = __ldg(b.ud_start + u); nr = __ldg(b.ud_start + u + 1) - rs;
+        const int slot = ndt ? dense_lookup(hsh, d) : -1;
+        if (slot >= 0) {
+          const int k = atomicAdd(&s_ndense, 1);
+          DBG_ASSERT(k < KD && slot < ndt && nr >= 1 && nr <= QB);
+          dl[k] = make_int4(slot, rs, nr, 0);
+          n_post += (unsigned long long)(unsigned)__ldg(dt.len + (size_t)tile * KD + slot) * (unsigned)nr;
+        } else {
+          s = __ldg(dirt + d); e = __ldg(dirt + d + 1);
+          DBG_ASSERT(d >= 0 && d < a.D && s >= 0 && e >= s && e <= tcnt && nr >= 1 && nr <= QB);
+        }
+      }
+      const int len = e - s;
+      n_post += (unsigned long long)(unsigned)len * (unsigned)nr;
+      if (len > 0 && len <= SPLIT) rw0 = __ldg(b.bt + rs);
+      bool coop = false;                      // segment queue full: walk it here, warp-cooperatively
+      if (len > SPLIT) {                      // queue in pieces of <= SEG_PIECE postings (balance across warps)
+        const int np = (len + SEG_PIECE - 1) / SEG_PIECE;
+        const int k = atomicAdd(&s_nseg, np);
+        if (k + np <= SEG_CAP) { for (int j = 0; j < np; ++j) segs[k + j] = make_int4(s + j * SEG_PIECE, min(e, s + (j + 1) * SEG_PIECE), rs, nr); }
+        else { atomicMin(&s_segvalid, k); coop = true; }      // the cursor only grows: later reservations fail too
+      }
+      lane_walk(acc, pt, b.bt, s, len <= SPLIT ? e : s, rs, nr, rw0, nwords, CR);
+      unsigned m = __ballot_sync(FULL, coop);
+      while (m) {
+        const int j = __ffs(m) - 1; m &= m - 1;
+        const int sj = __shfl_sync(FULL, s, j), ej = __shfl_sync(FULL, e, j);
+        const int rsj = __shfl_sync(FULL, rs, j), nrj = __shfl_sync(FULL, nr, j);
+        uint2 rw = make_uint2(0, 0);
+        if (lane < nrj) rw = __ldg(b.bt + rsj + lane);
+        for (int p0 = sj; p0 < ej; p0 += 32) {
+          const int p = p0 + lane;
+          uint2 pp = make_uint2(0, 0);
+          if (p < ej) pp = ld_stream(pt + p);
+          const float wc = __uint_as_float(pp.y);
+          for (int r = 0; r < nrj; ++r) {
+            const unsigned ro = __shfl_sync(FULL, rw.x, r);
+            const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
+            if (p < ej) acc_add16(acc, ro, pp.x, ws, wc);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    PHASE_MARK(1);
+    const int nd = s_ndense;
+    const int nseg = min(s_nseg, s_segvalid);
+    // ---- Wq[entry][row] from the block's row lists
+    for (int k = warp; k < nd; k += WARPS) {
+      const int4 e = dl[k];
+      if (lane < e.z) {
+        const uint2 rw = __ldg(b.bt + e.y + lane);
+        DBG_ASSERT(rw.x / (unsigned)RW < (unsigned)QB && k < KD);
+        Wq[k * QB + rw.x / (unsigned)RW] = __uint_as_float(rw.y);
+      }
+    }
+    __syncthreads();
+    // ---- phase D: dense dims by FFMA, thread = COLS adjacent candidates x QB rows
+    if (nd) {
+      const float* __restrict__ wbase = dt.w + (size_t)tile * KD * CR;
+      for (int cb = tid * COLS; cb < CR; cb += NT * COLS) {
+        float av[COLS][QB];
+#pragma unroll
+        for (int c = 0; c < COLS; ++c)
+#pragma unroll
+          for (int r = 0; r < QB; ++r) av[c][r] = 0.f;
+        float wv[4][COLS], wn[4][COLS];
+        auto load4 = [&](float (&dst)[4][COLS], int e0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = e0 + j;
+            if (e < nd) {
+              DBG_ASSERT(dl[e].x >= 0 && dl[e].x < KD && cb + COLS <= CR);
+              const float* src = wbase + (size_t)dl[e].x * CR + cb;
+              if (COLS == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(src)); dst[j][0] = t.x; dst[j][COLS - 1] = t.y; }
+              else if (COLS == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(src)); dst[j][0] = t.x; dst[j][1 % COLS] = t.y; dst[j][2 % COLS] = t.z; dst[j][3 % COLS] = t.w; }
+              else { for (int c = 0; c < COLS; ++c) dst[j][c] = __ldg(src + c); }
+            } else {
+#pragma unroll
+              for (int c = 0; c < COLS; ++c) dst[j][c] = 0.f;
+            }
+          }
+        };
+        load4(wv, 0);
+        for (int e0 = 0; e0 < nd; e0 += 4) {
+          if (e0 + 4 < nd) load4(wn, e0 + 4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (e0 + j < nd) {
+              const float4* q4 = reinterpret_cast<const float4*>(Wq + (e0 + j) * QB);
+#pragma unroll
+              for (int r4 = 0; r4 < QB / 4; ++r4) {
+                const float4 q = q4[r4];
+#pragma unroll
+                for (int c = 0; c < COLS; ++c) {
+                  av[c][r4 * 4 + 0] = fmaf(q.x, wv[j][c], av[c][r4 * 4 + 0]);
+                  av[c][r4 * 4 + 1] = fmaf(q.y, wv[j][c], av[c][r4 * 4 + 1]);
+                  av[c][r4 * 4 + 2] = fmaf(q.z, wv[j][c], av[c][r4 * 4 + 2]);
+                  av[c][r4 * 4 + 3] = fmaf(q.w, wv[j][c], av[c][r4 * 4 + 3]);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) wv[j][c] = wn[j][c];
+        }
+        // add to the accumulators: exclusive phase (between barriers), plain read-modify-write of
+        // whole words (COLS is even, so a thread owns both halves of each word it touches)
+#pragma unroll
+        for (int r = 0; r < QB; ++r)
+#pragma unroll
+          for (int c = 0; c < COLS; c += 2) {
+            const float v0 = av[c][r], v1 = av[c + 1][r];
+            const unsigned add = (v0 > 0.f ? __float2uint_ru(v0) : 0u) | ((v1 > 0.f ? __float2uint_ru(v1) : 0u) << 16);
+            if (add) acc[r * RW + ((cb + c) >> 1)] += add;
+          }
+      }
+    }
+    __syncthreads();
+    PHASE_MARK(2);
+    // ---- phase L: queued segment pieces, one warp per piece; the next piece's row list and first
+    // chunk are loaded while the current piece is processed
+    {
+      int k = warp;
+      int4 Sn = make_int4(0, 0, 0, 0); uint2 rwn = make_uint2(0, 0), ppn = make_uint2(0, 0);
+      if (k < nseg) {
+        Sn = segs[k];
+        if (lane < Sn.w) rwn = __ldg(b.bt + Sn.z + lane);
+        if (Sn.x + lane < Sn.y) ppn = ld_stream(pt + Sn.x + lane);
+      }
+      while (k < nseg) {
+        const int4 S = Sn; const uint2 rw = rwn; uint2 nx = ppn;
+        k += WARPS;
+        if (k < nseg) {
+          Sn = segs[k];
+          if (lane < Sn.w) rwn = __ldg(b.bt + Sn.z + lane);
+          if (Sn.x + lane < Sn.y) ppn = ld_stream(pt + Sn.x + lane);
+        }
+        // the first rows of the dimension's (row, weight) list, broadcast once per piece
+        const unsigned ro0 = __shfl_sync(FULL, rw.x, 0), ro1 = __shfl_sync(FULL, rw.x, 1);
+        const float ws0 = __uint_as_float(__shfl_sync(FULL, rw.y, 0)), ws1 = __uint_as_float(__shfl_sync(FULL, rw.y, 1));
+        int p = S.x + lane;
+        for (int p0 = S.x; p0 < S.y; p0 += 32) {
+          const uint2 pp = nx; const bool ok = p < S.y;
+          p += 32;
+          if (p < S.y) nx = ld_stream(pt + p);
+          const float wc = __uint_as_float(pp.y);
+          unsigned* colp = acc + (pp.x >> 1);
+          const unsigned sh = (pp.x & 1u) << 4;
+          DBG_ASSERT(!ok || pp.x < (unsigned)CR);
+          if (ok) {
+            atomicAdd(colp + ro0, __float2uint_ru(ws0 * wc) << sh);
+            if (S.w > 1) atomicAdd(colp + ro1, __float2uint_ru(ws1 * wc) << sh);
+          }
+          for (int r = 2; r < S.w; ++r) {
+            const unsigned ro = __shfl_sync(FULL, rw.x, r);
+            const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
+            if (ok) atomicAdd(colp + ro, __float2uint_ru(ws * wc) << sh);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    PHASE_MARK(3);
+    // ---- phase 3: epilogue
+    {
+      const long long c0 = (long long)tile * CR;
+      const int q0 = qb * QB;
+      // a query indexed in this call sees its own postings: clear its own accumulator first (IWA:91)
+      if (a.q_local_base >= 0 && tid < QB) {
+        const long long selfc = a.q_local_base + q0 + tid - c0;
+        if (selfc >= 0 && selfc < CR) acc[tid * RW + (int)(selfc >> 1)] &= (selfc & 1) ? 0x0000ffffu : 0xffff0000u;
+      }
+      __syncthreads();
+      PHASE_MARK(7);
+      for (int i = tid * 4; i < nwords; i += NT * 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(acc + i);
+        if ((v.x | v.y | v.z | v.w) == 0) continue;
+        *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
+        const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+        unsigned hot = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                            // plain compares (the SIMD-in-word intrinsics are emulated)
+          const unsigned lo = vv[k] & 0xffffu;
+          if (!DUPKEYS) n_cand += (unsigned)(lo != 0) + (unsigned)(vv[k] > 0xffffu);
+          hot |= (unsigned)(lo != 0 && lo >= b.thr_int) | (unsigned)(vv[k] > 0xffffu && vv[k] >= thr_hi);
+        }
+        if (DUPKEYS || hot) {                                   // rare: something to emit (or key checks)
+          if (tid == 0) ph[6] += 1;
+          const int row = i / RW, wcol = i - row * RW;
+          const int q = q0 + row;
+          long long qkey = 0;
+          if (DUPKEYS) qkey = __ldg(a.q_key + q);
+          unsigned pm = 0;                                      // halves to emit
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const unsigned val = (vv[k >> 1] >> ((k & 1) << 4)) & 0xffffu;
+            if (!val) continue;
+            if (DUPKEYS) { if (__ldg(a.c_key + c0 + (long long)(wcol + (k >> 1)) * 2 + (k & 1)) == qkey) continue; ++n_cand; }
+            if (val >= b.thr_int) pm |= 1u << k;
+          }
+          if (pm) {                                             // one slot claim per thread (<= 8 pairs)
+            unsigned long long slot = atomicAdd(&a.counters[C_PF], (unsigned long long)__popc(pm));
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if ((pm >> k) & 1u) {
+                const unsigned val = (vv[k >> 1] >> ((k & 1) << 4)) & 0xffffu;
+                if (slot < a.out_cap) { a.out_q[slot] = q; a.out_c[slot] = (int32_t)(c0 + (long long)(wcol + (k >> 1)) * 2 + (k & 1)); a.out_est[slot] = (float)val * b.inv_scale; }
+                ++slot;
+              }
+          }
+        }
+      }
+      PHASE_MARK(4);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_post += __shfl_down_sync(FULL, n_post, o);
+    n_cand += __shfl_down_sync(FULL, n_cand, o);
+  }
+  if (lane == 0) { atomicAdd(&a.counters[C_POSTINGS], n_post); atomicAdd(&a.counters[C_CANDS], n_cand); }
+  if (tid == 0) { for (int k = 0; k < 8; ++k) atomicAdd(&a.counters[C_PHASE + k], (unsigned long long)ph[k]); }
+#undef PHASE_MARK
 }
 
 // ------------------------------------------------------------------ K4: fp64 verify

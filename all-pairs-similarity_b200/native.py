@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libapss_b200.so")
+LIB_PATH = os.path.join(_HERE, "libapss_b200_dbg.so" if os.environ.get("APSS_DEBUG_LIB") else "libapss_b200.so")
 
 ABI_VERSION = 1
 SEM_R1, SEM_R0 = 0, 1
@@ -53,6 +53,7 @@ class StatsC(C.Structure):
                 ("bytes_directory", C.c_int64), ("bytes_forward", C.c_int64), ("tot_postings_visited", C.c_int64),
                 ("tot_candidates_unique", C.c_int64), ("tot_pairs", C.c_int64), ("tot_prefilter", C.c_int64),
                 ("score_launches", C.c_int64), ("kernel_launches", C.c_int64), ("tot_score_ms", C.c_double),
+                ("phase_cycles", C.c_int64 * 8),
                 ("frozen", C.c_int32), ("tile_vectors", C.c_int32), ("warps_per_cta", C.c_int32), ("sm_count", C.c_int32)]
 
 
@@ -216,7 +217,9 @@ class Index:
     def stats(self):
         s = StatsC()
         self._check(self._L.apss_get_stats(self._h, C.byref(s)))
-        return {f: getattr(s, f) for f, _ in StatsC._fields_}
+        d = {f: getattr(s, f) for f, _ in StatsC._fields_}
+        d["phase_cycles"] = list(d["phase_cycles"])
+        return d
 
     @property
     def stream_ptr(self):

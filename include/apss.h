@@ -107,6 +107,9 @@ typedef struct apss_stats {
   int64_t score_launches;    /* launches of the scoring kernel so far                                */
   int64_t kernel_launches;   /* all kernels launched by this handle so far                           */
   double tot_score_ms;
+  int64_t phase_cycles[8];   /* last batch, dense-head kernel: CTA-thread-0 cycles summed over CTAs in      */
+                             /* item setup, look-up/short segments, query-weight fill, dense FFMA, tasks,  */
+                             /* epilogue (a diagnostic: where the scoring kernel's time goes)              */
   int32_t frozen;
   int32_t tile_vectors;
   int32_t warps_per_cta;

@@ -42,6 +42,20 @@ A = {0: .6, 1: .8}
 B2 = {1: .8, 2: .6}
 
 
+@pytest.mark.parametrize("algo", [2, 3])
+def test_kats_other_kernels(algo):
+    kv = dict(kernel_variant=algo << 16)
+    _, _, out = run_both([csr_from_dicts([A]), csr_from_dicts([dict(A)])], 64, 0.5, **kv)
+    assert out[1][2] == {(1, 0): .6 * .6 + .8 * .8} and out[1][1].postings_visited == 4 and out[1][1].candidates_unique == 1
+    _, _, out = run_both([csr_from_dicts([A, B2])], 64, 0.5, **kv)
+    assert out[0][2] == {(0, 1): .8 * .8, (1, 0): .8 * .8} and out[0][1].candidates_unique == 2
+    a = {0: .5, 1: .5, 2: .5, 3: .5}; b = {0: .7, 1: .1, 2: .7, 3: .1}
+    _, _, out = run_both([csr_from_dicts([a]), csr_from_dicts([b])], 64, 0.9, **kv)
+    assert out[1][2] == {} and out[1][1].candidates_unique == 1 and out[1][1].postings_visited == 8
+    _, g, out = run_both([csr_from_dicts([A]), csr_from_dicts([dict(A), dict(A)])], 64, 0.5, freeze_after=0, **kv)
+    assert set(out[1][2]) == {(1, 0), (2, 0)}
+
+
 def test_kat_a_b_c():
     _, _, out = run_both([csr_from_dicts([A]), csr_from_dicts([dict(A)])], 64, 0.5)
     ro, rg, gp, _ = out[1]
@@ -81,9 +95,11 @@ def test_kat_g_frozen_and_query_only():
     assert set(out[1][2]) == {(1, 0)} and set(out[2][2]) == {(1, 0)}   # ids continue from the indexed ones
 
 
-def test_kat_h_same_external_id_never_paired():
+@pytest.mark.parametrize("algo", [1, 2, 3])
+def test_kat_h_same_external_id_never_paired(algo):
     keys = [np.array([42]), np.array([42]), np.array([43])]
-    _, _, out = run_both([csr_from_dicts([A]), csr_from_dicts([dict(A)]), csr_from_dicts([dict(A)])], 64, 0.5, keys=keys)
+    _, _, out = run_both([csr_from_dicts([A]), csr_from_dicts([dict(A)]), csr_from_dicts([dict(A)])], 64, 0.5, keys=keys,
+                         kernel_variant=algo << 16)
     assert out[1][2] == {} and out[1][1].candidates_unique == 0
     assert set(out[2][2]) == {(2, 0), (2, 1)} and out[2][1].candidates_unique == 2
 
@@ -122,8 +138,8 @@ def _synth(N, D, nnz, seed, **kw):
     return apss_b200.synth.generate(N, D, nnz, seed=seed, **kw).numpy()
 
 
-@pytest.mark.parametrize("algo", [1, 2])
-@pytest.mark.parametrize("tile,batch", [(128, 100), (256, 333), (3584, 1000), (1024, 4096), (0, 2500)])
+@pytest.mark.parametrize("algo", [1, 2, 3])
+@pytest.mark.parametrize("tile,batch", [(128, 100), (256, 333), (3584, 1000), (1024, 4096), (0, 2500), (256, 7)])
 def test_synthetic_parity_small(tile, batch, algo):
     """Zipf data, several tile sizes / batch sizes (ragged last tile, tiles spanning batches)."""
     N, D, t = 6000, 1 << 12, 0.6
@@ -148,14 +164,16 @@ def variant(algo=0, warps=0, unroll=0, qb=0):
 
 
 @pytest.mark.parametrize("algo,warps,unroll,qb", [(1, 8, 4, 0), (1, 16, 2, 0), (1, 16, 8, 0), (1, 32, 4, 0),
-                                                  (2, 16, 0, 16), (2, 8, 0, 4), (2, 32, 0, 32), (2, 16, 0, 1), (2, 16, 0, 7)])
+                                                  (2, 16, 0, 16), (2, 8, 0, 4), (2, 32, 0, 32), (2, 16, 0, 1), (2, 16, 0, 7),
+                                                  (3, 16, 2, 32), (3, 12, 2, 32), (3, 8, 2, 32), (3, 16, 2, 16), (3, 16, 4, 16),
+                                                  (3, 8, 4, 16), (3, 16, 4, 8)])
 def test_kernel_variants_agree(algo, warps, unroll, qb):
     """row kernel (fp32 plain RMW) and query-block kernel (fixed-point atomics) give identical results"""
     N, D, t = 3000, 1 << 11, 0.5
     data = _synth(N, D, 25, seed=5)
     n = native()
     o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
-    g = n.Index(D, t, tile_vectors=1024, kernel_variant=variant(algo, warps, unroll, qb))
+    g = n.Index(D, t, tile_vectors=1024 if algo != 3 else 512, kernel_variant=variant(algo, warps, unroll, qb))
     assert g.stats()["warps_per_cta"] == warps
     for lo in range(0, N, 1000):
         csr = csr_slice(data, lo, lo + 1000)
@@ -164,14 +182,15 @@ def test_kernel_variants_agree(algo, warps, unroll, qb):
         assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
 
 
-def test_r0_parity_against_faithful_oracle():
+@pytest.mark.parametrize("algo", [1, 2, 3])
+def test_r0_parity_against_faithful_oracle(algo):
     """As-built semantics (first posting list skipped) through the R0 post-filter; vectors with >= 5
     components exercise the Scala HashSet iteration order."""
     N, D, t = 1500, 1 << 9, 0.4
     data = _synth(N, D, 8, seed=3)
     n = native()
     o = orc.Oracle(D, t, semantics=orc.R0, algo=orc.ALGO_FAITHFUL, threads=8)
-    g = n.Index(D, t, semantics=n.SEM_R0, tile_vectors=256)
+    g = n.Index(D, t, semantics=n.SEM_R0, tile_vectors=256, kernel_variant=algo << 16)
     dropped = 0
     for lo in range(0, N, 500):
         csr = csr_slice(data, lo, lo + 500)
@@ -182,14 +201,17 @@ def test_r0_parity_against_faithful_oracle():
     assert dropped > 0
 
 
-def test_index_threshold_and_unnormalised_values():
-    """Value prune changes what is scored (Q6); inputs need not be unit-norm (Q8)."""
-    N, D, t = 2000, 1 << 10, 0.3
+@pytest.mark.parametrize("algo,scale", [(1, 1.7), (2, 1.7), (3, 1.7), (2, 1e6), (3, 1e-6)])
+def test_index_threshold_and_unnormalised_values(algo, scale):
+    """Value prune changes what is scored (Q6); inputs need not be unit-norm (Q8): the fixed-point
+    scale follows the largest squared norm seen."""
+    N, D = 2000, 1 << 10
     ip, ix, v = _synth(N, D, 20, seed=9)
-    v = v * 1.7
+    v = v * scale
+    t, ith = 0.3 * scale * scale, 0.12 * scale
     n = native()
-    o = orc.Oracle(D, t, 0.12, algo=orc.ALGO_FAST, threads=8)
-    g = n.Index(D, t, 0.12, tile_vectors=512)
+    o = orc.Oracle(D, t, ith, algo=orc.ALGO_FAST, threads=8)
+    g = n.Index(D, t, ith, tile_vectors=512, kernel_variant=algo << 16)
     for lo in range(0, N, 700):
         csr = csr_slice((ip, ix, v), lo, min(N, lo + 700))
         ro = o.insert_batch(*csr); rg = g.insert_batch(*csr)
@@ -198,13 +220,14 @@ def test_index_threshold_and_unnormalised_values():
         assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
 
 
-def test_pair_buffer_overflow_grows_and_replays():
+@pytest.mark.parametrize("algo", [1, 3])
+def test_pair_buffer_overflow_grows_and_replays(algo):
     """Threshold 0 makes every candidate a pair: far more than the initial pair buffer."""
     N, D = 1500, 1 << 8
     data = _synth(N, D, 10, seed=2, dup_frac=0.0)
     n = native()
     o = orc.Oracle(D, 0.0, algo=orc.ALGO_FAST, threads=8)
-    g = n.Index(D, 0.0, tile_vectors=256, reserve_pairs=1024)
+    g = n.Index(D, 0.0, tile_vectors=256, reserve_pairs=1024, kernel_variant=algo << 16)
     ro = o.insert_batch(*data); rg = g.insert_batch(*data)
     assert rg.n_pairs == len(ro.sim) == ro.candidates_unique > 1024
     assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
@@ -226,14 +249,15 @@ def test_device_pointer_entry_matches_host_entry():
         assert (r1.postings_visited, r1.candidates_unique) == (r2.postings_visited, r2.candidates_unique)
 
 
-def test_c2_scale_sampled_parity():
+@pytest.mark.parametrize("algo", [1, 3])
+def test_c2_scale_sampled_parity(algo):
     """Config C2 shape (2^16 dims, nnz ~50, t=0.8) at 30K vectors: full parity + invariants."""
     import apss_b200
     N, D, t, B = 30000, 1 << 16, 0.8, 4096
     data = apss_b200.synth.generate(N, D, 50, seed=20260102).numpy()
     n = native()
     o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=orc.max_threads())
-    g = n.Index(D, t)
+    g = n.Index(D, t, kernel_variant=algo << 16)
     seen = {}
     for lo in range(0, N, B):
         hi = min(N, lo + B)
