@@ -235,6 +235,10 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
     if (h->fwd_ptr.reserve(nv + 1, 0, h->stream) != cudaSuccess || h->gid.reserve(nv, 0, h->stream) != cudaSuccess ||
         h->key.reserve(nv, 0, h->stream) != cudaSuccess || h->dir.reserve((size_t)nt * ((size_t)cfg->dim + 1), 0, h->stream) != cudaSuccess ||
         h->tile_base.reserve(nt + 1, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+    if (algo == 3 && (h->dn_cnt.reserve(nt, 0, h->stream) != cudaSuccess || h->tile_cnt.reserve(nt, 0, h->stream) != cudaSuccess ||
+                      h->dn_dim.reserve((size_t)nt * KD, 0, h->stream) != cudaSuccess || h->dn_len.reserve((size_t)nt * KD, 0, h->stream) != cudaSuccess ||
+                      h->dn_hash.reserve((size_t)nt * HS, 0, h->stream) != cudaSuccess || h->dn_w.reserve((size_t)nt * KD * CR, 0, h->stream) != cudaSuccess))
+      return bail(APSS_E_NOMEM);
   }
   if (cfg->reserve_nnz > 0) {
     if (h->fwd_idx.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess || h->fwd_val.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess ||

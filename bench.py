@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true", help="per-step timings on stderr")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed value region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--cpu-index", type=int, default=50_000, help="index sample size for the CPU arms")
@@ -273,7 +274,11 @@ def main():
     ev0.record(lib_stream)
     tot = dict(cands=0, pairs=0, postings=0, score_ms=0.0, local_postings=0, items=0)
     for _ in range(K):
+        ts_ = time.time()
         r = step_device(cursor); cursor += B
+        if args.verbose and rank == 0:
+            print("value step: wall %.1f ms score %.1f ms device %.1f ms pairs %d prefilter %d" % (
+                (time.time() - ts_) * 1e3, r.local.score_ms, r.local.device_ms, r.n_pairs, r.local.n_prefilter), file=sys.stderr, flush=True)
         tot["cands"] += r.candidates_unique; tot["pairs"] += r.n_pairs; tot["postings"] += r.postings_visited
         tot["score_ms"] += r.local.score_ms; tot["local_postings"] += r.local.postings_visited; tot["items"] += r.local.work_items
     ev1.record(lib_stream)
@@ -300,8 +305,13 @@ def main():
     def step_host(k):
         if world == 1:
             ip, ix, v = host_batches[k]
+            ts_ = time.time()
             r = eng.insert_batch(ip.numpy(), ix.numpy(), v.numpy())      # H2D inside the call
+            tm_ = time.time()
             eng.fetch_pairs(out_q.numpy(), out_c.numpy(), out_s.numpy())  # D2H of the result
+            if args.verbose:
+                print("e2e step: insert %.1f ms fetch %.1f ms score %.1f ms device %.1f ms pairs %d prefilter %d" % (
+                    (tm_ - ts_) * 1e3, (time.time() - tm_) * 1e3, r.score_ms, r.device_ms, r.n_pairs, r.n_prefilter), file=sys.stderr, flush=True)
             return r.candidates_unique, r.n_pairs, ip.numel() * 8 + ix.numel() * 4 + v.numel() * 8, r.n_pairs * 16
         ip, ix, v = host_batches[k] if rank == 0 else (None, None, None)
         r = disp.insert_batch(ip, ix, v)                                  # rank 0: pinned host -> device -> broadcast; pairs -> host
