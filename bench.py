@@ -358,7 +358,10 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None if not traffic else traffic.get("dram_bytes_per_launch"),
-                     "peak_source": peak_src, "kernel": "apss::k_score", "launches_timed": score_launches,
+                     "traffic_source": None if not traffic else traffic.get("kernel"),
+                     "peak_source": peak_src,
+                     "kernel": {1: "apss::k_score", 2: "apss::k_score_blk"}.get((args.variant >> 16) & 0xff, "apss::k_score_dense"),
+                     "launches_timed": score_launches,
                      "algorithmic_bytes_per_launch": 8.0 * tot["local_postings"] / max(score_launches, 1),
                      "avg_launch_ms": tot["score_ms"] / max(score_launches, 1),
                      "kernel_share_of_step": tot["score_ms"] * 1e-3 / dt_value,

@@ -275,3 +275,24 @@ def test_c2_scale_sampled_parity(algo):
             assert seen[(c, q)] == s and q // B == c // B
         else:
             assert q // B > c // B
+
+
+def test_dispatcher_single_rank_device_path():
+    """ShardDispatcher with one rank (no process group): device tensors in, global ids out."""
+    import torch
+    import apss_b200
+    from apss_b200.dispatcher import ShardDispatcher
+    N, D, t, B = 4000, 1 << 11, 0.5, 1000
+    data = _synth(N, D, 25, seed=31)
+    n = native()
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
+    disp = ShardDispatcher(n.Index(D, t, tile_vectors=512), device="cuda:0")
+    disp.preload(*[torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in csr_slice(data, 0, B)])
+    o.insert_batch(*csr_slice(data, 0, B), index_only=True)
+    for lo in range(B, N, B):
+        csr = csr_slice(data, lo, lo + B)
+        r = disp.insert_batch(*[torch.from_numpy(np.ascontiguousarray(a)) for a in csr])
+        ro = o.insert_batch(*csr)
+        got = {(int(r.id_base + q), int(c)): float(s) for q, c, s in zip(r.q, r.c, r.sim)}
+        assert_pairs_equal(got, ro.pair_set())
+        assert (r.postings_visited, r.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
