@@ -67,7 +67,7 @@ struct apss_handle {
   DevBuf<unsigned long long> s_keys_in, s_keys_out, s_vals_in; DevBuf<int64_t> s_tile_start; DevBuf<char> cub_tmp;
   // dense-head tiles (algo 3)
   DevBuf<int32_t> dn_cnt, dn_dim, dn_len, tile_cnt; DevBuf<int2> dn_hash; DevBuf<float> dn_w; DevBuf<unsigned long long> s_vals_out;
-  int dense_shift = 2, COLS = 4;
+  int dense_shift = 2, COLS = 4, ctas_per_sm = 1, seg_cap = SEG_CAP;
   // query-block transposition (v2 kernel)
   DevBuf<unsigned long long> bt_keys_in, bt_keys_out, bt_vals_in, bt_vals_out, ud_key; DevBuf<int32_t> bt_flags, bt_pos, ud_dim, ud_start, bd_ptr;
   // outputs
@@ -144,7 +144,7 @@ static cudaError_t launch_dense_t(apss_handle* h, const ScoreArgs& a, const Bloc
   auto kern = dup ? k_score_dense<QB, WARPS, COLS, true> : k_score_dense<QB, WARPS, COLS, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   if (e != cudaSuccess) return e;
-  kern<<<h->sm_count, WARPS * 32, h->smem_bytes, h->stream>>>(a, b, d);
+  kern<<<h->sm_count * h->ctas_per_sm, WARPS * 32, h->smem_bytes, h->stream>>>(a, b, d);
   return cudaGetLastError();
 }
 
@@ -177,7 +177,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   cudaDeviceProp prop{};
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return bail(APSS_E_NO_DEVICE);
   h->sm_count = prop.multiProcessorCount;
-  const size_t max_smem = prop.sharedMemPerBlockOptin;
+  const size_t max_smem1 = prop.sharedMemPerBlockOptin;
   // kernel_variant: bits 0-7 unroll (row kernel), 8-15 warps per CTA, 16-23 algorithm (0/2 = query-block
   // kernel with fixed-point atomics, 1 = warp-per-(query, tile) row kernel), 24-31 queries per block
   int algo = (cfg->kernel_variant >> 16) & 0xff;   // 0 = default
@@ -187,7 +187,11 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (QB > 32) QB = 32;   // a dimension's row list is staged one entry per lane
   if (algo == 3 && QB != 8 && QB != 16 && QB != 32) QB = qb_given ? 32 : 16;
   size_t blk_extra = (size_t)LONG_CAP * 16 + (size_t)(LONG_CAP + 1) * 4 + 64;
-  if (algo == 3) blk_extra = (size_t)SEG_CAP * 16 + 64 + (size_t)KD * QB * 4 + (size_t)KD * 16 + (size_t)HS * 8;
+  const int want_w = (cfg->kernel_variant >> 8) & 0xff;
+  const int ctas = (algo == 3 && want_w == 8) ? 2 : 1;          // 8-warp CTAs run two per SM
+  const int seg_cap = ctas == 2 ? 640 : SEG_CAP;
+  if (algo == 3) blk_extra = (size_t)seg_cap * 16 + 64 + (size_t)KD * QB * 4 + (size_t)KD * 16 + (size_t)HS * 8;
+  const size_t max_smem = ctas == 2 ? (prop.sharedMemPerMultiprocessor / 2 - 1024) : max_smem1;
   const size_t acc_bytes = algo == 3 ? 2 : 4;   // u16 packed (dense-head kernel) or u32 / fp32
   int CR = cfg->tile_vectors;
   if (CR <= 0) {
@@ -221,6 +225,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   }
   if (!warps) return bail(APSS_E_INVALID);
   h->CR = CR; h->WARPS = warps; h->variant = cfg->kernel_variant; h->algo = algo; h->QB = QB;
+  h->ctas_per_sm = ctas; h->seg_cap = seg_cap;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(APSS_E_CUDA);
   if (cudaMalloc(&h->d_counters, C_COUNT * sizeof(unsigned long long)) != cudaSuccess) return bail(APSS_E_NOMEM);
   if (cudaMallocHost(&h->h_counters, C_COUNT * sizeof(unsigned long long)) != cudaSuccess) return bail(APSS_E_NOMEM);
@@ -497,7 +502,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     a.thr_emit = thr_emit;
     a.out_q = h->pf_q.p; a.out_c = h->pf_c.p; a.out_est = h->pf_est.p; a.out_cap = h->pf_q.cap;
     a.counters = h->d_counters;
-    a.tile_cnt = h->algo == 3 ? h->tile_cnt.p : nullptr; a.post_cap = (long long)h->post.cap;
+    a.tile_cnt = h->algo == 3 ? h->tile_cnt.p : nullptr; a.post_cap = (long long)h->post.cap; a.seg_cap = h->seg_cap;
     a.total_items = (unsigned long long)h->ntiles * (unsigned long long)n;
     CK(cudaMemsetAsync(h->d_counters, 0, 7 * sizeof(unsigned long long), s));   // keep the prefilter tallies
     CK(cudaMemsetAsync(h->d_counters + C_PHASE, 0, 8 * sizeof(unsigned long long), s));

@@ -169,6 +169,7 @@ struct ScoreArgs {
   unsigned long long* counters;
   unsigned long long total_items;
   const int32_t* tile_cnt;   // debug builds: sparse postings per tile (bounds checks)
+  int32_t seg_cap;           // dense-head kernel: capacity of the per-item segment queue
   long long post_cap;        // debug builds: capacity of post[]
 };
 
@@ -627,9 +628,9 @@ __global__ void k_dir_fix(int ntiles_aff, int D, int64_t tile0, const int32_t* _
 // Scoring kernel for dense-head tiles.  Same work items, fixed-point accumulators, sparse phases and
 // epilogue as k_score_blk; in addition the dimensions of the query block that are dense in the tile
 // are applied by FFMA: thread = COLS adjacent candidates x all QB query rows in registers.
-static constexpr int SEG_CAP = 1280;    // sparse segments longer than SPLIT, per work item (shared memory)
+static constexpr int SEG_CAP = 1280;    // max queued segment pieces per work item (shared memory); ScoreArgs.seg_cap <= this
 static constexpr int SPLIT = 8;         // segments up to this length are walked by the lane that looked them up
-static constexpr int SEG_PIECE = 512;   // queued segments are cut into pieces of at most this many postings
+static constexpr int SEG_PIECE = 256;   // queued segments are cut into pieces of at most this many postings
 
 // Accumulators of the dense-head kernel are u16 fixed point, two per 32-bit word: word (row*CR + c)/2,
 // half c & 1 (CR is even).  An update is one native shared atomic add of (value << 16*(c&1)); halves
@@ -675,7 +676,7 @@ __device__ __forceinline__ void lane_walk(unsigned* acc, const uint2* __restrict
 //            compaction, clear
 // bt entries for this kernel hold (row * CR / 2, weight * 2^F).
 template <int QB, int WARPS, int COLS, bool DUPKEYS>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_score_dense(const ScoreArgs a, const BlockArgs b, const DenseTiles dt) {
+__global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dense(const ScoreArgs a, const BlockArgs b, const DenseTiles dt) {
   extern __shared__ __align__(16) unsigned smem_u[];
   const int CR = a.CR;
   const int RW = CR >> 1;                                               // words per accumulator row
@@ -685,20 +686,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_dense(const ScoreArgs a
   int2* hsh = reinterpret_cast<int2*>(dl + KD);                         // [HS]
   int4* segs = reinterpret_cast<int4*>(hsh + HS);                       // [SEG_CAP] (s, e, rs, nr)
   __shared__ unsigned long long s_item;
-  __shared__ int s_nseg, s_segvalid, s_ndense;
+  __shared__ int s_nseg, s_segvalid, s_ndense, s_next;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   constexpr int NT = WARPS * 32;
   const int nwords = QB * RW;
   for (int i = tid * 4; i < nwords; i += NT * 4) *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
   unsigned long long n_post = 0, n_cand = 0;
+#ifdef APSS_PHASE_TIMERS
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tc = clock64();
 #define PHASE_MARK(k) do { if (tid == 0) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; } } while (0)
+#else
+#define PHASE_MARK(k) ((void)0)
+#endif
   const unsigned thr_hi = b.thr_int << 16;   // high half >= thr  <=>  word >= thr << 16
 
   for (;;) {
     __syncthreads();
     PHASE_MARK(5);
-    if (tid == 0) { s_item = atomicAdd(&a.counters[C_WORK], 1ULL); s_nseg = 0; s_segvalid = SEG_CAP; s_ndense = 0; }
+    if (tid == 0) { s_item = atomicAdd(&a.counters[C_WORK], 1ULL); s_nseg = 0; s_segvalid = a.seg_cap; s_ndense = 0; s_next = 0; }
     __syncthreads();
     const unsigned long long item = s_item;
     if (item >= a.total_items) break;
@@ -742,7 +747,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_dense(const ScoreArgs a
       if (len > SPLIT) {                      // queue in pieces of <= SEG_PIECE postings (balance across warps)
         const int np = (len + SEG_PIECE - 1) / SEG_PIECE;
         const int k = atomicAdd(&s_nseg, np);
-        if (k + np <= SEG_CAP) { for (int j = 0; j < np; ++j) segs[k + j] = make_int4(s + j * SEG_PIECE, min(e, s + (j + 1) * SEG_PIECE), rs, nr); }
+        if (k + np <= a.seg_cap) { for (int j = 0; j < np; ++j) segs[k + j] = make_int4(s + j * SEG_PIECE, min(e, s + (j + 1) * SEG_PIECE), rs, nr); }
         else { atomicMin(&s_segvalid, k); coop = true; }      // the cursor only grows: later reservations fail too
       }
       lane_walk(acc, pt, b.bt, s, len <= SPLIT ? e : s, rs, nr, rw0, nwords, CR);
@@ -770,6 +775,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_dense(const ScoreArgs a
     PHASE_MARK(1);
     const int nd = s_ndense;
     const int nseg = min(s_nseg, s_segvalid);
+    // pad the dense list to a multiple of 4 with entries whose query weights stay zero (Wq is cleared per item)
+    if (tid < 4 && nd + tid < ((nd + 3) & ~3)) dl[nd + tid] = make_int4(0, 0, 0, 0);
     // ---- Wq[entry][row] from the block's row lists
     for (int k = warp; k < nd; k += WARPS) {
       const int4 e = dl[k];
@@ -793,36 +800,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_dense(const ScoreArgs a
         auto load4 = [&](float (&dst)[4][COLS], int e0) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int e = e0 + j;
-            if (e < nd) {
-              DBG_ASSERT(dl[e].x >= 0 && dl[e].x < KD && cb + COLS <= CR);
-              const float* src = wbase + (size_t)dl[e].x * CR + cb;
-              if (COLS == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(src)); dst[j][0] = t.x; dst[j][COLS - 1] = t.y; }
-              else if (COLS == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(src)); dst[j][0] = t.x; dst[j][1 % COLS] = t.y; dst[j][2 % COLS] = t.z; dst[j][3 % COLS] = t.w; }
-              else { for (int c = 0; c < COLS; ++c) dst[j][c] = __ldg(src + c); }
-            } else {
-#pragma unroll
-              for (int c = 0; c < COLS; ++c) dst[j][c] = 0.f;
-            }
+            const float* src = wbase + (size_t)dl[e0 + j].x * CR + cb;
+            if (COLS == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(src)); dst[j][0] = t.x; dst[j][COLS - 1] = t.y; }
+            else if (COLS == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(src)); dst[j][0] = t.x; dst[j][1 % COLS] = t.y; dst[j][2 % COLS] = t.z; dst[j][3 % COLS] = t.w; }
+            else { for (int c = 0; c < COLS; ++c) dst[j][c] = __ldg(src + c); }
           }
         };
+        const int nd4 = (nd + 3) & ~3;
         load4(wv, 0);
-        for (int e0 = 0; e0 < nd; e0 += 4) {
-          if (e0 + 4 < nd) load4(wn, e0 + 4);
+        for (int e0 = 0; e0 < nd4; e0 += 4) {
+          if (e0 + 4 < nd4) load4(wn, e0 + 4);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (e0 + j < nd) {
-              const float4* q4 = reinterpret_cast<const float4*>(Wq + (e0 + j) * QB);
+            const float4* q4 = reinterpret_cast<const float4*>(Wq + (e0 + j) * QB);
 #pragma unroll
-              for (int r4 = 0; r4 < QB / 4; ++r4) {
-                const float4 q = q4[r4];
+            for (int r4 = 0; r4 < QB / 4; ++r4) {
+              const float4 q = q4[r4];
 #pragma unroll
-                for (int c = 0; c < COLS; ++c) {
-                  av[c][r4 * 4 + 0] = fmaf(q.x, wv[j][c], av[c][r4 * 4 + 0]);
-                  av[c][r4 * 4 + 1] = fmaf(q.y, wv[j][c], av[c][r4 * 4 + 1]);
-                  av[c][r4 * 4 + 2] = fmaf(q.z, wv[j][c], av[c][r4 * 4 + 2]);
-                  av[c][r4 * 4 + 3] = fmaf(q.w, wv[j][c], av[c][r4 * 4 + 3]);
-                }
+              for (int c = 0; c < COLS; ++c) {
+                av[c][r4 * 4 + 0] = fmaf(q.x, wv[j][c], av[c][r4 * 4 + 0]);
+                av[c][r4 * 4 + 1] = fmaf(q.y, wv[j][c], av[c][r4 * 4 + 1]);
+                av[c][r4 * 4 + 2] = fmaf(q.z, wv[j][c], av[c][r4 * 4 + 2]);
+                av[c][r4 * 4 + 3] = fmaf(q.w, wv[j][c], av[c][r4 * 4 + 3]);
               }
             }
           }
@@ -845,46 +844,58 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_dense(const ScoreArgs a
     }
     __syncthreads();
     PHASE_MARK(2);
-    // ---- phase L: queued segment pieces, one warp per piece; the next piece's row list and first
-    // chunk are loaded while the current piece is processed
+    // ---- phase L: queued segment pieces (<= SEG_PIECE = 256 postings), one warp per piece, handed out
+    // dynamically.  A lane keeps the piece's 8 postings (one per 32-posting chunk) in registers: 8
+    // independent load -> FMUL -> F2I -> shift -> ATOMS chains, and each register slot is refilled with
+    // the NEXT piece's chunk as soon as it has been consumed.  Chunks past the end of the piece are
+    // skipped warp-uniformly; only the last chunk is predicated per lane.
     {
-      int k = warp;
-      int4 Sn = make_int4(0, 0, 0, 0); uint2 rwn = make_uint2(0, 0), ppn = make_uint2(0, 0);
+      constexpr int NCH = SEG_PIECE / 32;
+      int k = 0;
+      if (lane == 0) k = atomicAdd(&s_next, 1);
+      k = __shfl_sync(FULL, k, 0);
+      int4 S = make_int4(0, 0, 0, 0); uint2 rw = make_uint2(0, 0); uint2 pn[NCH];
       if (k < nseg) {
-        Sn = segs[k];
-        if (lane < Sn.w) rwn = __ldg(b.bt + Sn.z + lane);
-        if (Sn.x + lane < Sn.y) ppn = ld_stream(pt + Sn.x + lane);
+        S = segs[k];
+        if (lane < S.w) rw = __ldg(b.bt + S.z + lane);
+      }
+#pragma unroll
+      for (int u = 0; u < NCH; ++u) {
+        const int p = S.x + lane + 32 * u;
+        pn[u] = make_uint2(0u, 0u);
+        if (p < S.y) pn[u] = ld_stream(pt + p);
       }
       while (k < nseg) {
-        const int4 S = Sn; const uint2 rw = rwn; uint2 nx = ppn;
-        k += WARPS;
+        if (lane == 0) k = atomicAdd(&s_next, 1);
+        k = __shfl_sync(FULL, k, 0);
+        int4 Sn = make_int4(0, 0, 0, 0); uint2 rwn = make_uint2(0, 0);
         if (k < nseg) {
           Sn = segs[k];
           if (lane < Sn.w) rwn = __ldg(b.bt + Sn.z + lane);
-          if (Sn.x + lane < Sn.y) ppn = ld_stream(pt + Sn.x + lane);
         }
-        // the first rows of the dimension's (row, weight) list, broadcast once per piece
         const unsigned ro0 = __shfl_sync(FULL, rw.x, 0), ro1 = __shfl_sync(FULL, rw.x, 1);
         const float ws0 = __uint_as_float(__shfl_sync(FULL, rw.y, 0)), ws1 = __uint_as_float(__shfl_sync(FULL, rw.y, 1));
-        int p = S.x + lane;
-        for (int p0 = S.x; p0 < S.y; p0 += 32) {
-          const uint2 pp = nx; const bool ok = p < S.y;
-          p += 32;
-          if (p < S.y) nx = ld_stream(pt + p);
-          const float wc = __uint_as_float(pp.y);
-          unsigned* colp = acc + (pp.x >> 1);
-          const unsigned sh = (pp.x & 1u) << 4;
-          DBG_ASSERT(!ok || pp.x < (unsigned)CR);
-          if (ok) {
-            atomicAdd(colp + ro0, __float2uint_ru(ws0 * wc) << sh);
-            if (S.w > 1) atomicAdd(colp + ro1, __float2uint_ru(ws1 * wc) << sh);
-          }
-          for (int r = 2; r < S.w; ++r) {
-            const unsigned ro = __shfl_sync(FULL, rw.x, r);
-            const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
-            if (ok) atomicAdd(colp + ro, __float2uint_ru(ws * wc) << sh);
+        unsigned* base0 = acc + ro0; unsigned* base1 = acc + ro1;
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+          const uint2 pp = pn[u];
+          const int pnx = Sn.x + lane + 32 * u;
+          if (pnx < Sn.y) pn[u] = ld_stream(pt + pnx);           // refill the slot with the next piece's chunk
+          if (S.x + 32 * u < S.y) {                               // warp-uniform: chunk u exists in this piece
+            const bool ok = S.x + lane + 32 * u < S.y;           // only the last chunk is partial
+            DBG_ASSERT(!ok || pp.x < (unsigned)CR);
+            const float wc = __uint_as_float(pp.y);
+            const unsigned w = pp.x >> 1, sh = (pp.x & 1u) << 4;
+            if (ok) atomicAdd(base0 + w, __float2uint_ru(ws0 * wc) << sh);
+            if (S.w > 1 && ok) atomicAdd(base1 + w, __float2uint_ru(ws1 * wc) << sh);
+            for (int r = 2; r < S.w; ++r) {
+              const unsigned ro = __shfl_sync(FULL, rw.x, r);
+              const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
+              if (ok) atomicAdd(acc + ro + w, __float2uint_ru(ws * wc) << sh);
+            }
           }
         }
+        S = Sn; rw = rwn;
       }
     }
     __syncthreads();
@@ -913,7 +924,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_dense(const ScoreArgs a
           hot |= (unsigned)(lo != 0 && lo >= b.thr_int) | (unsigned)(vv[k] > 0xffffu && vv[k] >= thr_hi);
         }
         if (DUPKEYS || hot) {                                   // rare: something to emit (or key checks)
+#ifdef APSS_PHASE_TIMERS
           if (tid == 0) ph[6] += 1;
+#endif
           const int row = i / RW, wcol = i - row * RW;
           const int q = q0 + row;
           long long qkey = 0;
@@ -947,7 +960,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_dense(const ScoreArgs a
     n_cand += __shfl_down_sync(FULL, n_cand, o);
   }
   if (lane == 0) { atomicAdd(&a.counters[C_POSTINGS], n_post); atomicAdd(&a.counters[C_CANDS], n_cand); }
+#ifdef APSS_PHASE_TIMERS
   if (tid == 0) { for (int k = 0; k < 8; ++k) atomicAdd(&a.counters[C_PHASE + k], (unsigned long long)ph[k]); }
+#endif
 #undef PHASE_MARK
 }
 
