@@ -296,3 +296,34 @@ def test_dispatcher_single_rank_device_path():
         got = {(int(r.id_base + q), int(c)): float(s) for q, c, s in zip(r.q, r.c, r.sim)}
         assert_pairs_equal(got, ro.pair_set())
         assert (r.postings_visited, r.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+
+
+@pytest.mark.parametrize("sem", ["R1", "R0"])
+def test_c1_maildir_fixture_parity(sem):
+    """Config C1: TF-IDF vectors of the reference's own corpus (a 1536-mail sample of data/maildir_small,
+    fixture pinned by the reference's CRC side files, see tests/test_etl.py), L2-normalised as
+    LoadGenerator.scala:35-37 does, D = 2^20, cosine >= 0.9, batches of 256."""
+    import os
+    import apss_b200
+    from apss_b200 import etl
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "maildir_small_tfidf_sample.npz"))
+    ip, ix = g["indptr"], g["indices"]
+    v = etl.l2_normalise(ip, g["values"])
+    D, t, B = etl.NUM_FEATURES, 0.9, 256
+    n = native()
+    N = len(ip) - 1 if sem == "R1" else 512
+    o = orc.Oracle(D, t, semantics=orc.R0 if sem == "R0" else orc.R1, algo=orc.ALGO_FAITHFUL if sem == "R0" else orc.ALGO_FAST,
+                   threads=orc.max_threads())
+    gi = n.Index(D, t, semantics=n.SEM_R0 if sem == "R0" else n.SEM_R1)
+    pairs = 0
+    for lo in range(0, N, B):
+        csr = csr_slice((ip, ix, v), lo, min(N, lo + B))
+        fd = orc.first_dims(*csr) if sem == "R0" else None
+        ro = o.insert_batch(*csr)
+        rg = gi.insert_batch(*csr, first_dim=fd)
+        assert_pairs_equal(gpu_pairs(gi, rg), ro.pair_set())
+        assert list(gi.fetch_status(len(csr[0]) - 1)) == list(ro.status)
+        if sem == "R1":
+            assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+        pairs += rg.n_pairs
+    assert pairs > 100          # the corpus is full of duplicated mails (sent vs sent_items ...)
