@@ -635,8 +635,14 @@ static constexpr int SEG_PIECE = 256;   // queued segments are cut into pieces o
 // Accumulators of the dense-head kernel are u16 fixed point, two per 32-bit word: word (row*CR + c)/2,
 // half c & 1 (CR is even).  An update is one native shared atomic add of (value << 16*(c&1)); halves
 // cannot carry into each other because every sum is < 2^16 by the choice of the scale.
+// float -> fixed point without the (slow, XU-pipe) F2I: for 0 <= p < 2^22, fmaf(ws, wc, 2^23 + 1) has the
+// integer round(p + 1) in its low mantissa bits.  round(p + 1) >= ceil(p) >= 1: every contribution is at
+// least one quantum and never below the exact product, and over-shoots by at most 1.5 quanta.
+__device__ __forceinline__ unsigned fx_contrib(float ws, float wc) {
+  return __float_as_uint(fmaf(ws, wc, 8388609.0f)) & 0x7fffffu;
+}
 __device__ __forceinline__ void acc_add16(unsigned* acc, unsigned rowoff_words, unsigned c, float ws, float wc) {
-  atomicAdd(acc + rowoff_words + (c >> 1), __float2uint_ru(ws * wc) << ((c & 1u) << 4));
+  atomicAdd(acc + rowoff_words + (c >> 1), fx_contrib(ws, wc) << ((c & 1u) << 4));
 }
 
 // apply postings [p, pe) (<= SPLIT of them) of one sparse segment to the rows [rs, rs+nr) of the block:
@@ -886,12 +892,12 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
             DBG_ASSERT(!ok || pp.x < (unsigned)CR);
             const float wc = __uint_as_float(pp.y);
             const unsigned w = pp.x >> 1, sh = (pp.x & 1u) << 4;
-            if (ok) atomicAdd(base0 + w, __float2uint_ru(ws0 * wc) << sh);
-            if (S.w > 1 && ok) atomicAdd(base1 + w, __float2uint_ru(ws1 * wc) << sh);
+            if (ok) atomicAdd(base0 + w, fx_contrib(ws0, wc) << sh);
+            if (S.w > 1 && ok) atomicAdd(base1 + w, fx_contrib(ws1, wc) << sh);
             for (int r = 2; r < S.w; ++r) {
               const unsigned ro = __shfl_sync(FULL, rw.x, r);
               const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
-              if (ok) atomicAdd(acc + ro + w, __float2uint_ru(ws * wc) << sh);
+              if (ok) atomicAdd(acc + ro + w, fx_contrib(ws, wc) << sh);
             }
           }
         }
