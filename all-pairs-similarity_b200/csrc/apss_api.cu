@@ -4,6 +4,7 @@
 #include "apss_kernels.cuh"
 
 #include <cub/cub.cuh>
+#include <cuda.h>   // driver types only; entry points are resolved at run time (no libcuda link)
 
 #include <algorithm>
 #include <cmath>
@@ -38,6 +39,100 @@ struct DevBuf {
   size_t bytes() const { return cap * sizeof(T); }
 };
 
+// ---- growable device array backed by CUDA virtual memory management: one virtual range is reserved up
+// front, physical chunks are mapped behind it as the index grows.  The pointer never moves, growth copies
+// nothing and frees nothing (a cudaMalloc + copy + cudaFree of a few hundred MB stalls a live index for
+// ~1 s), and the arrays can grow to the whole 180 GB of HBM without a 2x peak.
+struct VmApi {
+  CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false;
+};
+
+static VmApi& vm_api() {
+  static VmApi api = [] {
+    VmApi a;
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult st;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess && *fn;
+    };
+    a.ok = get("cuMemAddressReserve", (void**)&a.AddressReserve) && get("cuMemAddressFree", (void**)&a.AddressFree) &&
+           get("cuMemCreate", (void**)&a.Create) && get("cuMemRelease", (void**)&a.Release) && get("cuMemMap", (void**)&a.Map) &&
+           get("cuMemUnmap", (void**)&a.Unmap) && get("cuMemSetAccess", (void**)&a.SetAccess) &&
+           get("cuMemGetAllocationGranularity", (void**)&a.GetGranularity);
+    if (getenv("APSS_NO_VMM")) a.ok = false;
+    cudaGetLastError();
+    return a;
+  }();
+  return api;
+}
+
+template <typename T>
+struct VmBuf {
+  T* p = nullptr;
+  size_t cap = 0;                       // elements backed by physical memory
+  int device = 0;
+  size_t va_bytes = 0, mapped = 0, gran = 0;
+  std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
+  bool vmm = false;
+  DevBuf<T> fallback;                   // used when the VMM entry points are unavailable
+
+  cudaError_t reserve(size_t n, size_t keep, cudaStream_t s) {
+    if (n <= cap) return cudaSuccess;
+    VmApi& api = vm_api();
+    if (!api.ok || (p && !vmm)) {
+      cudaError_t e = fallback.reserve(n, keep, s);
+      p = fallback.p; cap = fallback.cap;
+      return e;
+    }
+    CUmemAllocationProp prop{};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED; prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE; prop.location.id = device;
+    if (!p) {
+      if (api.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || !gran) gran = 2u << 20;
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      va_bytes = ((std::max<size_t>(total_b, (size_t)1 << 30) + gran - 1) / gran) * gran;    // never more than the whole HBM
+      CUdeviceptr va = 0;
+      if (api.AddressReserve(&va, va_bytes, 0, 0, 0) != CUDA_SUCCESS) {                      // fall back for good
+        cudaError_t e = fallback.reserve(n, keep, s);
+        p = fallback.p; cap = fallback.cap;
+        return e;
+      }
+      p = reinterpret_cast<T*>(va); vmm = true;
+    }
+    size_t want = std::max(n * sizeof(T), mapped + mapped / 4);      // geometric, 25 %
+    want = ((want + gran - 1) / gran) * gran;
+    if (want > va_bytes) return cudaErrorMemoryAllocation;
+    const size_t add = want - mapped;
+    CUmemGenericAllocationHandle hnd;
+    if (api.Create(&hnd, add, &prop, 0) != CUDA_SUCCESS) return cudaErrorMemoryAllocation;
+    if (api.Map((CUdeviceptr)p + mapped, add, 0, hnd, 0) != CUDA_SUCCESS) { api.Release(hnd); return cudaErrorMemoryAllocation; }
+    CUmemAccessDesc acc{};
+    acc.location = prop.location; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (api.SetAccess((CUdeviceptr)p + mapped, add, &acc, 1) != CUDA_SUCCESS) { api.Unmap((CUdeviceptr)p + mapped, add); api.Release(hnd); return cudaErrorMemoryAllocation; }
+    chunks.emplace_back(hnd, add);
+    mapped = want; cap = mapped / sizeof(T);
+    return cudaSuccess;
+  }
+  void release() {
+    if (vmm) {
+      VmApi& api = vm_api();
+      size_t off = 0;
+      for (auto& c : chunks) { api.Unmap((CUdeviceptr)p + off, c.second); api.Release(c.first); off += c.second; }
+      chunks.clear();
+      if (p) api.AddressFree((CUdeviceptr)p, va_bytes);
+    } else fallback.release();
+    p = nullptr; cap = 0; mapped = 0; vmm = false;
+  }
+  size_t bytes() const { return cap * sizeof(T); }
+};
+
 }  // namespace
 
 struct apss_handle {
@@ -57,8 +152,8 @@ struct apss_handle {
   // shard
   int64_t n_local = 0, nnz = 0, n_post = 0;
   int64_t ntiles = 0;
-  DevBuf<int64_t> fwd_ptr; DevBuf<int32_t> fwd_idx; DevBuf<double> fwd_val; DevBuf<int32_t> gid; DevBuf<int64_t> key;
-  DevBuf<uint2> post; DevBuf<int32_t> dir; DevBuf<int64_t> tile_base;
+  VmBuf<int64_t> fwd_ptr; VmBuf<int32_t> fwd_idx; VmBuf<double> fwd_val; VmBuf<int32_t> gid; VmBuf<int64_t> key;
+  VmBuf<uint2> post; VmBuf<int32_t> dir; VmBuf<int64_t> tile_base;
   DevBuf<double> maxw;
   // batch staging
   DevBuf<int64_t> b_ptr; DevBuf<int32_t> b_idx; DevBuf<double> b_val; DevBuf<int64_t> b_key; DevBuf<int32_t> b_first;
@@ -66,7 +161,7 @@ struct apss_handle {
   // build scratch
   DevBuf<unsigned long long> s_keys_in, s_keys_out, s_vals_in; DevBuf<int64_t> s_tile_start; DevBuf<char> cub_tmp;
   // dense-head tiles (algo 3)
-  DevBuf<int32_t> dn_cnt, dn_dim, dn_len, tile_cnt; DevBuf<int2> dn_hash; DevBuf<float> dn_w; DevBuf<unsigned long long> s_vals_out;
+  VmBuf<int32_t> dn_cnt, dn_dim, dn_len, tile_cnt; VmBuf<int2> dn_hash; VmBuf<float> dn_w; DevBuf<unsigned long long> s_vals_out;
   int dense_shift = 2, COLS = 4, ctas_per_sm = 1, seg_cap = SEG_CAP;
   // query-block transposition (v2 kernel)
   DevBuf<unsigned long long> bt_keys_in, bt_keys_out, bt_vals_in, bt_vals_out, ud_key; DevBuf<int32_t> bt_flags, bt_pos, ud_dim, ud_start, bd_ptr;
@@ -172,6 +267,9 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) { cudaGetLastError(); return APSS_E_NO_DEVICE; }
   apss_handle* h = new apss_handle();
   h->cfg = *cfg; h->cfg.max_weight = nullptr; h->device = cfg->device;
+  h->fwd_ptr.device = h->fwd_idx.device = h->fwd_val.device = h->gid.device = h->key.device = h->post.device = h->dir.device =
+      h->tile_base.device = h->dn_cnt.device = h->dn_dim.device = h->dn_len.device = h->tile_cnt.device = h->dn_hash.device =
+      h->dn_w.device = cfg->device;
   auto bail = [&](int32_t rc) { apss_destroy(h); return rc; };
   if (cudaSetDevice(h->device) != cudaSuccess) return bail(APSS_E_NO_DEVICE);
   cudaDeviceProp prop{};
