@@ -641,6 +641,11 @@ static constexpr int SEG_PIECE = 256;   // queued segments are cut into pieces o
 __device__ __forceinline__ unsigned fx_contrib(float ws, float wc) {
   return __float_as_uint(fmaf(ws, wc, 8388609.0f)) & 0x7fffffu;
 }
+// predicated shared-memory reduction on a 32-bit shared-space address: one instruction, no branch and no
+// convergence barrier around it (the compiler wraps `if (p) atomicAdd(..)` in BSSY / BRA / BSYNC)
+__device__ __forceinline__ void red_shared_if(unsigned saddr, unsigned val, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.shared.add.u32 [%0], %1;\n\t}" :: "r"(saddr), "r"(val), "r"((unsigned)p) : "memory");
+}
 __device__ __forceinline__ void acc_add16(unsigned* acc, unsigned rowoff_words, unsigned c, float ws, float wc) {
   atomicAdd(acc + rowoff_words + (c >> 1), fx_contrib(ws, wc) << ((c & 1u) << 4));
 }
@@ -650,21 +655,24 @@ __device__ __forceinline__ void acc_add16(unsigned* acc, unsigned rowoff_words, 
 __device__ __forceinline__ void lane_walk(unsigned* acc, const uint2* __restrict__ pt, const uint2* __restrict__ bt,
                                           int p, int pe, int rs, int nr, uint2 rw0, int nwords, int CR) {
   DBG_ASSERT(p >= 0 && pe >= p && pe - p <= SPLIT);
+  const unsigned acc_s = (unsigned)__cvta_generic_to_shared(acc);
   while (__any_sync(FULL, p < pe)) {
     uint2 pp[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) if (p + u < pe) pp[u] = ld_stream(pt + p + u);
+    for (int u = 0; u < 4; ++u) { pp[u] = make_uint2(0u, 0u); if (p + u < pe) pp[u] = ld_stream(pt + p + u); }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (p + u < pe) {
-        const float wc = __uint_as_float(pp[u].y);
-        DBG_ASSERT(pp[u].x < (unsigned)CR && rw0.x + (pp[u].x >> 1) < (unsigned)nwords);
-        acc_add16(acc, rw0.x, pp[u].x, __uint_as_float(rw0.y), wc);
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = p + u < pe;
+      const float wc = __uint_as_float(pp[u].y);
+      DBG_ASSERT(!ok || (pp[u].x < (unsigned)CR && rw0.x + (pp[u].x >> 1) < (unsigned)nwords));
+      const unsigned w4 = (pp[u].x >> 1) << 2, sh = (pp[u].x & 1u) << 4;
+      red_shared_if(acc_s + (rw0.x << 2) + w4, fx_contrib(__uint_as_float(rw0.y), wc) << sh, ok);
+      if (ok)
         for (int r = 1; r < nr; ++r) {
           const uint2 rw = __ldg(bt + rs + r);
           acc_add16(acc, rw.x, pp[u].x, __uint_as_float(rw.y), wc);
         }
-      }
+    }
     p += 4;
   }
 }
@@ -857,6 +865,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
     // skipped warp-uniformly; only the last chunk is predicated per lane.
     {
       constexpr int NCH = SEG_PIECE / 32;
+      const unsigned acc_s = (unsigned)__cvta_generic_to_shared(acc);
       int k = 0;
       if (lane == 0) k = atomicAdd(&s_next, 1);
       k = __shfl_sync(FULL, k, 0);
@@ -881,7 +890,8 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
         }
         const unsigned ro0 = __shfl_sync(FULL, rw.x, 0), ro1 = __shfl_sync(FULL, rw.x, 1);
         const float ws0 = __uint_as_float(__shfl_sync(FULL, rw.y, 0)), ws1 = __uint_as_float(__shfl_sync(FULL, rw.y, 1));
-        unsigned* base0 = acc + ro0; unsigned* base1 = acc + ro1;
+        const unsigned base0 = acc_s + (ro0 << 2), base1 = acc_s + (ro1 << 2);
+        const bool two = S.w > 1;
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
           const uint2 pp = pn[u];
@@ -891,13 +901,13 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
             const bool ok = S.x + lane + 32 * u < S.y;           // only the last chunk is partial
             DBG_ASSERT(!ok || pp.x < (unsigned)CR);
             const float wc = __uint_as_float(pp.y);
-            const unsigned w = pp.x >> 1, sh = (pp.x & 1u) << 4;
-            if (ok) atomicAdd(base0 + w, fx_contrib(ws0, wc) << sh);
-            if (S.w > 1 && ok) atomicAdd(base1 + w, fx_contrib(ws1, wc) << sh);
+            const unsigned w4 = (pp.x >> 1) << 2, sh = (pp.x & 1u) << 4;
+            red_shared_if(base0 + w4, fx_contrib(ws0, wc) << sh, ok);
+            red_shared_if(base1 + w4, fx_contrib(ws1, wc) << sh, ok && two);
             for (int r = 2; r < S.w; ++r) {
               const unsigned ro = __shfl_sync(FULL, rw.x, r);
               const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
-              if (ok) atomicAdd(acc + ro + w, fx_contrib(ws, wc) << sh);
+              red_shared_if(acc_s + (ro << 2) + w4, fx_contrib(ws, wc) << sh, ok);
             }
           }
         }
