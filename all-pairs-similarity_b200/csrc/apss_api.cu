@@ -262,7 +262,7 @@ extern "C" int32_t apss_abi_version(void) { return APSS_ABI_VERSION; }
 extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (!cfg || !out || cfg->struct_size != (int32_t)sizeof(apss_config)) return APSS_E_INVALID;
   *out = nullptr;
-  if (cfg->dim <= 0 || !(cfg->index_threshold >= 0.0) || (cfg->semantics != APSS_SEM_R1 && cfg->semantics != APSS_SEM_R0)) return APSS_E_INVALID;
+  if (cfg->dim <= 0 || cfg->dim > (1 << 30) || !(cfg->index_threshold >= 0.0) || !(cfg->similarity_threshold == cfg->similarity_threshold) || (cfg->semantics != APSS_SEM_R1 && cfg->semantics != APSS_SEM_R0)) return APSS_E_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) { cudaGetLastError(); return APSS_E_NO_DEVICE; }
   apss_handle* h = new apss_handle();
@@ -464,6 +464,8 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
                                      const int64_t* ext_keys, const int32_t* first_dim, uint32_t flags, apss_batch_result* out) {
   if (!h) return APSS_E_INVALID;
   if (n < 0 || (n > 0 && (!indptr || (!indices && !values)))) return h->fail(APSS_E_INVALID, "null batch arrays");
+  if (n > (1 << 24)) return h->fail(APSS_E_INVALID, "batch too large: at most 2^24 vectors per call");
+  if (h->n_local + n > 0x7fffff00LL) return h->fail(APSS_E_INVALID, "shard full: internal ids are int32");
   CK(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const bool dev_ptrs = flags & APSS_BATCH_DEVICE_PTRS;
@@ -483,6 +485,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   } else {
     in_nnz = indptr[n];
     if (indptr[0] != 0 || in_nnz < 0) return h->fail(APSS_E_INPUT, "indptr must start at 0 and be non-negative");
+    if (in_nnz > 0x7fffff00LL) return h->fail(APSS_E_INVALID, "batch too large: at most 2^31 components per call");
     CK(h->b_ptr.reserve(n + 1, 0, s)); CK(h->b_idx.reserve(std::max<int64_t>(in_nnz, 1), 0, s)); CK(h->b_val.reserve(std::max<int64_t>(in_nnz, 1), 0, s));
     CK(cudaMemcpyAsync(h->b_ptr.p, indptr, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, s));
     if (in_nnz) {

@@ -27,7 +27,7 @@ def scala_set_order(dims: Sequence[int], n_total: int | None = None, ascending: 
     n_total = len(dims) if n_total is None else n_total
     if ascending or n_total <= 4:
         return list(dims)
-    return sorted(dims, key=lambda x: [(scala_improve(x & M32) >> (5 * lvl)) & 31 for lvl in range(7)])
+    return sorted(dims, key=lambda x: [(scala_improve(int(x) & M32) >> (5 * lvl)) & 31 for lvl in range(7)])
 
 
 class SparseVector:
