@@ -273,9 +273,11 @@ def main():
     w0 = time.time()
     ev0.record(lib_stream)
     tot = dict(cands=0, pairs=0, postings=0, score_ms=0.0, local_postings=0, items=0)
+    step_wall = []
     for _ in range(K):
         ts_ = time.time()
         r = step_device(cursor); cursor += B
+        step_wall.append((time.time() - ts_) * 1e3)
         if args.verbose and rank == 0:
             print("value step: wall %.1f ms score %.1f ms device %.1f ms pairs %d prefilter %d" % (
                 (time.time() - ts_) * 1e3, r.local.score_ms, r.local.device_ms, r.n_pairs, r.local.n_prefilter), file=sys.stderr, flush=True)
@@ -352,6 +354,7 @@ def main():
                    "tile_vectors": st["tile_vectors"], "warps_per_cta": st["warps_per_cta"], "kernel_variant": args.variant},
         "pairs_per_sec": tot["pairs"] / dt_value,
         "postings_per_sec": tot["postings"] / dt_value,
+        "step_latency_ms": {"min": float(np.min(step_wall)), "p50": float(np.percentile(step_wall, 50)), "max": float(np.max(step_wall))},
         "wall_s_value": wall_value, "wall_s_e2e": wall_e2e, "gen_s": t_gen, "preload_s": t_load,
         "e2e": {"value": e_c / dt_e2e if dt_e2e > 0 else None, "unit": UNIT, "h2d_bytes_per_step": e_h2d // K,
                 "d2h_bytes_per_step": e_d2h // K, "pairs_per_sec": e_p / dt_e2e if dt_e2e > 0 else None},
