@@ -158,6 +158,83 @@ def generate(N, D, nnz_mean, s=1.0, q=0.0, seed=0, dup_frac=0.10, device="cpu", 
     return SparseBatch(indptr, indices, val, D)
 
 
+class FlatShard:
+    """Structure (rows, dims, term frequencies) of a generated shard before IDF weighting; lets the
+    ranks of a multi-GPU job generate their own shards and all-reduce the document frequencies."""
+
+    def __init__(self, indptr, indices, tf, dup_mask_rows, D, seed):
+        self.indptr, self.indices, self.tf, self.is_dup, self.D, self.seed = indptr, indices, tf, dup_mask_rows, D, seed
+
+    @property
+    def n(self):
+        return self.indptr.numel() - 1
+
+    def df(self):
+        return torch.bincount(self.indices.long(), minlength=self.D)
+
+    def finalize(self, idf) -> SparseBatch:
+        """value = tf * idf(d) (jittered +-10 % on planted near-duplicates), L2-normalised."""
+        dev = self.indices.device
+        N = self.n
+        row_of = torch.repeat_interleave(torch.arange(N, device=dev), self.indptr[1:] - self.indptr[:-1])
+        g = torch.Generator(device=dev); g.manual_seed(int(self.seed) + 99991)
+        jitter = 0.9 + 0.2 * torch.rand(self.indices.numel(), generator=g, device=dev, dtype=torch.float64)
+        jitter = torch.where(self.is_dup[row_of], jitter, torch.ones_like(jitter))
+        val = self.tf.to(torch.float64) * idf.to(dev)[self.indices.long()] * jitter
+        sq = torch.zeros(N, dtype=torch.float64, device=dev).index_add_(0, row_of, val * val)
+        nrm = torch.sqrt(sq)
+        nrm = torch.where(nrm > 0, nrm, torch.ones_like(nrm))
+        return SparseBatch(self.indptr, self.indices, val / nrm[row_of], self.D)
+
+
+def generate_flat(N, D, nnz_mean, s=1.0, q=0.0, seed=0, dup_frac=0.10, device="cpu", heavy_tail=False, k_min=4) -> FlatShard:
+    """Variable-length ("flat") variant of generate() for heavy-tailed lengths (config C5) and per-rank
+    shards: no [N, kmax] matrix.  A planted near-duplicate is a copy of an earlier row OF THE SAME CALL with
+    ~10 % of its draws dropped (its weights are jittered in finalize())."""
+    dev = torch.device(device)
+    pmf = zipf_pmf(D, s, q)
+    lam = calibrate_lambda(pmf, nnz_mean)
+    cdf = torch.from_numpy(np.cumsum(pmf)).to(dev); cdf[-1] = 1.0
+    perm = torch.from_numpy(np.random.RandomState(20260105 ^ 0x5EED).permutation(D).astype(np.int64)).to(dev)   # shared by all shards
+    g = torch.Generator(device=dev); g.manual_seed(int(seed))
+    if heavy_tail:
+        sigma = 1.0
+        mu = math.log(lam) - 0.5 * sigma * sigma
+        k = torch.exp(mu + sigma * torch.randn(N, generator=g, device=dev, dtype=torch.float64)).round().clamp(8, 4096).long()
+    else:
+        k = torch.poisson(torch.full((N,), lam, device=dev, dtype=torch.float64), generator=g).long().clamp(min=k_min)
+    is_dup = torch.rand(N, generator=g, device=dev) < dup_frac
+    is_dup[0] = False
+    src = (torch.rand(N, generator=g, device=dev, dtype=torch.float64) * torch.arange(N, device=dev, dtype=torch.float64)).long()
+    src = torch.where(is_dup, src, torch.arange(N, device=dev))
+    start = torch.cumsum(k, 0) - k                       # draw ranges of the originals
+    total = int(k.sum())
+    u = torch.rand(total, generator=g, device=dev, dtype=torch.float64)
+    draws = perm[torch.searchsorted(cdf, u).clamp(max=D - 1)]
+    del u
+    # every row reads the draw range of its source row (itself for originals)
+    k_eff = k[src]
+    row_of = torch.repeat_interleave(torch.arange(N, device=dev), k_eff)
+    off = torch.arange(int(k_eff.sum()), device=dev) - torch.repeat_interleave(torch.cumsum(k_eff, 0) - k_eff, k_eff)
+    dims = draws[start[src][row_of] + off]
+    keep = ~(is_dup[row_of] & (torch.rand(dims.numel(), generator=g, device=dev) < 0.10))
+    key = (row_of * D + dims)[keep]
+    del draws, dims, off, row_of
+    key, _ = torch.sort(key)
+    uk, cnt = torch.unique_consecutive(key, return_counts=True)
+    del key
+    r = uk // D
+    indices = (uk - r * D).to(torch.int32)
+    indptr = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(torch.bincount(r, minlength=N), 0)])
+    return FlatShard(indptr, indices, cnt.to(torch.int16), is_dup, D, seed)
+
+
+def idf_from_df(df, n_docs):
+    """ln((N+1)/(df+1)) with libm's log on the host (Spark 1.2 IDF; see etl.idf_fit for why not numpy.log)."""
+    d = df.cpu().numpy().astype(np.float64)
+    return torch.from_numpy(np.log((n_docs + 1.0) / (d + 1.0)))
+
+
 # the named workloads of BASELINE.json / SURVEY.md 8(d)
 CONFIGS = {
     "C2": dict(N=100_000, D=1 << 16, nnz_mean=50, s=1.0, seed=20260102, threshold=0.8, batch=4096),

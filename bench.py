@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-gen", action="store_true", help="generate per-rank shards (default for heavy-tail configs)")
     ap.add_argument("--verbose", action="store_true", help="per-step timings on stderr")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed value region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
@@ -223,23 +224,78 @@ def main():
     K, W, B, N, D, t = args.steps, args.warmup, cfg["batch"], cfg["N"], cfg["D"], cfg["threshold"]
     n_fresh = (W + K) + (1 + K)                    # value phase + e2e phase (1 warm-up)
     t_gen = time.time()
-    data = synth.generate(N + n_fresh * B, D, cfg["nnz_mean"], s=cfg["s"], seed=cfg["seed"], device=dev)
-    torch.cuda.synchronize()
-    t_gen = time.time() - t_gen
+    shard_gen = bool(cfg.get("heavy_tail")) or args.shard_gen
+    if not shard_gen:
+        # every rank generates the whole data set (identical on all ranks); owners index their batches
+        data = synth.generate(N + n_fresh * B, D, cfg["nnz_mean"], s=cfg["s"], seed=cfg["seed"], device=dev)
+        torch.cuda.synchronize()
+        t_gen = time.time() - t_gen
 
-    def dev_rows(lo, hi):
-        b = data.rows(lo, hi)
-        return b.indptr.contiguous(), b.indices.contiguous(), b.values.contiguous()
+        def fresh_rows(i, pin=False):
+            b = data.rows(N + i * B, N + (i + 1) * B)
+            if pin:
+                b = b.pin()
+                return b.indptr, b.indices, b.values
+            return b.indptr.contiguous(), b.indices.contiguous(), b.values.contiguous()
 
-    per_rank_nnz = int(data.nnz / world * 1.15) + (1 << 20)
-    eng = native.Index(D, t, device=local_rank, tile_vectors=args.tile, kernel_variant=args.variant,
-                       reserve_vectors=int((N + n_fresh * B) / world * 1.1) + 2 * B, reserve_nnz=per_rank_nnz)
-    disp = ShardDispatcher(eng, device=dev)
-    t_load = time.time()
-    for lo in range(0, N, B):
-        disp.preload(*dev_rows(lo, min(N, lo + B)))
-    torch.cuda.synchronize()
-    t_load = time.time() - t_load
+        def dev_rows(lo, hi):
+            b = data.rows(lo, hi)
+            return b.indptr.contiguous(), b.indices.contiguous(), b.values.contiguous()
+
+        total_nnz = data.nnz
+        eng = native.Index(D, t, device=local_rank, tile_vectors=args.tile, kernel_variant=args.variant,
+                           reserve_vectors=int((N + n_fresh * B) / world * 1.1) + 2 * B, reserve_nnz=int(total_nnz / world * 1.15) + (1 << 20))
+        disp = ShardDispatcher(eng, device=dev)
+        t_load = time.time()
+        for lo in range(0, N, B):
+            disp.preload(*dev_rows(lo, min(N, lo + B)))
+        torch.cuda.synchronize()
+        t_load = time.time() - t_load
+    else:
+        # per-rank shards (config C5: too large to generate everywhere): rank r generates and indexes the
+        # batches r, r + world, ... itself; document frequencies are all-reduced so that every rank uses the
+        # same IDF; rank 0 also generates the fresh query batches
+        per_rank = max(1, (N // B) // world)
+        N = per_rank * world * B
+        fs = synth.generate_flat(per_rank * B, D, cfg["nnz_mean"], s=cfg["s"], seed=cfg["seed"] + 1009 * rank, device=dev,
+                                 heavy_tail=bool(cfg.get("heavy_tail")))
+        df = fs.df()
+        if world > 1:
+            dist.all_reduce(df)
+        idf = synth.idf_from_df(df, N)
+        shard = fs.finalize(idf)
+        del fs
+        fresh = None
+        if rank == 0:
+            fresh = synth.generate_flat(n_fresh * B, D, cfg["nnz_mean"], s=cfg["s"], seed=cfg["seed"] + 777, device=dev,
+                                        heavy_tail=bool(cfg.get("heavy_tail"))).finalize(idf)
+        torch.cuda.synchronize()
+        t_gen = time.time() - t_gen
+
+        def fresh_rows(i, pin=False):
+            b = fresh.rows(i * B, (i + 1) * B)
+            if pin:
+                b = b.pin()
+                return b.indptr, b.indices, b.values
+            return b.indptr.contiguous(), b.indices.contiguous(), b.values.contiguous()
+
+        total_nnz = shard.nnz * world
+        eng = native.Index(D, t, device=local_rank, tile_vectors=args.tile, kernel_variant=args.variant,
+                           reserve_vectors=int((N + n_fresh * B) / world * 1.1) + 2 * B, reserve_nnz=int(shard.nnz * 1.15) + (1 << 22))
+        disp = ShardDispatcher(eng, device=dev)
+        t_load = time.time()
+        for j in range(per_rank):
+            b = shard.rows(j * B, (j + 1) * B)
+            rows = (b.indptr.contiguous(), b.indices.contiguous(), b.values.contiguous())
+            torch.cuda.synchronize()
+            eng.set_next_id((j * world + rank) * B)
+            eng.insert_batch(*rows, index_only=True)
+        disp.next_id = N
+        disp.batch_no = N // B
+        torch.cuda.synchronize()
+        t_load = time.time() - t_load
+        cfg["workload"] = "%s: synthetic %d vectors x 2^%d dims, Zipf(s=1) %s nnz~%d, cosine>=%.2f, batches of %d" % (
+            args.config, N, int(np.log2(D)), "heavy-tail" if cfg.get("heavy_tail") else "", cfg["nnz_mean"], t, B)
 
     def barrier():
         if world > 1:
@@ -260,8 +316,11 @@ def main():
     cursor = N
 
     # ------------------------------------------------------------ value: inputs resident in HBM
-    def step_device(lo):
-        return disp.insert_batch(*(dev_rows(lo, lo + B) if rank == 0 else (None, None, None)))
+    fresh_i = [0]
+
+    def step_device(_lo):
+        i = fresh_i[0]; fresh_i[0] += 1
+        return disp.insert_batch(*(fresh_rows(i) if rank == 0 else (None, None, None)))
 
     for _ in range(W):
         step_device(cursor); cursor += B
@@ -297,9 +356,7 @@ def main():
     host_batches = []
     if rank == 0:
         for k in range(1 + K):
-            lo = cursor + k * B
-            b = data.rows(lo, lo + B).pin()
-            host_batches.append((b.indptr, b.indices, b.values))
+            host_batches.append(fresh_rows(W + K + k, pin=True))
     out_q = torch.empty(1 << 22, dtype=torch.int32).pin_memory()
     out_c = torch.empty(1 << 22, dtype=torch.int32).pin_memory()
     out_s = torch.empty(1 << 22, dtype=torch.float64).pin_memory()
@@ -373,7 +430,7 @@ def main():
                              "and achieved may exceed the HBM copy peak"},
         "clocks": sampler.summary([(w0, w1), (w2, w3)]),
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not shard_gen:
         threads = host_threads()
         nq = args.cpu_queries or 2 * threads
         n_index = min(args.cpu_index, N)

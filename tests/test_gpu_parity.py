@@ -327,3 +327,25 @@ def test_c1_maildir_fixture_parity(sem):
             assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
         pairs += rg.n_pairs
     assert pairs == (595 if sem == "R1" else 92)      # the corpus is full of duplicated mails (sent vs sent_items ...)
+
+
+def test_c5_shape_heavy_tail_parity():
+    """Config C5's shape at small scale: 2^20 dims, heavy-tailed nnz (lognormal, up to thousands of
+    components per vector), cosine >= 0.5."""
+    import apss_b200
+    from apss_b200 import synth
+    N, D, t, B = 6000, 1 << 20, 0.5, 1500
+    fs = synth.generate_flat(N, D, 200, seed=20260105, heavy_tail=True)
+    ip, ix, v = fs.finalize(synth.idf_from_df(fs.df(), N)).numpy()
+    assert np.diff(ip).max() > 1000
+    n = native()
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=orc.max_threads())
+    g = n.Index(D, t)
+    pairs = 0
+    for lo in range(0, N, B):
+        csr = csr_slice((ip, ix, v), lo, lo + B)
+        ro = o.insert_batch(*csr); rg = g.insert_batch(*csr)
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+        assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+        pairs += rg.n_pairs
+    assert pairs > 50
