@@ -349,3 +349,23 @@ def test_c5_shape_heavy_tail_parity():
         assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
         pairs += rg.n_pairs
     assert pairs > 50
+
+
+def test_admission_with_real_max_weights():
+    """EPA:81-93 with real per-dimension max weights (the reference stubs them to 1.0, EPA:51-57): the
+    admission predicate sum_d maxw(d) * v(d) >= t must agree with the oracle vector by vector."""
+    N, D, t = 3000, 1 << 10, 0.45
+    ip, ix, v = _synth(N, D, 12, seed=17)
+    mw = np.random.RandomState(3).uniform(0.05, 1.0, D)
+    n = native()
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, max_weight=mw, threads=8)
+    g = n.Index(D, t, max_weight=mw, tile_vectors=512)
+    rejected = 0
+    for lo in range(0, N, 1000):
+        csr = csr_slice((ip, ix, v), lo, lo + 1000)
+        ro = o.insert_batch(*csr); rg = g.insert_batch(*csr)
+        assert list(g.fetch_status(1000)) == list(ro.status)
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+        assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+        rejected += rg.n_rejected
+    assert 0 < rejected < N
