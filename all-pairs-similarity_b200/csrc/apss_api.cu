@@ -251,6 +251,7 @@ static cudaError_t launch_dense(apss_handle* h, const ScoreArgs& a, const BlockA
     case 320802: return launch_dense_t<32, 8, 2>(h, a, b, d, dup);
     case 161602: return launch_dense_t<16, 16, 2>(h, a, b, d, dup);
     case 161604: return launch_dense_t<16, 16, 4>(h, a, b, d, dup);
+    case 163202: return launch_dense_t<16, 32, 2>(h, a, b, d, dup);
     case 160804: return launch_dense_t<16, 8, 4>(h, a, b, d, dup);
     case 81604: return launch_dense_t<8, 16, 4>(h, a, b, d, dup);
     default: return cudaErrorInvalidValue;
@@ -315,7 +316,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
     if (algo == 3) {
       h->COLS = (cfg->kernel_variant & 0xff) == 2 ? 2 : 4;
       if (QB == 32) { h->COLS = 2; if (warps != 8 && warps != 12 && warps != 16) warps = 16; }
-      else if (QB == 16) { if (h->COLS == 2) warps = 16; else if (warps != 8) warps = 16; }
+      else if (QB == 16) { if (h->COLS == 2) { if (warps != 32) warps = 16; } else if (warps != 8) warps = 16; }
       else { h->COLS = 4; warps = 16; }
       const char* ds = getenv("APSS_DENSE_SHIFT");
       if (ds && atoi(ds) >= 0 && atoi(ds) <= 10) h->dense_shift = atoi(ds);

@@ -12,8 +12,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libapss_b200_dbg.so" if os.environ.get("APSS_DEBUG_LIB") else
-                        ("libapss_b200_prof.so" if os.environ.get("APSS_PROF_LIB") else "libapss_b200.so"))
+LIB_PATH = os.path.join(_HERE, os.environ.get("APSS_LIB_NAME") or ("libapss_b200_dbg.so" if os.environ.get("APSS_DEBUG_LIB") else
+                        ("libapss_b200_prof.so" if os.environ.get("APSS_PROF_LIB") else "libapss_b200.so")))
 
 ABI_VERSION = 1
 SEM_R1, SEM_R0 = 0, 1
