@@ -147,7 +147,7 @@ struct apss_handle {
   bool frozen = false, custom_keys = false;
   int64_t next_id = 0;
   int max_nnz_seen = 0;
-  int64_t phase_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // last batch, dense kernel: setup, phase 1, Wq, dense, tasks, epilogue
+  int64_t phase_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // last batch, profiling build only (see apss_stats)
 
   // shard
   int64_t n_local = 0, nnz = 0, n_post = 0;
@@ -175,7 +175,7 @@ struct apss_handle {
 
   // last batch
   int32_t last_n = -1; int64_t last_pairs = 0;
-  std::vector<uint8_t> last_status; bool status_fetched = false;
+  std::vector<uint8_t> last_status;
   // totals
   int64_t tot_postings = 0, tot_cands = 0, tot_pairs = 0, tot_pf = 0, score_launches = 0, kernel_launches = 0;
   double tot_score_ms = 0;
@@ -277,8 +277,9 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return bail(APSS_E_NO_DEVICE);
   h->sm_count = prop.multiProcessorCount;
   const size_t max_smem1 = prop.sharedMemPerBlockOptin;
-  // kernel_variant: bits 0-7 unroll (row kernel), 8-15 warps per CTA, 16-23 algorithm (0/2 = query-block
-  // kernel with fixed-point atomics, 1 = warp-per-(query, tile) row kernel), 24-31 queries per block
+  // kernel_variant (see include/apss.h): bits 0-7 unroll of the row kernel / candidates per thread of the dense
+  // phase, 8-15 warps per CTA, 16-23 scoring kernel (0/3 = dense-head, 1 = row, 2 = query-block), 24-31 queries
+  // per block.  The index layout (tile size) follows from the kernel's shared-memory budget.
   int algo = (cfg->kernel_variant >> 16) & 0xff;   // 0 = default
   if (algo != 1 && algo != 2 && algo != 3) algo = 3;   // default: dense-head kernel
   int QB = (cfg->kernel_variant >> 24) & 0xff; if (QB <= 0) QB = 16;

@@ -70,8 +70,11 @@ typedef struct apss_config {
   const double *max_weight;    /* dim entries, or NULL = 1.0 for every dim (the stub at EPA:51-57)   */
   int32_t device;              /* CUDA device ordinal                                                */
   int32_t semantics;           /* APSS_SEM_R1 / APSS_SEM_R0                                          */
-  int32_t tile_vectors;        /* candidates per index tile; 0 = default (3584)                      */
-  int32_t kernel_variant;      /* 0 = default scoring kernel; other values select experiments        */
+  int32_t tile_vectors;        /* candidates per index tile; 0 = default (6144 for the default kernel)  */
+  int32_t kernel_variant;      /* 0 = default.  Otherwise: bits 16-23 scoring kernel (3 dense-head [default],   */
+                               /* 1 warp-per-(query,tile) row kernel, 2 query-block kernel), bits 8-15 warps per */
+                               /* CTA, bits 24-31 queries per block, bits 0-7 unroll / candidates per thread.    */
+                               /* All variants give identical results; they exist for measurement.               */
   int64_t reserve_vectors;     /* capacity hints; 0 = grow on demand                                 */
   int64_t reserve_nnz;
   int64_t reserve_pairs;
@@ -107,9 +110,10 @@ typedef struct apss_stats {
   int64_t score_launches;    /* launches of the scoring kernel so far                                */
   int64_t kernel_launches;   /* all kernels launched by this handle so far                           */
   double tot_score_ms;
-  int64_t phase_cycles[8];   /* last batch, dense-head kernel: CTA-thread-0 cycles summed over CTAs in      */
-                             /* item setup, look-up/short segments, query-weight fill, dense FFMA, tasks,  */
-                             /* epilogue (a diagnostic: where the scoring kernel's time goes)              */
+  int64_t phase_cycles[8];   /* profiling build (libapss_b200_prof.so) only, last batch, dense-head kernel:  */
+                             /* thread-0 cycles summed over CTAs in [0] item setup, [1] look-ups + short     */
+                             /* segments, [2] query-weight fill + dense FFMA, [3] queued segments, [4]        */
+                             /* epilogue loop, [5] barrier + item fetch, [7] self-clear; [6] rare-path count  */
   int32_t frozen;
   int32_t tile_vectors;
   int32_t warps_per_cta;
