@@ -635,11 +635,14 @@ static constexpr int SEG_PIECE = 256;   // queued segments are cut into pieces o
 // Accumulators of the dense-head kernel are u16 fixed point, two per 32-bit word: word (row*CR + c)/2,
 // half c & 1 (CR is even).  An update is one native shared atomic add of (value << 16*(c&1)); halves
 // cannot carry into each other because every sum is < 2^16 by the choice of the scale.
-// float -> fixed point without the (slow, XU-pipe) F2I: for 0 <= p < 2^22, fmaf(ws, wc, 2^23 + 1) has the
-// integer round(p + 1) in its low mantissa bits.  round(p + 1) >= ceil(p) >= 1: every contribution is at
-// least one quantum and never below the exact product, and over-shoots by at most 1.5 quanta.
+// float -> fixed point without the (slow, XU-pipe) F2I: for 0 <= p < 2^23, fma(ws, wc, 2^23) rounded UP has
+// the integer ceil(p) in its low mantissa bits.  ceil(p) >= 1 for p > 0 and never below the exact product:
+// every contribution is at least one quantum and over-shoots by less than one.
 __device__ __forceinline__ unsigned fx_contrib(float ws, float wc) {
-  return __float_as_uint(fmaf(ws, wc, 8388609.0f)) & 0x7fffffu;
+  return __float_as_uint(__fmaf_ru(ws, wc, 8388608.0f)) & 0x7fffffu;
+}
+__device__ __forceinline__ unsigned fx_ceil(float v) {          // exact ceil(v) for 0 <= v < 2^23; 0 stays 0
+  return __float_as_uint(__fadd_ru(v, 8388608.0f)) & 0x7fffffu;
 }
 // predicated shared-memory reduction on a 32-bit shared-space address: one instruction, no branch and no
 // convergence barrier around it (the compiler wraps `if (p) atomicAdd(..)` in BSSY / BRA / BSYNC)
@@ -810,7 +813,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
         for (int c = 0; c < COLS; ++c)
 #pragma unroll
           for (int r = 0; r < QB; ++r) av[c][r] = 0.f;
-        float wv[4][COLS], wn[4][COLS];
+        float wa[4][COLS], wb[4][COLS];                   // ping-pong: no register copies between groups
         auto load4 = [&](float (&dst)[4][COLS], int e0) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -820,10 +823,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
             else { for (int c = 0; c < COLS; ++c) dst[j][c] = __ldg(src + c); }
           }
         };
-        const int nd4 = (nd + 3) & ~3;
-        load4(wv, 0);
-        for (int e0 = 0; e0 < nd4; e0 += 4) {
-          if (e0 + 4 < nd4) load4(wn, e0 + 4);
+        auto fma4 = [&](const float (&w)[4][COLS], int e0) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4* q4 = reinterpret_cast<const float4*>(Wq + (e0 + j) * QB);
@@ -832,17 +832,23 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
               const float4 q = q4[r4];
 #pragma unroll
               for (int c = 0; c < COLS; ++c) {
-                av[c][r4 * 4 + 0] = fmaf(q.x, wv[j][c], av[c][r4 * 4 + 0]);
-                av[c][r4 * 4 + 1] = fmaf(q.y, wv[j][c], av[c][r4 * 4 + 1]);
-                av[c][r4 * 4 + 2] = fmaf(q.z, wv[j][c], av[c][r4 * 4 + 2]);
-                av[c][r4 * 4 + 3] = fmaf(q.w, wv[j][c], av[c][r4 * 4 + 3]);
+                av[c][r4 * 4 + 0] = fmaf(q.x, w[j][c], av[c][r4 * 4 + 0]);
+                av[c][r4 * 4 + 1] = fmaf(q.y, w[j][c], av[c][r4 * 4 + 1]);
+                av[c][r4 * 4 + 2] = fmaf(q.z, w[j][c], av[c][r4 * 4 + 2]);
+                av[c][r4 * 4 + 3] = fmaf(q.w, w[j][c], av[c][r4 * 4 + 3]);
               }
             }
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int c = 0; c < COLS; ++c) wv[j][c] = wn[j][c];
+        };
+        const int nd4 = (nd + 3) & ~3;
+        load4(wa, 0);
+        for (int e0 = 0; e0 < nd4; e0 += 8) {
+          if (e0 + 4 < nd4) load4(wb, e0 + 4);
+          fma4(wa, e0);
+          if (e0 + 4 < nd4) {
+            if (e0 + 8 < nd4) load4(wa, e0 + 8);
+            fma4(wb, e0 + 4);
+          }
         }
         // add to the accumulators: exclusive phase (between barriers), plain read-modify-write of
         // whole words (COLS is even, so a thread owns both halves of each word it touches)
@@ -850,8 +856,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
         for (int r = 0; r < QB; ++r)
 #pragma unroll
           for (int c = 0; c < COLS; c += 2) {
-            const float v0 = av[c][r], v1 = av[c + 1][r];
-            const unsigned add = (v0 > 0.f ? __float2uint_ru(v0) : 0u) | ((v1 > 0.f ? __float2uint_ru(v1) : 0u) << 16);
+            const unsigned add = fx_ceil(av[c][r]) | (fx_ceil(av[c + 1][r]) << 16);
             if (add) acc[r * RW + ((cb + c) >> 1)] += add;
           }
       }
