@@ -419,6 +419,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None if not traffic else traffic.get("dram_bytes_per_launch"),
                      "traffic_source": None if not traffic else traffic.get("kernel"),
+                     "ncu": None if not traffic else traffic.get("ncu"),
                      "peak_source": peak_src,
                      "kernel": {1: "apss::k_score", 2: "apss::k_score_blk"}.get((args.variant >> 16) & 0xff, "apss::k_score_dense"),
                      "launches_timed": score_launches,
@@ -427,7 +428,8 @@ def main():
                      "kernel_share_of_step": tot["score_ms"] * 1e-3 / dt_value,
                      "note": "algorithmic bytes = 8 B per posting visited per QUERY TERM (SURVEY 8d); lists are re-read "
                              "from L2/shared memory across the queries of a batch, so DRAM traffic << algorithmic bytes "
-                             "and achieved may exceed the HBM copy peak"},
+                             "and achieved may exceed the HBM copy peak; the binding resource is on-chip (instruction issue / "
+                             "shared-memory atomics), see the ncu figures"},
         "clocks": sampler.summary([(w0, w1), (w2, w3)]),
     }
     if not args.no_cpu_baseline and not shard_gen:
