@@ -631,6 +631,7 @@ __global__ void k_dir_fix(int ntiles_aff, int D, int64_t tile0, const int32_t* _
 static constexpr int SEG_CAP = 1280;    // max queued segment pieces per work item (shared memory); ScoreArgs.seg_cap <= this
 static constexpr int SPLIT = 8;         // segments up to this length are walked by the lane that looked them up
 static constexpr int SEG_PIECE = 256;   // queued segments are cut into pieces of at most this many postings
+static constexpr int SHORT_PIECE = 64;  // pieces up to this length use the 2-slot piece loop
 
 // Accumulators of the dense-head kernel are u16 fixed point, two per 32-bit word: word (row*CR + c)/2,
 // half c & 1 (CR is even).  An update is one native shared atomic add of (value << 16*(c&1)); halves
@@ -680,6 +681,64 @@ __device__ __forceinline__ void lane_walk(unsigned* acc, const uint2* __restrict
   }
 }
 
+// Piece loop of phase L: one warp per piece (<= 32 * NCH postings), handed out dynamically from `next`.
+// A lane keeps the piece's NCH postings (one per 32-posting chunk) in registers -- NCH independent
+// load -> FFMA -> shift -> red.shared chains -- and each register slot is refilled with the NEXT piece's
+// chunk as soon as it has been consumed.  Chunks past the end of the piece are skipped warp-uniformly;
+// only the last chunk is predicated per lane.  dir = +1 / -1: the queue grows up / down from `segs`.
+template <int NCH>
+__device__ __forceinline__ void process_pieces(unsigned* acc, const int4* segs, int dir, int nseg, int* next,
+                                               const uint2* __restrict__ pt, const uint2* __restrict__ bt, int lane, int CR) {
+  const unsigned acc_s = (unsigned)__cvta_generic_to_shared(acc);
+  int k = 0;
+  if (lane == 0) k = atomicAdd(next, 1);
+  k = __shfl_sync(FULL, k, 0);
+  int4 S = make_int4(0, 0, 0, 0); uint2 rw = make_uint2(0, 0); uint2 pn[NCH];
+  if (k < nseg) {
+    S = segs[dir * k];
+    if (lane < S.w) rw = __ldg(bt + S.z + lane);
+  }
+#pragma unroll
+  for (int u = 0; u < NCH; ++u) {
+    const int p = S.x + lane + 32 * u;
+    pn[u] = make_uint2(0u, 0u);
+    if (p < S.y) pn[u] = ld_stream(pt + p);
+  }
+  while (k < nseg) {
+    if (lane == 0) k = atomicAdd(next, 1);
+    k = __shfl_sync(FULL, k, 0);
+    int4 Sn = make_int4(0, 0, 0, 0); uint2 rwn = make_uint2(0, 0);
+    if (k < nseg) {
+      Sn = segs[dir * k];
+      if (lane < Sn.w) rwn = __ldg(bt + Sn.z + lane);
+    }
+    const unsigned ro0 = __shfl_sync(FULL, rw.x, 0), ro1 = __shfl_sync(FULL, rw.x, 1);
+    const float ws0 = __uint_as_float(__shfl_sync(FULL, rw.y, 0)), ws1 = __uint_as_float(__shfl_sync(FULL, rw.y, 1));
+    const unsigned base0 = acc_s + (ro0 << 2), base1 = acc_s + (ro1 << 2);
+    const bool two = S.w > 1;
+#pragma unroll
+    for (int u = 0; u < NCH; ++u) {
+      const uint2 pp = pn[u];
+      const int pnx = Sn.x + lane + 32 * u;
+      if (pnx < Sn.y) pn[u] = ld_stream(pt + pnx);           // refill the slot with the next piece's chunk
+      if (S.x + 32 * u < S.y) {                               // warp-uniform: chunk u exists in this piece
+        const bool ok = S.x + lane + 32 * u < S.y;           // only the last chunk is partial
+        DBG_ASSERT(!ok || pp.x < (unsigned)CR);
+        const float wc = __uint_as_float(pp.y);
+        const unsigned w4 = (pp.x >> 1) << 2, sh = (pp.x & 1u) << 4;
+        red_shared_if(base0 + w4, fx_contrib(ws0, wc) << sh, ok);
+        red_shared_if(base1 + w4, fx_contrib(ws1, wc) << sh, ok && two);
+        for (int r = 2; r < S.w; ++r) {
+          const unsigned ro = __shfl_sync(FULL, rw.x, r);
+          const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
+          red_shared_if(acc_s + (ro << 2) + w4, fx_contrib(ws, wc) << sh, ok);
+        }
+      }
+    }
+    S = Sn; rw = rwn;
+  }
+}
+
 // Scoring kernel for dense-head tiles.  Persistent, one CTA per SM; a work item is (index tile, block
 // of QB queries); QB x CR u16 accumulators live in shared memory.  Per item:
 //   phase 1  32 directory look-ups per warp step.  Dims that are dense in the tile go to the dense list;
@@ -703,7 +762,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
   int2* hsh = reinterpret_cast<int2*>(dl + KD);                         // [HS]
   int4* segs = reinterpret_cast<int4*>(hsh + HS);                       // [SEG_CAP] (s, e, rs, nr)
   __shared__ unsigned long long s_item;
-  __shared__ int s_nseg, s_segvalid, s_ndense, s_next;
+  __shared__ int s_nseg, s_segvalid, s_nshort, s_shortvalid, s_ndense, s_next, s_next2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   constexpr int NT = WARPS * 32;
   const int nwords = QB * RW;
@@ -720,7 +779,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
   for (;;) {
     __syncthreads();
     PHASE_MARK(5);
-    if (tid == 0) { s_item = atomicAdd(&a.counters[C_WORK], 1ULL); s_nseg = 0; s_segvalid = a.seg_cap; s_ndense = 0; s_next = 0; }
+    if (tid == 0) { s_item = atomicAdd(&a.counters[C_WORK], 1ULL); s_nseg = 0; s_segvalid = a.seg_cap - (a.seg_cap * 3 >> 3); s_nshort = 0; s_shortvalid = a.seg_cap * 3 >> 3; s_ndense = 0; s_next = 0; s_next2 = 0; }
     __syncthreads();
     const unsigned long long item = s_item;
     if (item >= a.total_items) break;
@@ -761,11 +820,29 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
       n_post += (unsigned long long)(unsigned)len * (unsigned)nr;
       if (len > 0 && len <= SPLIT) rw0 = __ldg(b.bt + rs);
       bool coop = false;                      // segment queue full: walk it here, warp-cooperatively
-      if (len > SPLIT) {                      // queue in pieces of <= SEG_PIECE postings (balance across warps)
-        const int np = (len + SEG_PIECE - 1) / SEG_PIECE;
-        const int k = atomicAdd(&s_nseg, np);
-        if (k + np <= a.seg_cap) { for (int j = 0; j < np; ++j) segs[k + j] = make_int4(s + j * SEG_PIECE, min(e, s + (j + 1) * SEG_PIECE), rs, nr); }
-        else { atomicMin(&s_segvalid, k); coop = true; }      // the cursor only grows: later reservations fail too
+      if (len > SPLIT) {
+        // queue in pieces of <= SEG_PIECE postings (balance across warps); a (last) piece of <= SHORT_PIECE
+        // postings goes to the short queue (2 chunk slots per piece instead of 8)
+        const int rem = len % SEG_PIECE;
+        const int ns = (rem > 0 && rem <= SHORT_PIECE) ? 1 : 0;
+        const int nl = (len + SEG_PIECE - 1) / SEG_PIECE - ns;
+        // two independent queues: long pieces in segs[0, cap_l), short ones in segs[cap_l, seg_cap).  Each
+        // cursor only grows, so once a reservation on a cursor fails every later one on it fails too and
+        // the valid prefix of that queue is [0, first failed base).
+        const int cap_l = a.seg_cap - (a.seg_cap * 3 >> 3), cap_s = a.seg_cap - cap_l;
+        const int kl = nl ? atomicAdd(&s_nseg, nl) : 0;
+        const int ks = ns ? atomicAdd(&s_nshort, ns) : 0;
+        const bool okl = kl + nl <= cap_l, oks = ks + ns <= cap_s;
+        if (!okl && nl) atomicMin(&s_segvalid, kl);
+        if (!oks && ns) atomicMin(&s_shortvalid, ks);
+        if (okl && oks) {
+          for (int j = 0; j < nl; ++j) segs[kl + j] = make_int4(s + j * SEG_PIECE, min(e, s + (j + 1) * SEG_PIECE), rs, nr);
+          if (ns) segs[cap_l + ks] = make_int4(e - rem, e, rs, nr);
+        } else {                                  // all or nothing: neutralise the half that was reserved
+          if (okl) for (int j = 0; j < nl; ++j) segs[kl + j] = make_int4(0, 0, rs, 0);
+          if (oks && ns) segs[cap_l + ks] = make_int4(0, 0, rs, 0);
+          coop = true;
+        }
       }
       lane_walk(acc, pt, b.bt, s, len <= SPLIT ? e : s, rs, nr, rw0, nwords, CR);
       unsigned m = __ballot_sync(FULL, coop);
@@ -791,7 +868,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
     __syncthreads();
     PHASE_MARK(1);
     const int nd = s_ndense;
-    const int nseg = min(s_nseg, s_segvalid);
+    const int nlong = min(s_nseg, s_segvalid), nshort = min(s_nshort, s_shortvalid);
     // pad the dense list to a multiple of 4 with entries whose query weights stay zero (Wq is cleared per item)
     if (tid < 4 && nd + tid < ((nd + 3) & ~3)) dl[nd + tid] = make_int4(0, 0, 0, 0);
     // ---- Wq[entry][row] from the block's row lists
@@ -863,62 +940,10 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
     }
     __syncthreads();
     PHASE_MARK(2);
-    // ---- phase L: queued segment pieces (<= SEG_PIECE = 256 postings), one warp per piece, handed out
-    // dynamically.  A lane keeps the piece's 8 postings (one per 32-posting chunk) in registers: 8
-    // independent load -> FMUL -> F2I -> shift -> ATOMS chains, and each register slot is refilled with
-    // the NEXT piece's chunk as soon as it has been consumed.  Chunks past the end of the piece are
-    // skipped warp-uniformly; only the last chunk is predicated per lane.
-    {
-      constexpr int NCH = SEG_PIECE / 32;
-      const unsigned acc_s = (unsigned)__cvta_generic_to_shared(acc);
-      int k = 0;
-      if (lane == 0) k = atomicAdd(&s_next, 1);
-      k = __shfl_sync(FULL, k, 0);
-      int4 S = make_int4(0, 0, 0, 0); uint2 rw = make_uint2(0, 0); uint2 pn[NCH];
-      if (k < nseg) {
-        S = segs[k];
-        if (lane < S.w) rw = __ldg(b.bt + S.z + lane);
-      }
-#pragma unroll
-      for (int u = 0; u < NCH; ++u) {
-        const int p = S.x + lane + 32 * u;
-        pn[u] = make_uint2(0u, 0u);
-        if (p < S.y) pn[u] = ld_stream(pt + p);
-      }
-      while (k < nseg) {
-        if (lane == 0) k = atomicAdd(&s_next, 1);
-        k = __shfl_sync(FULL, k, 0);
-        int4 Sn = make_int4(0, 0, 0, 0); uint2 rwn = make_uint2(0, 0);
-        if (k < nseg) {
-          Sn = segs[k];
-          if (lane < Sn.w) rwn = __ldg(b.bt + Sn.z + lane);
-        }
-        const unsigned ro0 = __shfl_sync(FULL, rw.x, 0), ro1 = __shfl_sync(FULL, rw.x, 1);
-        const float ws0 = __uint_as_float(__shfl_sync(FULL, rw.y, 0)), ws1 = __uint_as_float(__shfl_sync(FULL, rw.y, 1));
-        const unsigned base0 = acc_s + (ro0 << 2), base1 = acc_s + (ro1 << 2);
-        const bool two = S.w > 1;
-#pragma unroll
-        for (int u = 0; u < NCH; ++u) {
-          const uint2 pp = pn[u];
-          const int pnx = Sn.x + lane + 32 * u;
-          if (pnx < Sn.y) pn[u] = ld_stream(pt + pnx);           // refill the slot with the next piece's chunk
-          if (S.x + 32 * u < S.y) {                               // warp-uniform: chunk u exists in this piece
-            const bool ok = S.x + lane + 32 * u < S.y;           // only the last chunk is partial
-            DBG_ASSERT(!ok || pp.x < (unsigned)CR);
-            const float wc = __uint_as_float(pp.y);
-            const unsigned w4 = (pp.x >> 1) << 2, sh = (pp.x & 1u) << 4;
-            red_shared_if(base0 + w4, fx_contrib(ws0, wc) << sh, ok);
-            red_shared_if(base1 + w4, fx_contrib(ws1, wc) << sh, ok && two);
-            for (int r = 2; r < S.w; ++r) {
-              const unsigned ro = __shfl_sync(FULL, rw.x, r);
-              const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
-              red_shared_if(acc_s + (ro << 2) + w4, fx_contrib(ws, wc) << sh, ok);
-            }
-          }
-        }
-        S = Sn; rw = rwn;
-      }
-    }
+    // ---- phase L: queued pieces.  Long pieces (65..256 postings) with 8 chunk slots, short ones (<= 64)
+    // with 2: most pieces are short and the per-piece cost grows with the number of slots.
+    process_pieces<SEG_PIECE / 32>(acc, segs, +1, nlong, &s_next, pt, b.bt, lane, CR);
+    process_pieces<SHORT_PIECE / 32>(acc, segs + (a.seg_cap - (a.seg_cap * 3 >> 3)), +1, nshort, &s_next2, pt, b.bt, lane, CR);
     __syncthreads();
     PHASE_MARK(3);
     // ---- phase 3: epilogue
