@@ -222,6 +222,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W, B, N, D, t = args.steps, args.warmup, cfg["batch"], cfg["N"], cfg["D"], cfg["threshold"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                            # early: see the wait before the timed region
     n_fresh = (W + K) + (1 + K)                    # value phase + e2e phase (1 warm-up)
     t_gen = time.time()
     shard_gen = bool(cfg.get("heavy_tail")) or args.shard_gen
@@ -310,9 +313,10 @@ def main():
         return float(tns[0])
 
     lib_stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    if rank == 0:          # nvidia-smi's start-up stalls the driver for ~1 s: it must be over before anything is timed
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 10.0:
+            time.sleep(0.05)
     cursor = N
 
     # ------------------------------------------------------------ value: inputs resident in HBM
