@@ -27,6 +27,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
 
 import numpy as np
 import torch
@@ -149,8 +150,12 @@ def cpu_sample(data_np, cfg, n_index, q_lo, n_queries, threads, algo_name):
 
 
 def host_threads():
-    from oracle import oracle as orc
-    return max(1, min(orc.max_threads(), os.cpu_count() or 1))
+    """All host cores this process may use.  (torchrun exports OMP_NUM_THREADS=1; the oracle takes its thread
+    count explicitly, so that default does not throttle the CPU arms.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def run_reference_arm(args, cfg, rank, world):
