@@ -27,7 +27,16 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+# stdout must carry exactly ONE JSON line, but native libraries (e.g. NCCL's version banner) write to fd 1
+# directly: keep the real stdout aside, point fd 1 at stderr for everything else, emit the line at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 import numpy as np
 import torch
@@ -198,7 +207,7 @@ def run_reference_arm(args, cfg, rank, world):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -460,7 +469,7 @@ def main():
                                 "seconds": dt_f,
                                 "opt_value": ro.candidates_unique / dt_o, "opt_seconds": dt_o,
                                 "opt_note": "same sample, weighted postings + dense accumulator (the GPU algorithm on CPU)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
