@@ -143,6 +143,7 @@ struct apss_handle {
   int CR = 0, WARPS = 0, variant = 0, algo = 2, QB = 16;
   double max_sq = 0.0;   // largest squared norm of any pruned vector seen (stored or query)
   size_t smem_bytes = 0;
+  size_t smem_optin = 0;   // device limit; the kernels' attribute is always set to it (the attribute is process-wide)
   std::string err;
   bool frozen = false, custom_keys = false;
   int64_t next_id = 0;
@@ -200,7 +201,7 @@ static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1
 template <int WARPS, int UNROLL>
 static cudaError_t launch_score_t(apss_handle* h, const ScoreArgs& a, bool dup) {
   auto kern = dup ? k_score<WARPS, UNROLL, true> : k_score<WARPS, UNROLL, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
   if (e != cudaSuccess) return e;
   kern<<<h->sm_count, WARPS * 32, h->smem_bytes, h->stream>>>(a);
   return cudaGetLastError();
@@ -219,7 +220,7 @@ static cudaError_t launch_score(apss_handle* h, const ScoreArgs& a, bool dup) {
 template <int WARPS>
 static cudaError_t launch_blk_t(apss_handle* h, const ScoreArgs& a, const BlockArgs& b, bool dup) {
   auto kern = dup ? k_score_blk<WARPS, true> : k_score_blk<WARPS, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
   if (e != cudaSuccess) return e;
   kern<<<h->sm_count, WARPS * 32, h->smem_bytes, h->stream>>>(a, b);
   return cudaGetLastError();
@@ -237,7 +238,7 @@ static cudaError_t launch_blk(apss_handle* h, const ScoreArgs& a, const BlockArg
 template <int QB, int WARPS, int COLS>
 static cudaError_t launch_dense_t(apss_handle* h, const ScoreArgs& a, const BlockArgs& b, const DenseTiles& d, bool dup) {
   auto kern = dup ? k_score_dense<QB, WARPS, COLS, true> : k_score_dense<QB, WARPS, COLS, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
   if (e != cudaSuccess) return e;
   kern<<<h->sm_count * h->ctas_per_sm, WARPS * 32, h->smem_bytes, h->stream>>>(a, b, d);
   return cudaGetLastError();
@@ -277,6 +278,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return bail(APSS_E_NO_DEVICE);
   h->sm_count = prop.multiProcessorCount;
   const size_t max_smem1 = prop.sharedMemPerBlockOptin;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
   // kernel_variant (see include/apss.h): bits 0-7 unroll of the row kernel / candidates per thread of the dense
   // phase, 8-15 warps per CTA, 16-23 scoring kernel (0/3 = dense-head, 1 = row, 2 = query-block), 24-31 queries
   // per block.  The index layout (tile size) follows from the kernel's shared-memory budget.

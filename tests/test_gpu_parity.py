@@ -370,3 +370,34 @@ def test_admission_with_real_max_weights(hi):
         assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
         rejected += rg.n_rejected
     assert 0 < rejected < N
+
+
+def test_two_handles_interleaved_and_threaded():
+    """Distinct handles (different tile sizes / kernels) on the same device, used alternately and from two
+    threads: a handle is single-caller but not thread-affine, distinct handles may run concurrently."""
+    import threading
+    N, D, t, B = 3000, 1 << 11, 0.5, 500
+    data = _synth(N, D, 25, seed=77)
+    n = native()
+    want = {}
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
+    for lo in range(0, N, B):
+        want.update(o.insert_batch(*csr_slice(data, lo, lo + B)).pair_set())
+    handles = [n.Index(D, t, tile_vectors=256), n.Index(D, t), n.Index(D, t, tile_vectors=512, kernel_variant=1 << 16)]
+    got = [dict() for _ in handles]
+    for lo in range(0, N, B):                       # interleaved on one thread
+        for k, g in enumerate(handles):
+            r = g.insert_batch(*csr_slice(data, lo, lo + B))
+            got[k].update(gpu_pairs(g, r))
+    assert all(x == want for x in got)
+    # two threads, one handle each, concurrently
+    res = [dict(), dict()]
+    hs = [n.Index(D, t, tile_vectors=256), n.Index(D, t)]
+
+    def work(k):
+        for lo in range(0, N, B):
+            r = hs[k].insert_batch(*csr_slice(data, lo, lo + B))
+            res[k].update(gpu_pairs(hs[k], r))
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [th.start() for th in ths]; [th.join() for th in ths]
+    assert res[0] == want and res[1] == want
