@@ -143,7 +143,8 @@ struct apss_handle {
   int CR = 0, WARPS = 0, variant = 0, algo = 2, QB = 16;
   double max_sq = 0.0;   // largest squared norm of any pruned vector seen (stored or query)
   size_t smem_bytes = 0;
-  size_t smem_optin = 0;   // device limit; the kernels' attribute is always set to it (the attribute is process-wide)
+  size_t smem_optin = 0;   // device limit; the kernels' dynamic-smem attribute is set to (just under) it, not to this
+                           // handle's need: the attribute is process-wide and handles with different tiles coexist
   std::string err;
   bool frozen = false, custom_keys = false;
   int64_t next_id = 0;
@@ -201,7 +202,7 @@ static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1
 template <int WARPS, int UNROLL>
 static cudaError_t launch_score_t(apss_handle* h, const ScoreArgs& a, bool dup) {
   auto kern = dup ? k_score<WARPS, UNROLL, true> : k_score<WARPS, UNROLL, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(h->smem_bytes, h->smem_optin - 1024));
   if (e != cudaSuccess) return e;
   kern<<<h->sm_count, WARPS * 32, h->smem_bytes, h->stream>>>(a);
   return cudaGetLastError();
@@ -220,7 +221,7 @@ static cudaError_t launch_score(apss_handle* h, const ScoreArgs& a, bool dup) {
 template <int WARPS>
 static cudaError_t launch_blk_t(apss_handle* h, const ScoreArgs& a, const BlockArgs& b, bool dup) {
   auto kern = dup ? k_score_blk<WARPS, true> : k_score_blk<WARPS, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(h->smem_bytes, h->smem_optin - 1024));
   if (e != cudaSuccess) return e;
   kern<<<h->sm_count, WARPS * 32, h->smem_bytes, h->stream>>>(a, b);
   return cudaGetLastError();
@@ -238,7 +239,7 @@ static cudaError_t launch_blk(apss_handle* h, const ScoreArgs& a, const BlockArg
 template <int QB, int WARPS, int COLS>
 static cudaError_t launch_dense_t(apss_handle* h, const ScoreArgs& a, const BlockArgs& b, const DenseTiles& d, bool dup) {
   auto kern = dup ? k_score_dense<QB, WARPS, COLS, true> : k_score_dense<QB, WARPS, COLS, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(h->smem_bytes, h->smem_optin - 1024));
   if (e != cudaSuccess) return e;
   kern<<<h->sm_count * h->ctas_per_sm, WARPS * 32, h->smem_bytes, h->stream>>>(a, b, d);
   return cudaGetLastError();
