@@ -323,7 +323,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
       else if (QB == 16) { if (h->COLS == 2) { if (warps != 32) warps = 16; } else if (warps != 8) warps = 16; }
       else { h->COLS = 4; warps = 16; }
       const char* ds = getenv("APSS_DENSE_SHIFT");
-      if (ds && atoi(ds) >= 0 && atoi(ds) <= 10) h->dense_shift = atoi(ds);
+      if (ds && atoi(ds) >= 0 && atoi(ds) <= 32) h->dense_shift = atoi(ds);   // experiments: see k_dense_select
     }
   }
   if (!warps) return bail(APSS_E_INVALID);

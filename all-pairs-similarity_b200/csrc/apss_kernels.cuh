@@ -551,7 +551,9 @@ __global__ void k_dense_select(int D, int CR, int64_t tile0, int64_t n_local, in
   __shared__ int s_run, s_warp[32], s_removed;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int64_t nt = min((int64_t)CR, n_local - tile * CR);
-  const int thr = max(8, (int)((nt + (1 << dense_shift) - 1) >> dense_shift));
+  // dense_shift < 16: threshold nt / 2^shift; otherwise (dense_shift - 16) sixteenths of the tile
+  const int thr = dense_shift < 16 ? max(8, (int)((nt + (1 << dense_shift) - 1) >> dense_shift))
+                                   : max(8, (int)((nt * (dense_shift - 16) + 15) / 16));
   if (tid == 0) { s_run = 0; s_removed = 0; }
   for (int h = tid; h < HS; h += blockDim.x) d_hash[tile * HS + h] = make_int2(-1, -1);
   __syncthreads();
