@@ -729,7 +729,7 @@ __device__ __forceinline__ void process_pieces(unsigned* acc, const int4* segs, 
         const float wc = __uint_as_float(pp.y);
         const unsigned w4 = (pp.x >> 1) << 2, sh = (pp.x & 1u) << 4;
         red_shared_if(base0 + w4, fx_contrib(ws0, wc) << sh, ok);
-        red_shared_if(base1 + w4, fx_contrib(ws1, wc) << sh, ok && two);
+        if (two) red_shared_if(base1 + w4, fx_contrib(ws1, wc) << sh, ok);     // warp-uniform branch
         for (int r = 2; r < S.w; ++r) {
           const unsigned ro = __shfl_sync(FULL, rw.x, r);
           const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
