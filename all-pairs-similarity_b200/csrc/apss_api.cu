@@ -560,7 +560,12 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   } else thr_emit = -INFINITY;
   // when keys are supplied, q_key lives in b_key (host path) or the caller's buffer (device path)
   const int64_t* d_qkey = d_keys;
-  if (h->custom_keys && !d_qkey) return h->fail(APSS_E_INVALID, "ext_keys were supplied for earlier batches: supply them for every batch");
+  if (h->custom_keys && !d_qkey) {     // keys were used before: this batch gets the default keys (its internal ids)
+    CK(h->b_key.reserve(n, 0, s));
+    k_default_keys<<<cdiv(n, 256), 256, 0, s>>>(n, res.id_base, h->b_key.p);
+    CK(cudaGetLastError()); h->kernel_launches++;
+    d_qkey = h->b_key.p;
+  }
   // ---- query-block transposition for the block kernel: (block, dim)-sorted (row, scaled weight) lists
   BlockArgs blk{};
   int F = 0; unsigned thr_int = 0;

@@ -103,6 +103,11 @@ __global__ void k_prefilter_write(int n, const int64_t* __restrict__ ptr, const 
   }
 }
 
+__global__ void k_default_keys(int n, int64_t id_base, int64_t* __restrict__ keys) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) keys[v] = id_base + v;     // the default key of a vector is its internal id
+}
+
 // ------------------------------------------------------------------ K1: index append
 
 __global__ void k_append_rows(int n, const int32_t* __restrict__ q_ptr, int64_t nnz_base, int64_t n_local,

@@ -135,7 +135,8 @@ void apss_destroy(apss_handle *h);
  *   indptr[n+1], indices[indptr[n]] strictly increasing per vector and < dim, values fp64:
  *     the CSR form of Set[(String, SparkSparseVector)] (Message.scala:13); strings stay on the host.
  *   ext_keys[n] or NULL: one integer per distinct caller id string; vectors with equal keys are
- *     never paired (the string compare at IWA:91).  NULL = every vector distinct.
+ *     never paired (the string compare at IWA:91).  NULL = every vector distinct (its key is its
+ *     internal id; callers that mix both must keep their keys disjoint from the internal ids).
  *   first_dim[n] or NULL: first(q) in Scala Set iteration order, only read when semantics = R0. */
 int32_t apss_insert_batch(apss_handle *h, int32_t n, const int64_t *indptr, const int32_t *indices,
                           const double *values, const int64_t *ext_keys, const int32_t *first_dim,

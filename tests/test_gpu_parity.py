@@ -401,3 +401,14 @@ def test_two_handles_interleaved_and_threaded():
     ths = [threading.Thread(target=work, args=(k,)) for k in range(2)]
     [th.start() for th in ths]; [th.join() for th in ths]
     assert res[0] == want and res[1] == want
+
+
+def test_keys_only_on_some_batches():
+    """ext_keys supplied for one batch only: the others fall back to the default key (= internal id)."""
+    n = native()
+    g = n.Index(64, 0.5)
+    r0 = g.insert_batch(*csr_from_dicts([A]))                                   # id 0, default key 0
+    r1 = g.insert_batch(*csr_from_dicts([dict(A)]), ext_keys=np.array([0]))      # same key as vector 0: never paired
+    assert gpu_pairs(g, r1) == {} and r1.candidates_unique == 0
+    r2 = g.insert_batch(*csr_from_dicts([dict(A)]))                              # default key 2: pairs with both
+    assert set(gpu_pairs(g, r2)) == {(2, 0), (2, 1)}
