@@ -465,6 +465,54 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
   return APSS_OK;
 }
 
+// Per-batch transposition of the (pruned) query batch into blocks of QB consecutive queries: for every block
+// the distinct dimensions it uses and, per dimension, the (row, weight * 2^F) list of the queries having it.
+// Also fixes the fixed-point scale F from the largest squared norm seen (Cauchy-Schwarz bound on any dot
+// product) and the integer emission threshold with its guard band.
+static int32_t transpose_query_blocks(apss_handle* h, int32_t n, int32_t batch_nnz, BlockArgs* blk_out, int* F_out, unsigned* thr_out) {
+  cudaStream_t s = h->stream;
+  const int D = h->cfg.dim;
+  const double t = h->cfg.similarity_threshold;
+  BlockArgs blk{};
+  int F = 0; unsigned thr_int = 0;
+  // fixed-point scale: every dot product is <= max squared norm (Cauchy-Schwarz); keep 2x headroom
+  const double bound = std::max(h->max_sq, 1e-300) * (1.0 + 1e-6);
+  // (dense-head kernel: u16 accumulators, sums stay below 2^15 + one quantum per shared dim)
+  F = (int)std::floor(std::log2((h->algo == 3 ? 32768.0 : 2147483648.0) / bound));
+  F = std::max(-100, std::min(100, F));
+  const double ts = t * std::ldexp(1.0, F) * (1.0 - std::ldexp(1.0, h->algo == 3 ? -16 : -20));
+  const double tmax = h->algo == 3 ? 65535.0 : 4294967295.0;
+  thr_int = ts <= 0 ? 0u : (ts >= tmax ? (unsigned)tmax : (unsigned)std::floor(ts));
+  const int QB = h->QB; const int nqb = (n + QB - 1) / QB;
+  int dimbits = 1; while ((1LL << dimbits) < (int64_t)D) ++dimbits;
+  int qbbits = 1; while ((1LL << qbbits) < nqb) ++qbbits;
+  CK(h->bt_keys_in.reserve(batch_nnz, 0, s)); CK(h->bt_keys_out.reserve(batch_nnz, 0, s)); CK(h->bt_vals_in.reserve(batch_nnz, 0, s));
+  CK(h->bt_vals_out.reserve(batch_nnz, 0, s)); CK(h->ud_key.reserve(batch_nnz + 1, 0, s));
+  CK(h->bt_flags.reserve(batch_nnz + 1, 0, s)); CK(h->bt_pos.reserve(batch_nnz + 1, 0, s));
+  CK(h->ud_dim.reserve(batch_nnz + 1, 0, s)); CK(h->ud_start.reserve(batch_nnz + 2, 0, s)); CK(h->bd_ptr.reserve(nqb + 1, 0, s));
+  k_bt_emit<<<cdiv(batch_nnz, 256), 256, 0, s>>>(n, batch_nnz, h->q_ptr.p, h->q_dim.p, h->q_w.p, QB, h->algo == 3 ? h->CR / 2 : h->CR, dimbits, (float)std::ldexp(1.0, F),
+                                                 h->bt_keys_in.p, h->bt_vals_in.p);
+  CK(cudaGetLastError());
+  size_t tb = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits + qbbits, s));
+  CK(h->cub_tmp.reserve(tb, 0, s));
+  CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits + qbbits, s));
+  k_bt_heads<<<cdiv(batch_nnz + 1, 256), 256, 0, s>>>(batch_nnz, h->bt_keys_out.p, h->bt_flags.p);
+  CK(cudaGetLastError());
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, h->bt_flags.p, h->bt_pos.p, batch_nnz + 1, s));
+  CK(h->cub_tmp.reserve(tb, 0, s));
+  CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tb, h->bt_flags.p, h->bt_pos.p, batch_nnz + 1, s));
+  k_bt_scatter<<<cdiv(batch_nnz + 1, 256), 256, 0, s>>>(batch_nnz, h->bt_keys_out.p, h->bt_flags.p, h->bt_pos.p, dimbits, h->ud_key.p, h->ud_dim.p, h->ud_start.p);
+  CK(cudaGetLastError());
+  k_bt_blocks<<<cdiv(nqb + 1, 128), 128, 0, s>>>(nqb, h->bt_pos.p, batch_nnz, h->ud_key.p, dimbits, h->bd_ptr.p);
+  CK(cudaGetLastError());
+  h->kernel_launches += 9;
+  blk.ud_dim = h->ud_dim.p; blk.ud_start = h->ud_start.p; blk.bd_ptr = h->bd_ptr.p;
+  blk.bt = reinterpret_cast<const uint2*>(h->bt_vals_out.p); blk.QB = QB; blk.n_qblocks = nqb;
+    *blk_out = blk; *F_out = F; *thr_out = thr_int;
+  return APSS_OK;
+}
+
 extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* indptr, const int32_t* indices, const double* values,
                                      const int64_t* ext_keys, const int32_t* first_dim, uint32_t flags, apss_batch_result* out) {
   if (!h) return APSS_E_INVALID;
@@ -566,44 +614,12 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     CK(cudaGetLastError()); h->kernel_launches++;
     d_qkey = h->b_key.p;
   }
-  // ---- query-block transposition for the block kernel: (block, dim)-sorted (row, scaled weight) lists
+  // ---- query-block transposition for the block kernels: (block, dim)-sorted (row, scaled weight) lists
   BlockArgs blk{};
   int F = 0; unsigned thr_int = 0;
   if (h->algo != 1 && batch_nnz) {
-    // fixed-point scale: every dot product is <= max squared norm (Cauchy-Schwarz); keep 2x headroom
-    const double bound = std::max(h->max_sq, 1e-300) * (1.0 + 1e-6);
-    // (dense-head kernel: u16 accumulators, sums stay below 2^15 + one quantum per shared dim)
-    F = (int)std::floor(std::log2((h->algo == 3 ? 32768.0 : 2147483648.0) / bound));
-    F = std::max(-100, std::min(100, F));
-    const double ts = t * std::ldexp(1.0, F) * (1.0 - std::ldexp(1.0, h->algo == 3 ? -16 : -20));
-    const double tmax = h->algo == 3 ? 65535.0 : 4294967295.0;
-    thr_int = ts <= 0 ? 0u : (ts >= tmax ? (unsigned)tmax : (unsigned)std::floor(ts));
-    const int QB = h->QB; const int nqb = (n + QB - 1) / QB;
-    int dimbits = 1; while ((1LL << dimbits) < (int64_t)D) ++dimbits;
-    int qbbits = 1; while ((1LL << qbbits) < nqb) ++qbbits;
-    CK(h->bt_keys_in.reserve(batch_nnz, 0, s)); CK(h->bt_keys_out.reserve(batch_nnz, 0, s)); CK(h->bt_vals_in.reserve(batch_nnz, 0, s));
-    CK(h->bt_vals_out.reserve(batch_nnz, 0, s)); CK(h->ud_key.reserve(batch_nnz + 1, 0, s));
-    CK(h->bt_flags.reserve(batch_nnz + 1, 0, s)); CK(h->bt_pos.reserve(batch_nnz + 1, 0, s));
-    CK(h->ud_dim.reserve(batch_nnz + 1, 0, s)); CK(h->ud_start.reserve(batch_nnz + 2, 0, s)); CK(h->bd_ptr.reserve(nqb + 1, 0, s));
-    k_bt_emit<<<cdiv(batch_nnz, 256), 256, 0, s>>>(n, batch_nnz, h->q_ptr.p, h->q_dim.p, h->q_w.p, QB, h->algo == 3 ? h->CR / 2 : h->CR, dimbits, (float)std::ldexp(1.0, F),
-                                                   h->bt_keys_in.p, h->bt_vals_in.p);
-    CK(cudaGetLastError());
-    size_t tb = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits + qbbits, s));
-    CK(h->cub_tmp.reserve(tb, 0, s));
-    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits + qbbits, s));
-    k_bt_heads<<<cdiv(batch_nnz + 1, 256), 256, 0, s>>>(batch_nnz, h->bt_keys_out.p, h->bt_flags.p);
-    CK(cudaGetLastError());
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, h->bt_flags.p, h->bt_pos.p, batch_nnz + 1, s));
-    CK(h->cub_tmp.reserve(tb, 0, s));
-    CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tb, h->bt_flags.p, h->bt_pos.p, batch_nnz + 1, s));
-    k_bt_scatter<<<cdiv(batch_nnz + 1, 256), 256, 0, s>>>(batch_nnz, h->bt_keys_out.p, h->bt_flags.p, h->bt_pos.p, dimbits, h->ud_key.p, h->ud_dim.p, h->ud_start.p);
-    CK(cudaGetLastError());
-    k_bt_blocks<<<cdiv(nqb + 1, 128), 128, 0, s>>>(nqb, h->bt_pos.p, batch_nnz, h->ud_key.p, dimbits, h->bd_ptr.p);
-    CK(cudaGetLastError());
-    h->kernel_launches += 9;
-    blk.ud_dim = h->ud_dim.p; blk.ud_start = h->ud_start.p; blk.bd_ptr = h->bd_ptr.p;
-    blk.bt = reinterpret_cast<const uint2*>(h->bt_vals_out.p); blk.QB = QB; blk.n_qblocks = nqb;
+    const int32_t rc = transpose_query_blocks(h, n, batch_nnz, &blk, &F, &thr_int);
+    if (rc != APSS_OK) return rc;
   }
   for (int attempt = 0; attempt < 3; ++attempt) {
     ScoreArgs a{};
