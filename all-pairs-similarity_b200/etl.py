@@ -175,3 +175,51 @@ def l2_normalise(indptr, values):
         if n > 0:
             out[a:b] = values[a:b] / n
     return out
+
+
+def vector_from_text(text: str) -> Tuple[int, np.ndarray, np.ndarray]:
+    """Inverse of vector_to_text: SparseVector.fromString (vector/SparseVector.scala:132-141).
+    Splits on ",[" into exactly three parts or raises like the reference ("cannot parse ...")."""
+    parts = text.split(",[")
+    if len(parts) != 3:
+        raise ValueError("cannot parse " + text)
+    size = int(parts[0].replace("(", ""))
+    idx = np.array([int(x) for x in parts[1].replace("]", "").split(",")], np.int32)
+    val = np.array([float(x) for x in parts[2].replace("])", "").split(",")], np.float64)
+    return size, idx, val
+
+
+def ccweb_line_parser(line: str) -> Tuple[str, int, np.ndarray, np.ndarray]:
+    """CCWEBVideoLoadGenerator.lineParser (benchmark/CCWEBVideoLoadGenerator.scala:10-21): a line
+    "(id,size,[v0,v1,...])" holds a DENSE feature vector; every bracket is stripped, the LAST `size`
+    comma fields are the values (takeRight, :16) and the non-zero ones become the sparse vector."""
+    for ch in "()[]":
+        line = line.replace(ch, "")
+    fields = line.split(",")
+    while fields and fields[-1] == "":           # Java split(",") drops trailing empty strings
+        fields.pop()
+    video_id, size = fields[0], int(fields[1])
+    dense = np.array([float(x) for x in fields[len(fields) - size:]] if size > 0 else [], np.float64)
+    if dense.shape[0] != size:
+        # allValues(_) for _ in 0 until size would throw ArrayIndexOutOfBounds in the reference
+        raise IndexError("line holds %d values, header says %d" % (dense.shape[0], size))
+    nz = np.nonzero(dense != 0)[0].astype(np.int32)
+    return video_id, size, nz, dense[nz]
+
+
+def ccweb_generate_vectors(path: str) -> List[Tuple[str, int, np.ndarray, np.ndarray]]:
+    """CCWEBVideoLoadGenerator.generateVectors (:23-29): one vector per line of the file."""
+    with open(path, "r", encoding="utf-8", errors="replace") as f:
+        return [ccweb_line_parser(ln.rstrip("\r\n")) for ln in f.read().split("\n") if ln != ""]
+
+
+def load_runner_vector(videos, msg_count: int, vector_dim: int):
+    """LoadRunner.generateVector (benchmark/LoadGenerator.scala:30-41): the video msg_count % len,
+    values divided by sqrt(left-to-right sum of squares), size replaced by vectorDim, id = msgCount."""
+    _, _, idx, val = videos[msg_count % len(videos)]
+    sq = 0.0
+    for x in val:                                 # foldLeft(0.0)(sum + value * value)
+        sq = sq + float(x) * float(x)
+    norm = math.sqrt(sq)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return str(msg_count), vector_dim, idx, val / norm

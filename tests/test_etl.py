@@ -1,6 +1,7 @@
 """TF-IDF ETL restatement (config C1's input).  The strongest check runs only where the reference is
 mounted: the text our restatement produces for data/maildir_small is compared, 512-byte chunk by
 chunk, with the Hadoop CRC side files of the reference's own (missing) output data/output/part-0000{0..3}."""
+import math
 import os
 import zlib
 
@@ -87,3 +88,36 @@ def test_etl_reproduces_reference_output_crc():
         a, b = g["indptr"][j], g["indptr"][j + 1]
         assert np.array_equal(g["indices"][a:b], indices[indptr[i]:indptr[i + 1]])
         assert np.array_equal(g["values"][a:b], values[indptr[i]:indptr[i + 1]])
+
+
+def test_vector_text_round_trip():
+    # SparseVector.scala:132-141 reads back what :204-205 writes
+    idx = np.array([3, 17, 1000], np.int32)
+    val = np.array([0.5, 1.25e-5, 3.0], np.float64)
+    txt = etl.vector_to_text(1 << 20, idx, val)
+    assert txt == "(1048576,[3,17,1000],[0.5,1.25E-5,3.0])"
+    size, i2, v2 = etl.vector_from_text(txt)
+    assert size == 1 << 20 and np.array_equal(i2, idx) and np.array_equal(v2, val)
+    with pytest.raises(ValueError, match="cannot parse"):
+        etl.vector_from_text("(3,[1,2])")
+
+
+def test_ccweb_line_parser(tmp_path):
+    # CCWEBVideoLoadGenerator.scala:10-21
+    vid, size, idx, val = etl.ccweb_line_parser("(v_17,6,[0.0,2.0,0,0.5,0.0,1])")
+    assert vid == "v_17" and size == 6
+    assert idx.tolist() == [1, 3, 5] and val.tolist() == [2.0, 0.5, 1.0]
+    # takeRight(size): extra leading fields are ignored
+    vid, size, idx, val = etl.ccweb_line_parser("(a,2,[9,9,0,4])")
+    assert idx.tolist() == [1] and val.tolist() == [4.0]
+    with pytest.raises(IndexError):
+        etl.ccweb_line_parser("(a,5,[1,2])")
+    f = tmp_path / "cc.txt"
+    f.write_text("(a,3,[1,0,2])\n(b,3,[0,0,4])\n")
+    videos = etl.ccweb_generate_vectors(str(f))
+    assert [v[0] for v in videos] == ["a", "b"]
+    # LoadGenerator.scala:30-41: cycle through the videos, id = message counter, unit norm
+    mid, dim, idx, val = etl.load_runner_vector(videos, 3, 64)
+    assert mid == "3" and dim == 64 and idx.tolist() == [2] and val.tolist() == [1.0]
+    mid, dim, idx, val = etl.load_runner_vector(videos, 2, 64)
+    assert idx.tolist() == [0, 2] and val.tolist() == [1 / math.sqrt(5.0), 2 / math.sqrt(5.0)]

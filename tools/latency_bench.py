@@ -6,7 +6,10 @@ test phase replays `totalMessageCount` vectors and records the response time of 
 (:112-131): message count, average / max / min response time.  Here time is measured around the call
 (the in-process transport is synchronous) with perf_counter, in milliseconds.
 
-  python tools/latency_bench.py [--config C2] [--n-index 100000] [--messages 500] [--bulk]
+  python tools/latency_bench.py [--config C2] [--n-index 100000] [--messages 500] [--bulk] [--ccweb FILE]
+--ccweb reads the reference's CC_WEB_VIDEO text format, "(id,size,[dense values])" per line
+(CCWEBVideoLoadGenerator.scala:10-29), normalises like LoadRunner.generateVector (LoadGenerator.scala:30-41)
+and uses those vectors instead of the synthetic ones (the dataset itself is not shipped with the reference).
 --bulk pre-loads the index with large batches instead of one message per vector (the per-message
 warm-up of the reference is itself reported when it is used)."""
 import argparse
@@ -29,13 +32,26 @@ ap.add_argument("--n-index", type=int, default=0)
 ap.add_argument("--messages", type=int, default=500)
 ap.add_argument("--bulk", action="store_true")
 ap.add_argument("--out", default="")
+ap.add_argument("--ccweb", default="")
+ap.add_argument("--threshold", type=float, default=0.0)
 args = ap.parse_args()
 cfg = synth.CONFIGS[args.config]
-N = args.n_index or cfg["N"]
-D, t = cfg["D"], cfg["threshold"]
-data = synth.generate(N, D, cfg["nnz_mean"], seed=cfg["seed"], device="cuda" if torch.cuda.is_available() else "cpu").numpy()
-ip, ix, v = data
-vec = lambda i: M.SparkSparseVector(D, ix[ip[i]:ip[i + 1]], v[ip[i]:ip[i + 1]])
+if args.ccweb:
+    from apss_b200 import etl
+    videos = etl.ccweb_generate_vectors(args.ccweb)
+    N = min(args.n_index, len(videos)) if args.n_index else len(videos)
+    D = max(v[1] for v in videos)                                 # cpslab.allpair.vectorDim
+    t = args.threshold or cfg["threshold"]
+
+    def vec(i):
+        _, dim, idx, val = etl.load_runner_vector(videos, i, D)
+        return M.SparkSparseVector(dim, idx, val)
+else:
+    N = args.n_index or cfg["N"]
+    D, t = cfg["D"], args.threshold or cfg["threshold"]
+    data = synth.generate(N, D, cfg["nnz_mean"], seed=cfg["seed"], device="cuda" if torch.cuda.is_available() else "cpu").numpy()
+    ip, ix, v = data
+    vec = lambda i: M.SparkSparseVector(D, ix[ip[i]:ip[i + 1]], v[ip[i]:ip[i + 1]])
 
 conf = {"cpslab.allpair.similarityThreshold": t, "cpslab.allpair.outputIODuration": 0, "cpslab.allpair.benchmark.expDuration": 30000,
         "cpslab.allpair.vectorDim": D, "cpslab.allpair.indexThreshold": 0.0, "cpslab.allpair.ioTriggerPeriod": 0}
@@ -72,7 +88,7 @@ for k in range(args.messages):
     lat.append((time.perf_counter() - start) * 1e3)
     neighbours += sum(len(m) for m in out.output.values())
 lat = np.array(lat)
-res = {"config": args.config, "index_vectors": N, "messages": args.messages, "warmup_s": warm_s,
+res = {"config": args.ccweb or args.config, "index_vectors": N, "messages": args.messages, "warmup_s": warm_s,
        "warmup_mode": "bulk batches of 4096" if args.bulk else "one vector per message",
        "warmup_ms_per_message": (float(np.mean(warm_lat)) if warm_lat else None),
        "avg_ms": float(lat.mean()), "max_ms": float(lat.max()), "min_ms": float(lat.min()),
