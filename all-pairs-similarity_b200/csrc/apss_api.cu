@@ -165,6 +165,13 @@ struct apss_handle {
   // dense-head tiles (algo 3)
   VmBuf<int32_t> dn_cnt, dn_dim, dn_len, tile_cnt; VmBuf<int2> dn_hash; VmBuf<float> dn_w; DevBuf<unsigned long long> s_vals_out;
   int dense_shift = 2, COLS = 4, ctas_per_sm = 1, seg_cap = SEG_CAP;
+  // exact index reduction (cfg.pruning): document frequencies, per stored component "not indexed" flag, per
+  // stored vector norm bound of its un-indexed part; per batch the same + rank-sort scratch
+  bool prune = false; double prune_lim = 0.0, max_qnorm = 1.0;
+  DevBuf<int32_t> df; VmBuf<uint8_t> fwd_skip; VmBuf<float> row_ub;
+  DevBuf<uint8_t> q_skip; DevBuf<float> q_cu, q_nrm;
+  DevBuf<unsigned long long> pr_keys_in, pr_keys_out, pr_vals_in, pr_vals_out;
+  int64_t tot_skipped = 0;
   // query-block transposition (v2 kernel)
   DevBuf<unsigned long long> bt_keys_in, bt_keys_out, bt_vals_in, bt_vals_out, ud_key; DevBuf<int32_t> bt_flags, bt_pos, ud_dim, ud_start, bd_ptr;
   // outputs
@@ -270,6 +277,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) { cudaGetLastError(); return APSS_E_NO_DEVICE; }
   apss_handle* h = new apss_handle();
   h->cfg = *cfg; h->cfg.max_weight = nullptr; h->device = cfg->device;
+  h->fwd_skip.device = h->row_ub.device = cfg->device;
   h->fwd_ptr.device = h->fwd_idx.device = h->fwd_val.device = h->gid.device = h->key.device = h->post.device = h->dir.device =
       h->tile_base.device = h->dn_cnt.device = h->dn_dim.device = h->dn_len.device = h->tile_cnt.device = h->dn_hash.device =
       h->dn_w.device = cfg->device;
@@ -338,6 +346,17 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
     if (h->maxw.reserve(cfg->dim, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
     if (cudaMemcpyAsync(h->maxw.p, cfg->max_weight, sizeof(double) * cfg->dim, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return bail(APSS_E_CUDA);
   }
+  if (cfg->pruning) {
+    if (cfg->pruning != 1 || algo != 3) return bail(APSS_E_INVALID);      // only the default scoring kernel applies the bound
+    const double alpha = cfg->prune_alpha == 0.0 ? 0.8 : cfg->prune_alpha;
+    const double qn = cfg->max_query_norm == 0.0 ? 1.0 : cfg->max_query_norm;
+    if (!(alpha > 0.0 && alpha < 1.0) || !(qn > 0.0) || !std::isfinite(qn)) return bail(APSS_E_INVALID);
+    const double t = cfg->similarity_threshold;
+    h->prune = true; h->max_qnorm = qn;
+    h->prune_lim = t > 0.0 ? alpha * t * t / (qn * qn) * (1.0 - std::ldexp(1.0, -20)) : 0.0;
+    if (h->df.reserve(cfg->dim, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+    if (cudaMemsetAsync(h->df.p, 0, sizeof(int32_t) * (size_t)cfg->dim, h->stream) != cudaSuccess) return bail(APSS_E_CUDA);
+  }
   if (cfg->reserve_vectors > 0) {
     int64_t nv = cfg->reserve_vectors, nt = (nv + CR - 1) / CR;
     if (h->fwd_ptr.reserve(nv + 1, 0, h->stream) != cudaSuccess || h->gid.reserve(nv, 0, h->stream) != cudaSuccess ||
@@ -376,6 +395,8 @@ extern "C" void apss_destroy(apss_handle* h) {
   h->dn_cnt.release(); h->dn_dim.release(); h->dn_len.release(); h->tile_cnt.release(); h->dn_hash.release(); h->dn_w.release(); h->s_vals_out.release();
   h->s_keys_in.release(); h->s_keys_out.release(); h->s_vals_in.release(); h->s_tile_start.release(); h->cub_tmp.release();
   h->pf_q.release(); h->pf_c.release(); h->pf_est.release(); h->out_q.release(); h->out_c.release(); h->out_sim.release();
+  h->df.release(); h->fwd_skip.release(); h->row_ub.release(); h->q_skip.release(); h->q_cu.release(); h->q_nrm.release();
+  h->pr_keys_in.release(); h->pr_keys_out.release(); h->pr_vals_in.release(); h->pr_vals_out.release();
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->h_total) cudaFreeHost(h->h_total);
@@ -389,6 +410,30 @@ extern "C" void apss_destroy(apss_handle* h) {
 
 // IWA:61-71 on the GPU: append the batch's pruned vectors to the forward store and (re)build the
 // index tiles they fall into: at most the last, partially filled tile plus the new ones.
+// Exact index reduction: choose, for every vector of the batch, the components that stay out of the index
+// (see k_prune_mark).  Fills q_skip[batch_nnz] and q_cu[n]; the document frequencies include this batch.
+static int32_t prune_select(apss_handle* h, int32_t n, int32_t batch_nnz) {
+  cudaStream_t s = h->stream;
+  CK(h->q_skip.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_cu.reserve(n, 0, s));
+  CK(h->pr_keys_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_keys_out.reserve(std::max(batch_nnz, 1), 0, s));
+  CK(h->pr_vals_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_vals_out.reserve(std::max(batch_nnz, 1), 0, s));
+  if (batch_nnz) {
+    k_df_update<<<cdiv(batch_nnz, 256), 256, 0, s>>>(batch_nnz, h->q_dim.p, h->df.p);
+    CK(cudaGetLastError());
+    k_rank_keys<<<cdiv(n, 128), 128, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->df.p, h->pr_keys_in.p, h->pr_vals_in.p);
+    CK(cudaGetLastError());
+    int rowbits = 1; while ((1LL << rowbits) < n) ++rowbits;
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->pr_keys_in.p, h->pr_keys_out.p, h->pr_vals_in.p, h->pr_vals_out.p, batch_nnz, 0, 31 + rowbits, s));
+    CK(h->cub_tmp.reserve(tb, 0, s));
+    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->pr_keys_in.p, h->pr_keys_out.p, h->pr_vals_in.p, h->pr_vals_out.p, batch_nnz, 0, 31 + rowbits, s));
+    h->kernel_launches += 4;
+  }
+  k_prune_mark<<<cdiv(n, 128), 128, 0, s>>>(n, h->q_ptr.p, h->q_val.p, h->pr_vals_out.p, h->prune_lim, h->q_skip.p, h->q_cu.p, h->d_counters);
+  CK(cudaGetLastError()); h->kernel_launches++;
+  return APSS_OK;
+}
+
 static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const int64_t* d_ext_keys) {
   cudaStream_t s = h->stream;
   const int CR = h->CR; const int D = h->cfg.dim;
@@ -403,6 +448,11 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
   if (batch_nnz) {
     CK(cudaMemcpyAsync(h->fwd_idx.p + nnz_old, h->q_dim.p, sizeof(int32_t) * batch_nnz, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(h->fwd_val.p + nnz_old, h->q_val.p, sizeof(double) * batch_nnz, cudaMemcpyDeviceToDevice, s));
+  }
+  if (h->prune) {
+    CK(h->fwd_skip.reserve(std::max<int64_t>(nnz_new, 1), nnz_old, s)); CK(h->row_ub.reserve(n_new, n_old, s));
+    if (batch_nnz) CK(cudaMemcpyAsync(h->fwd_skip.p + nnz_old, h->q_skip.p, (size_t)batch_nnz, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->row_ub.p + n_old, h->q_cu.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, s));
   }
   // tiles to (re)build: [tile0, tile1)
   const int64_t tile0 = n_old / CR, tile1 = (n_new + CR - 1) / CR;
@@ -422,11 +472,11 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
   CK(h->tile_base.reserve(tile1 + 1, tile0, s));
   CK(h->s_tile_start.reserve(ntiles_aff + 1, 0, s));
   int dimbits = 1; while ((1LL << dimbits) < (int64_t)D + 1) ++dimbits;
-  int tilebits = 1; while ((1LL << tilebits) < ntiles_aff) ++tilebits;
+  int tilebits = 1; while ((1LL << tilebits) < ntiles_aff + 1) ++tilebits;   // + the "not indexed" sentinel tile
   if (m > 0) {
     CK(h->s_keys_in.reserve(m, 0, s)); CK(h->s_keys_out.reserve(m, 0, s)); CK(h->s_vals_in.reserve(m, 0, s));
-    k_emit_postings<<<cdiv(m, 256), 256, 0, s>>>(nnz_lo, nnz_new, row_lo, n_new, h->fwd_ptr.p, h->fwd_idx.p, h->fwd_val.p, CR, tile0, dimbits,
-                                                  h->s_keys_in.p, h->s_vals_in.p);
+    k_emit_postings<<<cdiv(m, 256), 256, 0, s>>>(nnz_lo, nnz_new, row_lo, n_new, h->fwd_ptr.p, h->fwd_idx.p, h->fwd_val.p,
+                                                  h->prune ? h->fwd_skip.p : nullptr, ntiles_aff, CR, tile0, dimbits, h->s_keys_in.p, h->s_vals_in.p);
     CK(cudaGetLastError()); h->kernel_launches++;
     size_t tmp = 0;
     unsigned long long* vals_out = reinterpret_cast<unsigned long long*>(h->post.p + post_base);
@@ -453,7 +503,7 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(h->dn_w.p + (size_t)tile0 * KD * CR, 0, (size_t)ntiles_aff * KD * CR * sizeof(float), s));
     if (m > 0) {
-      k_post_scatter<<<cdiv(m, 256), 256, 0, s>>>(m, h->s_keys_out.p, h->s_vals_out.p, dimbits, tile0, CR, h->s_tile_start.p, h->tile_base.p,
+      k_post_scatter<<<cdiv(m, 256), 256, 0, s>>>(m, h->s_keys_out.p, h->s_vals_out.p, dimbits, tile0, ntiles_aff, CR, h->s_tile_start.p, h->tile_base.p,
                                                    h->dn_cnt.p, h->dn_dim.p, h->dn_len.p, h->dn_hash.p, h->dn_w.p,
                                                    reinterpret_cast<unsigned long long*>(h->post.p), (long long)h->post.cap);
       CK(cudaGetLastError());
@@ -553,10 +603,11 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
 
   // ---- K5: validate + admit + prune (count, scan, write)
   CK(h->q_cnt.reserve(n + 1, 0, s)); CK(h->q_ptr.reserve(n + 1, 0, s)); CK(h->q_status.reserve(n, 0, s));
+  if (h->prune) CK(h->q_nrm.reserve(n, 0, s));
   CK(cudaMemsetAsync(h->d_counters, 0, C_COUNT * sizeof(unsigned long long), s));
   const double admit_thr = (flags & APSS_BATCH_SKIP_ADMIT) ? -INFINITY : h->cfg.similarity_threshold;
   k_prefilter_count<<<cdiv(n + 1, 128), 128, 0, s>>>(n, d_ptr, d_idx, d_val, D, h->maxw.p, admit_thr, h->cfg.index_threshold,
-                                                     h->q_cnt.p, h->q_status.p, h->d_counters);
+                                                     h->q_cnt.p, h->q_status.p, h->prune ? h->q_nrm.p : nullptr, h->d_counters);
   CK(cudaGetLastError());
   size_t tmp = 0;
   CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, h->q_cnt.p, h->q_ptr.p, n + 1, s));
@@ -575,7 +626,13 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   const int32_t batch_nnz = h->h_total[0];
   res.n_rejected = (int32_t)h->h_counters[C_NREJ]; res.n_empty = (int32_t)h->h_counters[C_NEMPTY]; res.n_active = (int32_t)h->h_counters[C_NACTIVE];
   h->max_nnz_seen = std::max(h->max_nnz_seen, (int)h->h_counters[C_MAXNNZ]);
-  { double sq; std::memcpy(&sq, &h->h_counters[C_MAXSQ], sizeof sq); if (sq > h->max_sq) h->max_sq = sq; }
+  {
+    double sq; std::memcpy(&sq, &h->h_counters[C_MAXSQ], sizeof sq);
+    // index reduction relies on |q| <= max_query_norm for EVERY query: refuse the batch rather than mis-score it
+    if (h->prune && sq > h->max_qnorm * h->max_qnorm * (1.0 + 1e-9))
+      return h->fail(APSS_E_INPUT, "pruning: a vector of this batch has L2 norm %.9g > max_query_norm %.9g", std::sqrt(sq), h->max_qnorm);
+    if (sq > h->max_sq) h->max_sq = sq;
+  }
   CK(h->q_dim.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_val.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_w.reserve(std::max(batch_nnz, 1), 0, s));
   k_prefilter_write<<<cdiv(n, 128), 128, 0, s>>>(n, d_ptr, d_idx, d_val, h->cfg.index_threshold, h->q_status.p, h->q_ptr.p, h->q_dim.p, h->q_val.p, h->q_w.p);
   CK(cudaGetLastError()); h->kernel_launches++;
@@ -585,6 +642,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   int64_t q_local_base = -1;
   if (!query_only) {
     q_local_base = h->n_local;
+    if (h->prune) { const int32_t rcp = prune_select(h, n, batch_nnz); if (rcp != APSS_OK) return rcp; }
     int32_t rc = index_append(h, n, batch_nnz, d_keys);
     if (rc != APSS_OK) return rc;
     h->next_id += n;
@@ -592,7 +650,9 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
 
   if ((flags & APSS_BATCH_INDEX_ONLY) && !query_only) {
     CK(cudaEventRecord(h->ev_b1, s));
+    if (h->prune) CK(cudaMemcpyAsync(h->h_counters + C_SKIPPED, h->d_counters + C_SKIPPED, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (h->prune) { h->tot_skipped += (int64_t)h->h_counters[C_SKIPPED]; h->n_post = h->nnz - h->tot_skipped; }
     float ms0 = 0.f; CK(cudaEventElapsedTime(&ms0, h->ev_b0, h->ev_b1)); res.device_ms = ms0;
     h->last_n = n; h->last_pairs = 0;
     if (out) *out = res;
@@ -631,13 +691,14 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     a.counters = h->d_counters;
     a.tile_cnt = h->algo == 3 ? h->tile_cnt.p : nullptr; a.post_cap = (long long)h->post.cap; a.seg_cap = h->seg_cap;
     a.total_items = (unsigned long long)h->ntiles * (unsigned long long)n;
+    a.row_ub = h->prune ? h->row_ub.p : nullptr; a.q_nrm = h->prune ? h->q_nrm.p : nullptr;
     CK(cudaMemsetAsync(h->d_counters, 0, 7 * sizeof(unsigned long long), s));   // keep the prefilter tallies
     CK(cudaMemsetAsync(h->d_counters + C_PHASE, 0, 8 * sizeof(unsigned long long), s));
     CK(cudaEventRecord(h->ev_s0, s));
     if (h->algo == 1) {
       if (a.total_items && batch_nnz) { CK(launch_score(h, a, h->custom_keys)); h->score_launches++; h->kernel_launches++; }
     } else if (h->ntiles && batch_nnz) {
-      blk.thr_int = thr_int; blk.inv_scale = (float)std::ldexp(1.0, -F);
+      blk.thr_int = thr_int; blk.inv_scale = (float)std::ldexp(1.0, -F); blk.scale = (float)std::ldexp(1.0, F);
       a.total_items = (unsigned long long)h->ntiles * (unsigned long long)blk.n_qblocks;
       if (h->algo == 3) {
         DenseTiles dtl{h->dn_cnt.p, h->dn_dim.p, h->dn_len.p, h->dn_hash.p, h->dn_w.p};
@@ -656,6 +717,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     CK(cudaEventRecord(h->ev_b1, s));
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->h_counters + C_PHASE, h->d_counters + C_PHASE, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if (h->prune) CK(cudaMemcpyAsync(h->h_counters + C_SKIPPED, h->d_counters + C_SKIPPED, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (h->h_counters[C_PF] <= h->pf_q.cap) break;
     if (attempt == 2) return h->fail(APSS_E_NOMEM, "pair buffer overflow persisted");
@@ -671,6 +733,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   res.n_pairs = (int64_t)h->h_counters[C_FINAL];
   res.n_pairs_r1 = (int64_t)h->h_counters[C_R1];
   for (int k = 0; k < 8; ++k) h->phase_cycles[k] = (int64_t)h->h_counters[C_PHASE + k];
+  if (h->prune && !query_only) { h->tot_skipped += (int64_t)h->h_counters[C_SKIPPED]; h->n_post = h->nnz - h->tot_skipped; }
   res.work_items = (int64_t)((unsigned long long)h->ntiles * (unsigned long long)(h->algo == 1 ? n : (n + h->QB - 1) / h->QB));
   h->last_n = n; h->last_pairs = res.n_pairs;
   h->tot_postings += res.postings_visited; h->tot_cands += res.candidates_unique; h->tot_pairs += res.n_pairs; h->tot_pf += res.n_prefilter;
@@ -731,6 +794,7 @@ extern "C" int32_t apss_get_stats(apss_handle* h, apss_stats* out) {
   s.score_launches = h->score_launches; s.kernel_launches = h->kernel_launches; s.tot_score_ms = h->tot_score_ms;
   for (int k = 0; k < 8; ++k) s.phase_cycles[k] = h->phase_cycles[k];
   s.frozen = h->frozen; s.tile_vectors = h->CR; s.warps_per_cta = h->WARPS; s.sm_count = h->sm_count;
+  s.n_unindexed = h->tot_skipped;
   *out = s;
   return APSS_OK;
 }

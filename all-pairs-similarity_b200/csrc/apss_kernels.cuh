@@ -39,6 +39,7 @@ enum Counter : int {
   C_WORK = 6,      // persistent-kernel work cursor
   C_NREJ = 7, C_NEMPTY = 8, C_NACTIVE = 9, C_MAXNNZ = 10,
   C_MAXSQ = 11,    // max squared L2 norm of a pruned vector (bits of a non-negative double)
+  C_SKIPPED = 12,  // components of this batch left out of the index by exact index reduction
   C_PHASE = 16,    // 8 per-phase cycle totals of the dense kernel (thread 0 of every CTA)
   C_COUNT = 24
 };
@@ -64,7 +65,7 @@ __device__ __forceinline__ uint2 ld_stream(const uint2* p) {
 __global__ void k_prefilter_count(int n, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                                   const double* __restrict__ val, int D, const double* __restrict__ maxw,
                                   double sim_thr, double idx_thr, int32_t* __restrict__ cnt,
-                                  uint8_t* __restrict__ status, unsigned long long* counters) {
+                                  uint8_t* __restrict__ status, float* __restrict__ q_nrm, unsigned long long* counters) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v > n) return;
   if (v == n) { cnt[n] = 0; return; }
@@ -88,6 +89,8 @@ __global__ void k_prefilter_count(int n, const int64_t* __restrict__ ptr, const 
     atomicMax(&counters[C_MAXSQ], (unsigned long long)__double_as_longlong(sq));
   }
   status[v] = st; cnt[v] = kept;
+  // upper bound of the L2 norm of the pruned vector (used only by the index-reduction bound)
+  if (q_nrm) q_nrm[v] = st == 2 ? __double2float_ru(sqrt(sq) * (1.0 + 1e-9)) : 0.f;
 }
 
 __global__ void k_prefilter_write(int n, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
@@ -108,6 +111,52 @@ __global__ void k_default_keys(int n, int64_t id_base, int64_t* __restrict__ key
   if (v < n) keys[v] = id_base + v;     // the default key of a vector is its internal id
 }
 
+
+// ------------------------------------------------------------------ exact index reduction
+
+// Which components of a vector c stay OUT of the index: rank its components by document frequency
+// (descending; ties by ascending dim) and take the longest prefix U whose squared weights sum to at most
+// `lim` = alpha * (t / max query norm)^2.  For any query q with |q| <= max query norm,
+// dot(q, c restricted to U) <= |q| |c_U| <= sqrt(alpha) t < t, so a pair with dot >= t always shares an
+// indexed component, and the candidate test becomes  indexed part + |q| |c_U| >= t  (checked in the
+// scoring kernel's epilogue; the fp64 verify kernel then computes the full dot product as before).
+__global__ void k_df_update(int nnz, const int32_t* __restrict__ q_dim, int32_t* __restrict__ df) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nnz) atomicAdd(df + q_dim[p], 1);
+}
+
+// sort key (row, max_df - df): a stable sort keeps ascending dims among equal frequencies
+__global__ void k_rank_keys(int n, const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim,
+                            const int32_t* __restrict__ df, unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  for (int p = q_ptr[v]; p < q_ptr[v + 1]; ++p) {
+    keys[p] = ((unsigned long long)(unsigned)v << 31) | (unsigned long long)(0x7fffffff - df[q_dim[p]]);
+    vals[p] = (unsigned long long)(unsigned)p;
+  }
+}
+
+// one thread per vector: walk its components in rank order, fp64 running sum of squares (separate
+// multiply and add, like the oracle), mark the prefix, record |c_U| rounded up
+__global__ void k_prune_mark(int n, const int32_t* __restrict__ q_ptr, const double* __restrict__ q_val,
+                             const unsigned long long* __restrict__ ranked, double lim,
+                             uint8_t* __restrict__ skip, float* __restrict__ cu, unsigned long long* counters) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int a = q_ptr[v], b = q_ptr[v + 1];
+  double s = 0.0; int k = a;
+  for (; k < b; ++k) {
+    const double x = q_val[(int)ranked[k]];
+    const double s2 = __dadd_rn(s, __dmul_rn(x, x));
+    if (!(s2 <= lim)) break;
+    s = s2;
+    skip[(int)ranked[k]] = 1;
+  }
+  if (k > a) atomicAdd(&counters[C_SKIPPED], (unsigned long long)(k - a));
+  for (int j = k; j < b; ++j) skip[(int)ranked[j]] = 0;
+  cu[v] = s > 0.0 ? __double2float_ru(sqrt(s) * (1.0 + 1e-9)) : 0.f;
+}
+
 // ------------------------------------------------------------------ K1: index append
 
 __global__ void k_append_rows(int n, const int32_t* __restrict__ q_ptr, int64_t nnz_base, int64_t n_local,
@@ -124,10 +173,15 @@ __global__ void k_append_rows(int n, const int32_t* __restrict__ q_ptr, int64_t 
 // One thread per stored component in [nnz_lo, nnz_hi): find its row, emit (sort key, posting).
 __global__ void k_emit_postings(int64_t nnz_lo, int64_t nnz_hi, int64_t row_lo, int64_t row_hi,
                                 const int64_t* __restrict__ fwd_ptr, const int32_t* __restrict__ fwd_idx,
-                                const double* __restrict__ fwd_val, int CR, int64_t tile0, int dimbits,
+                                const double* __restrict__ fwd_val, const uint8_t* __restrict__ fwd_skip, int ntiles_aff,
+                                int CR, int64_t tile0, int dimbits,
                                 unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
   int64_t p = nnz_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nnz_hi) return;
+  if (fwd_skip && fwd_skip[p]) {             // not indexed: sorts behind the last affected tile and is dropped
+    keys[p - nnz_lo] = (unsigned long long)ntiles_aff << dimbits; vals[p - nnz_lo] = 0ULL;
+    return;
+  }
   int64_t lo = row_lo, hi = row_hi;          // largest row with fwd_ptr[row] <= p
   while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (fwd_ptr[mid] <= p) lo = mid; else hi = mid; }
   int64_t row = lo;
@@ -176,6 +230,8 @@ struct ScoreArgs {
   const int32_t* tile_cnt;   // debug builds: sparse postings per tile (bounds checks)
   int32_t seg_cap;           // dense-head kernel: capacity of the per-item segment queue
   long long post_cap;        // debug builds: capacity of post[]
+  const float* row_ub;       // index reduction: per stored vector, upper bound of the L2 norm of its un-indexed part (else NULL)
+  const float* q_nrm;        // index reduction: per query, upper bound of its L2 norm
 };
 
 // Persistent kernel.  One CTA per SM, WARPS warps per CTA; each warp owns one row of CR fp32
@@ -308,6 +364,7 @@ struct BlockArgs {
   int32_t QB, n_qblocks;
   unsigned thr_int;         // emit iff acc >= thr_int  (t * 2^F with guard band, rounded down)
   float inv_scale;          // 2^-F
+  float scale;              // 2^F
 };
 
 __global__ void k_bt_emit(int nq, int nnz, const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim,
@@ -601,7 +658,7 @@ __device__ __forceinline__ int dense_lookup(const int2* __restrict__ hash, int d
 
 // thread per sorted posting: dense dims go to dense_w, the rest are compacted into the tile's postings
 __global__ void k_post_scatter(int64_t m, const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ vals,
-                               int dimbits, int64_t tile0, int CR, const int64_t* __restrict__ tile_start,
+                               int dimbits, int64_t tile0, int ntiles_aff, int CR, const int64_t* __restrict__ tile_start,
                                const int64_t* __restrict__ tile_base, const int32_t* __restrict__ d_cnt, const int32_t* __restrict__ d_dim,
                                const int32_t* __restrict__ d_len, const int2* __restrict__ d_hash, float* __restrict__ d_w,
                                unsigned long long* __restrict__ post, long long post_cap) {
@@ -609,6 +666,7 @@ __global__ void k_post_scatter(int64_t m, const unsigned long long* __restrict__
   if (i >= m) return;
   const unsigned long long key = keys[i], val = vals[i];
   const int trel = (int)(key >> dimbits); const int d = (int)(key & ((1ULL << dimbits) - 1));
+  if (trel >= ntiles_aff) return;           // components left out of the index (exact index reduction)
   const int64_t tile = tile0 + trel;
   const int slot = dense_lookup(d_hash + tile * HS, d);
   DBG_ASSERT(trel >= 0 && (unsigned)(val & 0xffffffffu) < (unsigned)CR && slot < KD);
@@ -781,7 +839,10 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
 #else
 #define PHASE_MARK(k) ((void)0)
 #endif
-  const unsigned thr_hi = b.thr_int << 16;   // high half >= thr  <=>  word >= thr << 16
+  // index reduction: the accumulator holds only the indexed part of the dot product, so every touched
+  // candidate takes the rare path and is tested there against its own threshold
+  const unsigned thr_lo = a.row_ub ? 1u : b.thr_int;
+  const unsigned thr_hi = thr_lo << 16;      // high half >= thr  <=>  word >= thr << 16
 
   for (;;) {
     __syncthreads();
@@ -974,7 +1035,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
         for (int k = 0; k < 4; ++k) {                            // plain compares (the SIMD-in-word intrinsics are emulated)
           const unsigned lo = vv[k] & 0xffffu;
           if (!DUPKEYS) n_cand += (unsigned)(lo != 0) + (unsigned)(vv[k] > 0xffffu);
-          hot |= (unsigned)(lo != 0 && lo >= b.thr_int) | (unsigned)(vv[k] > 0xffffu && vv[k] >= thr_hi);
+          hot |= (unsigned)(lo != 0 && lo >= thr_lo) | (unsigned)(vv[k] > 0xffffu && vv[k] >= thr_hi);
         }
         if (DUPKEYS || hot) {                                   // rare: something to emit (or key checks)
 #ifdef APSS_PHASE_TIMERS
@@ -984,13 +1045,20 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
           const int q = q0 + row;
           long long qkey = 0;
           if (DUPKEYS) qkey = __ldg(a.q_key + q);
+          const float qn = a.row_ub ? __fmul_ru(__ldg(a.q_nrm + q), b.scale) : 0.f;
           unsigned pm = 0;                                      // halves to emit
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const unsigned val = (vv[k >> 1] >> ((k & 1) << 4)) & 0xffffu;
             if (!val) continue;
             if (DUPKEYS) { if (__ldg(a.c_key + c0 + (long long)(wcol + (k >> 1)) * 2 + (k & 1)) == qkey) continue; ++n_cand; }
-            if (val >= b.thr_int) pm |= 1u << k;
+            unsigned thr_k = b.thr_int;
+            if (a.row_ub) {
+              // dot(q, c) <= indexed part + |q| * |un-indexed part of c| (Cauchy-Schwarz), all rounded up
+              const unsigned ub = fx_ceil(fminf(__fmul_ru(__ldg(a.row_ub + c0 + (long long)(wcol + (k >> 1)) * 2 + (k & 1)), qn), 8388607.f));
+              thr_k = ub >= thr_k ? 0u : thr_k - ub;
+            }
+            if (val >= thr_k) pm |= 1u << k;
           }
           if (pm) {                                             // one slot claim per thread (<= 8 pairs)
             unsigned long long slot = atomicAdd(&a.counters[C_PF], (unsigned long long)__popc(pm));

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get("APSS_LIB_NAME") or ("libapss_b200_dbg.so" if os.environ.get("APSS_DEBUG_LIB") else
                         ("libapss_b200_prof.so" if os.environ.get("APSS_PROF_LIB") else "libapss_b200.so")))
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 SEM_R1, SEM_R0 = 0, 1
 BATCH_QUERY_ONLY, BATCH_DEVICE_PTRS, BATCH_SKIP_ADMIT, BATCH_INDEX_ONLY = 1, 2, 4, 8
 ST_REJECTED, ST_EMPTY, ST_ACTIVE = 0, 1, 2
@@ -39,7 +39,8 @@ class Config(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("dim", C.c_int32), ("similarity_threshold", C.c_double),
                 ("index_threshold", C.c_double), ("max_weight", C.c_void_p), ("device", C.c_int32),
                 ("semantics", C.c_int32), ("tile_vectors", C.c_int32), ("kernel_variant", C.c_int32),
-                ("reserve_vectors", C.c_int64), ("reserve_nnz", C.c_int64), ("reserve_pairs", C.c_int64)]
+                ("reserve_vectors", C.c_int64), ("reserve_nnz", C.c_int64), ("reserve_pairs", C.c_int64),
+                ("pruning", C.c_int32), ("reserved0", C.c_int32), ("prune_alpha", C.c_double), ("max_query_norm", C.c_double)]
 
 
 class BatchResultC(C.Structure):
@@ -55,7 +56,8 @@ class StatsC(C.Structure):
                 ("tot_candidates_unique", C.c_int64), ("tot_pairs", C.c_int64), ("tot_prefilter", C.c_int64),
                 ("score_launches", C.c_int64), ("kernel_launches", C.c_int64), ("tot_score_ms", C.c_double),
                 ("phase_cycles", C.c_int64 * 8),
-                ("frozen", C.c_int32), ("tile_vectors", C.c_int32), ("warps_per_cta", C.c_int32), ("sm_count", C.c_int32)]
+                ("frozen", C.c_int32), ("tile_vectors", C.c_int32), ("warps_per_cta", C.c_int32), ("sm_count", C.c_int32),
+                ("n_unindexed", C.c_int64)]
 
 
 _lib = None
@@ -136,14 +138,16 @@ class Index:
     vector store and the inverted index (IWA:22-25), configured by the same three keys."""
 
     def __init__(self, dim, similarity_threshold, index_threshold=0.0, max_weight=None, device=0, semantics=SEM_R1,
-                 tile_vectors=0, kernel_variant=0, reserve_vectors=0, reserve_nnz=0, reserve_pairs=0):
+                 tile_vectors=0, kernel_variant=0, reserve_vectors=0, reserve_nnz=0, reserve_pairs=0,
+                 pruning=False, prune_alpha=0.0, max_query_norm=0.0):
         self._L = load_library()
         self._mw = None if max_weight is None else np.ascontiguousarray(max_weight, dtype=np.float64)
         if self._mw is not None and len(self._mw) != dim:
             raise ValueError("max_weight must have `dim` entries")
         cfg = Config(C.sizeof(Config), int(dim), float(similarity_threshold), float(index_threshold),
                      None if self._mw is None else self._mw.ctypes.data, int(device), int(semantics), int(tile_vectors),
-                     int(kernel_variant), int(reserve_vectors), int(reserve_nnz), int(reserve_pairs))
+                     int(kernel_variant), int(reserve_vectors), int(reserve_nnz), int(reserve_pairs),
+                     1 if pruning else 0, 0, float(prune_alpha), float(max_query_norm))
         h = C.c_void_p()
         rc = self._L.apss_create(C.byref(cfg), C.byref(h))
         if rc != 0:

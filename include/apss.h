@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define APSS_ABI_VERSION 1
+#define APSS_ABI_VERSION 2
 
 typedef enum apss_status {
   APSS_OK = 0,
@@ -78,6 +78,16 @@ typedef struct apss_config {
   int64_t reserve_vectors;     /* capacity hints; 0 = grow on demand                                 */
   int64_t reserve_nnz;
   int64_t reserve_pairs;
+  /* Exact index reduction (the pruning the reference planned around its max-weight stub,  */
+  /* EPA:51-57,81-93).  Off by default: with it on, the pair set and similarities are unchanged but        */
+  /* postings_visited / candidates_unique count only what the reduced index makes the kernel touch.         */
+  int32_t pruning;             /* 0 = off (parity counters), 1 = on (default scoring kernel only)          */
+  int32_t reserved0;
+  double prune_alpha;          /* share of (t / max_query_norm)^2 a vector may keep out of the index;      */
+                               /* 0 = default 0.8; must be < 1                                             */
+  double max_query_norm;       /* promise: every vector of every batch has L2 norm <= this after the value */
+                               /* prune; 0 = default 1.0 (LoadGenerator.scala:35-37 normalises).  A batch  */
+                               /* that breaks the promise is refused (APSS_E_INPUT), never mis-scored.      */
 } apss_config;
 
 typedef struct apss_batch_result {
@@ -118,6 +128,7 @@ typedef struct apss_stats {
   int32_t tile_vectors;
   int32_t warps_per_cta;
   int32_t sm_count;
+  int64_t n_unindexed;       /* stored components kept out of the index by exact index reduction     */
 } apss_stats;
 
 int32_t apss_abi_version(void);

@@ -25,6 +25,10 @@
  *                  (the guard bug fixed); see SURVEY.md section 8(a).
  *   ALGO_FAST      weighted postings + dense fp64 accumulator (R1 only).  Used where the
  *                  faithful algorithm would take hours; cross-checked against it in tests.
+ *                  oracle_set_pruning() adds the EXACT INDEX REDUCTION the reference planned around
+ *                  its max-weight stub (EPA:51-57,81-93) -- not reference behaviour,
+ *                  a restatement of the GPU library's rule so that its counters can be predicted:
+ *                  the pair set must equal the un-pruned one (tests check exactly that).
  *
  * Similarities are accumulated in ascending-dimension order with separate multiply and add
  * (compile with -ffp-contract=off), which is the order the CUDA fp64 verify kernel uses, so
@@ -99,6 +103,7 @@ typedef struct {            /* a stored (pruned) vector: what WWA:193-194 puts i
   int32_t nnz;
   int32_t *idx;             /* ascending (SparseVector.scala:96-108 sorts)                    */
   double *val;
+  uint8_t *skip;            /* index reduction: 1 = component kept out of the index (else NULL) */
 } ovec_t;
 
 typedef struct {            /* one emulated IndexingWorkerActor (IWA:21-25)                   */
@@ -129,6 +134,8 @@ typedef struct {
   int64_t postings_visited, candidates_unique, dot_calls_ref;
   int64_t tot_postings_visited, tot_candidates_unique, tot_dot_calls_ref, tot_pairs;
   int32_t threads;
+  /* exact index reduction (ALGO_FAST): off unless oracle_set_pruning() was called */
+  int32_t prune; double prune_lim, max_qnorm; int32_t *df; int64_t n_unindexed;
   char err[256];
 } oracle_t;
 
@@ -237,6 +244,24 @@ oracle_t *oracle_create(int32_t dim, double sim_thr, double idx_thr, int32_t sem
 }
 
 void oracle_set_threads(oracle_t *o, int32_t t) { o->threads = t < 1 ? 1 : t; }
+
+/* Exact index reduction, same rule as the GPU library (include/apss.h `pruning`): a vector keeps out of
+ * the index the longest prefix, in (document frequency descending, dim ascending) order, whose squared
+ * weights sum to <= alpha * (t / max_query_norm)^2 * (1 - 2^-20).  Cauchy-Schwarz: the un-indexed part can
+ * contribute < t to any dot product with a query of norm <= max_query_norm, so every pair with dot >= t
+ * still shares an indexed component.  Returns 0, or -1 for a bad argument / wrong algorithm. */
+int32_t oracle_set_pruning(oracle_t *o, double alpha, double max_qnorm) {
+  if (o->algo != ORC_ALGO_FAST || o->n_vecs) return -1;
+  if (alpha == 0.0) alpha = 0.8;
+  if (max_qnorm == 0.0) max_qnorm = 1.0;
+  if (!(alpha > 0.0 && alpha < 1.0) || !(max_qnorm > 0.0)) return -1;
+  double t = o->sim_thr;
+  o->prune = 1; o->max_qnorm = max_qnorm;
+  o->prune_lim = t > 0.0 ? alpha * t * t / (max_qnorm * max_qnorm) * (1.0 - ldexp(1.0, -20)) : 0.0;
+  o->df = (int32_t*)calloc((size_t)o->dim, sizeof(int32_t));
+  return 0;
+}
+int64_t oracle_n_unindexed(const oracle_t *o) { return o->n_unindexed; }
 int32_t oracle_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
@@ -247,8 +272,8 @@ int32_t oracle_max_threads(void) {
 
 void oracle_destroy(oracle_t *o) {
   if (!o) return;
-  for (int64_t i = 0; i < o->n_vecs; i++) { free(o->vecs[i].idx); free(o->vecs[i].val); }
-  free(o->vecs);
+  for (int64_t i = 0; i < o->n_vecs; i++) { free(o->vecs[i].idx); free(o->vecs[i].val); free(o->vecs[i].skip); }
+  free(o->vecs); free(o->df);
   for (int32_t w = 0; w < o->n_workers; w++) {
     oworker_t *wk = &o->workers[w];
     free(wk->store_vec.v); map64_free(&wk->dim2list);
@@ -352,10 +377,32 @@ static void worker_query_one(const oracle_t *o, const oworker_t *wk, const owrap
 
 /* ------------------------------------------------------------------ fast (weighted) index */
 
+typedef struct { int32_t df, dim, pos; } rank_t;
+static int rank_cmp(const void *a, const void *b) {
+  const rank_t *x = (const rank_t*)a, *y = (const rank_t*)b;
+  if (x->df != y->df) return x->df > y->df ? -1 : 1;
+  return x->dim < y->dim ? -1 : x->dim > y->dim;
+}
+static void prune_select_vector(oracle_t *o, ovec_t *v) {
+  rank_t *r = (rank_t*)malloc(sizeof(rank_t) * (size_t)(v->nnz ? v->nnz : 1));
+  for (int32_t i = 0; i < v->nnz; i++) { r[i].df = o->df[v->idx[i]]; r[i].dim = v->idx[i]; r[i].pos = i; }
+  qsort(r, (size_t)v->nnz, sizeof(rank_t), rank_cmp);
+  v->skip = (uint8_t*)calloc((size_t)(v->nnz ? v->nnz : 1), 1);
+  double s = 0.0;
+  for (int32_t k = 0; k < v->nnz; k++) {
+    double x = v->val[r[k].pos];
+    double s2 = s + x * x;
+    if (!(s2 <= o->prune_lim)) break;
+    s = s2; v->skip[r[k].pos] = 1; o->n_unindexed++;
+  }
+  free(r);
+}
+
 static void fast_index_vector(oracle_t *o, int32_t ord) {
   const ovec_t *v = &o->vecs[ord];
   for (int32_t i = 0; i < v->nnz; i++) {
     int32_t d = v->idx[i];
+    if (v->skip && v->skip[i]) continue;
     ivec_t *l = &o->fp_ids[d];
     if (l->n == o->fp_wcap[d]) {
       int32_t nc = o->fp_wcap[d] ? o->fp_wcap[d] * 2 : 4;
@@ -397,9 +444,22 @@ int32_t oracle_insert_batch(oracle_t *o, int32_t n, const int64_t *indptr, const
     int32_t nn = (int32_t)(indptr[v + 1] - indptr[v]);
     ovec_t *ov = &o->vecs[base + v];
     ov->key = keys ? keys[v] : base + v;
+    ov->skip = NULL;
     if (!(flags & ORC_FLAG_SKIP_ADMIT) && !admit_vector(o, idx, val, nn)) { o->status[v] = ORC_ST_REJECTED; ov->nnz = 0; ov->idx = NULL; ov->val = NULL; continue; }
     prune_vector(o, idx, val, nn, ov);
     o->status[v] = ov->nnz ? ORC_ST_ACTIVE : ORC_ST_EMPTY;
+  }
+  if (o->prune) {   /* the bound needs |q| <= max_query_norm for every query: refuse the batch otherwise */
+    int bad = 0;
+    for (int32_t v = 0; v < n && !bad; v++) {
+      const ovec_t *ov = &o->vecs[base + v]; double sq = 0.0;
+      for (int32_t i = 0; i < ov->nnz; i++) sq += ov->val[i] * ov->val[i];
+      if (sq > o->max_qnorm * o->max_qnorm * (1.0 + 1e-9)) bad = 1;
+    }
+    if (bad) {
+      for (int32_t v = 0; v < n; v++) { free(o->vecs[base + v].idx); free(o->vecs[base + v].val); }
+      snprintf(o->err, sizeof o->err, "pruning: vector norm exceeds max_query_norm"); return -4;
+    }
   }
   o->n_vecs += n;
 
@@ -497,6 +557,10 @@ int32_t oracle_insert_batch(oracle_t *o, int32_t n, const int64_t *indptr, const
   } else {
     /* ---- ALGO_FAST: R1 by accumulation over weighted postings (same arithmetic order as
      * the ascending-index dot: acc starts at 0.0, products added in ascending dim). */
+    if (!query_only && o->prune) {     /* document frequencies include the whole batch, then rank and mark */
+      for (int32_t v = 0; v < n; v++) { const ovec_t *ov = &o->vecs[base + v]; if (o->status[v] == ORC_ST_ACTIVE) for (int32_t i = 0; i < ov->nnz; i++) o->df[ov->idx[i]]++; }
+      for (int32_t v = 0; v < n; v++) if (o->status[v] == ORC_ST_ACTIVE) prune_select_vector(o, &o->vecs[base + v]);
+    }
     if (!query_only) for (int32_t v = 0; v < n; v++) if (o->status[v] == ORC_ST_ACTIVE) fast_index_vector(o, (int32_t)(base + v));
     int64_t nvis = query_only ? base : o->n_vecs;      /* candidates are ordinals < nvis */
     int64_t postings = 0, cands = 0;
@@ -532,8 +596,10 @@ int32_t oracle_insert_batch(oracle_t *o, int32_t n, const int64_t *indptr, const
           const ovec_t *cv = &o->vecs[c];
           if (cv->key == qv->key) continue;                        /* IWA:91 */
           cands++;
-          if (acc[c] >= o->sim_thr) {                              /* IWA:93 */
-            opair_t pr; pr.qkey = qv->key; pr.ckey = cv->key; pr.q = (int32_t)(base + v); pr.c = c; pr.sim = acc[c];
+          double sim = acc[c];
+          if (o->prune) { int32_t ns; sim = dot_merge(cv->idx, cv->val, cv->nnz, qv->idx, qv->val, qv->nnz, &ns); }   /* acc holds the indexed part only */
+          if (sim >= o->sim_thr) {                              /* IWA:93 */
+            opair_t pr; pr.qkey = qv->key; pr.ckey = cv->key; pr.q = (int32_t)(base + v); pr.c = c; pr.sim = sim;
             push_pair(&lp, &ln, &lc, pr);
           }
         }
@@ -548,7 +614,7 @@ int32_t oracle_insert_batch(oracle_t *o, int32_t n, const int64_t *indptr, const
   }
 
   if (query_only) {   /* the batch was never stored (IWA:125): drop it from the table again */
-    for (int64_t i = base; i < o->n_vecs; i++) { free(o->vecs[i].idx); free(o->vecs[i].val); }
+    for (int64_t i = base; i < o->n_vecs; i++) { free(o->vecs[i].idx); free(o->vecs[i].val); free(o->vecs[i].skip); }
     o->n_vecs = base;
   }
   o->tot_postings_visited += o->postings_visited;

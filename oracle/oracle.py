@@ -47,6 +47,10 @@ def lib():
         L.oracle_freeze.argtypes = [C.c_void_p]
         L.oracle_set_threads.argtypes = [C.c_void_p, C.c_int32]
         L.oracle_max_threads.restype = C.c_int32
+        L.oracle_set_pruning.restype = C.c_int32
+        L.oracle_set_pruning.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.oracle_n_unindexed.restype = C.c_int64
+        L.oracle_n_unindexed.argtypes = [C.c_void_p]
         L.oracle_last_error.restype = C.c_char_p
         L.oracle_last_error.argtypes = [C.c_void_p]
         L.oracle_insert_batch.restype = C.c_int32
@@ -97,7 +101,7 @@ class BatchResult:
 class Oracle:
     def __init__(self, dim, similarity_threshold, index_threshold=0.0, semantics=R1, algo=ALGO_FAITHFUL,
                  max_shard_num=1, max_entry_num=1, max_index_entry_actor_num=1, set_order=SET_ORDER_SCALA,
-                 max_weight=None, threads=1):
+                 max_weight=None, threads=1, pruning=False, prune_alpha=0.0, max_query_norm=0.0):
         self._L = lib()
         mw = None if max_weight is None else np.ascontiguousarray(max_weight, dtype=np.float64)
         if algo == ALGO_FAST and semantics != R1:
@@ -107,6 +111,8 @@ class Oracle:
                                         int(max_index_entry_actor_num), int(set_order), _p(mw))
         self.dim = dim
         self._L.oracle_set_threads(self._h, int(threads))
+        if pruning and self._L.oracle_set_pruning(self._h, float(prune_alpha), float(max_query_norm)) != 0:
+            raise ValueError("pruning needs ALGO_FAST, 0 < alpha < 1 and max_query_norm > 0")
 
     def close(self):
         if self._h:
@@ -121,6 +127,11 @@ class Oracle:
 
     def freeze(self):
         self._L.oracle_freeze(self._h)
+
+    @property
+    def n_unindexed(self):
+        """components kept out of the index by exact index reduction so far"""
+        return int(self._L.oracle_n_unindexed(self._h))
 
     @property
     def n_vectors(self):

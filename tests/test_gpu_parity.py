@@ -412,3 +412,95 @@ def test_keys_only_on_some_batches():
     assert gpu_pairs(g, r1) == {} and r1.candidates_unique == 0
     r2 = g.insert_batch(*csr_from_dicts([dict(A)]))                              # default key 2: pairs with both
     assert set(gpu_pairs(g, r2)) == {(2, 0), (2, 1)}
+
+
+# ---------------------------------------------------------------- exact index reduction
+
+@pytest.mark.parametrize("tile,batch,t,alpha", [(0, 2500, 0.6, 0.0), (256, 333, 0.6, 0.5), (1024, 4096, 0.4, 0.95),
+                                                (128, 7, 0.7, 0.0), (512, 1000, 0.9, 0.3)])
+def test_pruned_index_same_pairs_fewer_postings(tile, batch, t, alpha):
+    """With `pruning` on the pair set and the fp64 similarities are those of the un-pruned run (bit-exact),
+    while the counters are those of the oracle's restatement of the same reduction rule."""
+    N, D = 6000, 1 << 12
+    data = _synth(N, D, 30, seed=11)
+    n = native()
+    o_full = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
+    o_pr = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8, pruning=True, prune_alpha=alpha)
+    g = n.Index(D, t, tile_vectors=tile, pruning=True, prune_alpha=alpha)
+    tot_full = tot_pr = 0
+    for lo in range(0, N, batch):
+        csr = csr_slice(data, lo, min(N, lo + batch))
+        rf = o_full.insert_batch(*csr); rp = o_pr.insert_batch(*csr); rg = g.insert_batch(*csr)
+        assert_pairs_equal(gpu_pairs(g, rg), rf.pair_set())
+        assert_pairs_equal(rp.pair_set(), rf.pair_set())
+        assert (rg.postings_visited, rg.candidates_unique) == (rp.postings_visited, rp.candidates_unique)
+        tot_full += rf.postings_visited; tot_pr += rg.postings_visited
+    st = g.stats()
+    assert st["n_unindexed"] == o_pr.n_unindexed > 0
+    assert st["n_postings"] == len(data[1]) - st["n_unindexed"]
+    assert st["tot_pairs"] == o_full.totals()["pairs"] > 0
+    assert tot_pr * 2 < tot_full
+
+
+def test_pruned_index_query_only_keys_and_r0():
+    """frozen / query-only batches, duplicate external ids and the R0 post-filter on top of the reduced index"""
+    N, D, t = 3000, 1 << 10, 0.5
+    data = _synth(N, D, 12, seed=9)
+    n = native()
+    keys = np.arange(N, dtype=np.int64); keys[1::7] = keys[0:-1:7]          # some vectors share an id with their neighbour
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
+    g = n.Index(D, t, tile_vectors=256, pruning=True)
+    for lo in range(0, 2000, 500):
+        csr = csr_slice(data, lo, lo + 500)
+        ro = o.insert_batch(*csr, keys=keys[lo:lo + 500]); rg = g.insert_batch(*csr, ext_keys=keys[lo:lo + 500])
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+    o.freeze(); g.freeze()
+    csr = csr_slice(data, 2000, 3000)
+    ro = o.insert_batch(*csr, keys=keys[2000:3000]); rg = g.insert_batch(*csr, ext_keys=keys[2000:3000])
+    assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+    assert g.stats()["n_vectors"] == 2000 and rg.n_pairs > 0
+    # R0 on the reduced index against the faithful as-built oracle
+    o0 = orc.Oracle(D, t, semantics=orc.R0, algo=orc.ALGO_FAITHFUL, threads=8)
+    g0 = n.Index(D, t, semantics=n.SEM_R0, tile_vectors=256, pruning=True)
+    for lo in range(0, 1500, 500):
+        csr = csr_slice(data, lo, lo + 500)
+        ro = o0.insert_batch(*csr); rg = g0.insert_batch(*csr, first_dim=orc.first_dims(*csr))
+        assert_pairs_equal(gpu_pairs(g0, rg), ro.pair_set())
+
+
+def test_pruned_index_refuses_vectors_over_the_norm_promise():
+    n = native()
+    g = n.Index(64, 0.5, pruning=True)                       # max_query_norm defaults to 1
+    g.insert_batch(*csr_from_dicts([A]))
+    with pytest.raises(n.ApssError) as e:
+        g.insert_batch(*csr_from_dicts([{0: .6, 1: .8}, {0: 3.0, 1: 4.0}]))
+    assert e.value.code == -4 and "max_query_norm" in str(e.value)
+    assert g.stats()["n_vectors"] == 1                       # all-or-nothing
+    rg = g.insert_batch(*csr_from_dicts([dict(A)]))
+    assert gpu_pairs(g, rg) == {(1, 0): .6 * .6 + .8 * .8}
+    g5 = n.Index(64, 6.0, pruning=True, max_query_norm=5.0)   # un-normalised data with a declared bound
+    g5.insert_batch(*csr_from_dicts([{0: 3.0, 1: 4.0}]))
+    rg = g5.insert_batch(*csr_from_dicts([{0: 3.0, 1: 4.0}, {0: 1.0}]))
+    assert gpu_pairs(g5, rg) == {(1, 0): 25.0}
+    for kv in (1 << 16, 2 << 16):                            # only the default scoring kernel applies the bound
+        with pytest.raises(n.ApssError):
+            n.Index(64, 0.5, pruning=True, kernel_variant=kv)
+    with pytest.raises(n.ApssError):
+        n.Index(64, 0.5, pruning=True, prune_alpha=1.0)
+
+
+def test_pruned_c2_shape():
+    """C2's shape (100 K x 2^16, t = 0.8) on a 30 K prefix: full pair-set parity, large work reduction"""
+    import apss_b200
+    N, D, t = 30_000, 1 << 16, 0.8
+    data = apss_b200.synth.generate(N, D, 50, seed=20260102).numpy()
+    n = native()
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=16)
+    g = n.Index(D, t, pruning=True)
+    tf = tp = 0
+    for lo in range(0, N, 4096):
+        csr = csr_slice(data, lo, min(N, lo + 4096))
+        ro = o.insert_batch(*csr); rg = g.insert_batch(*csr)
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+        tf += ro.postings_visited; tp += rg.postings_visited
+    assert o.totals()["pairs"] > 0 and tp * 20 < tf

@@ -103,3 +103,25 @@ def test_more_workers_can_only_lose_pairs_that_r1_has():
     r0_multi, _ = run(data, B, t, algo=orc.ALGO_FAITHFUL, semantics=orc.R0, max_shard_num=4, max_index_entry_actor_num=3)
     assert r1 == r1_single                      # R1 does not depend on the sharding
     assert set(r0_multi) <= set(r1)
+
+
+@pytest.mark.parametrize("t,alpha", [(0.6, 0.0), (0.4, 0.95), (0.9, 0.3)])
+def test_index_reduction_keeps_the_pair_set(t, alpha):
+    """oracle_set_pruning (the GPU library's exact index reduction) must not change pairs or sims"""
+    import apss_b200
+    N, D = 5000, 1 << 12
+    ip, ix, v = apss_b200.synth.generate(N, D, 30, seed=11).numpy()
+    full = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
+    red = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8, pruning=True, prune_alpha=alpha)
+    pf = pr = 0
+    for lo in range(0, N, 1024):
+        hi = min(N, lo + 1024)
+        csr = (ip[lo:hi + 1] - ip[lo], ix[ip[lo]:ip[hi]], v[ip[lo]:ip[hi]])
+        a = full.insert_batch(*csr); b = red.insert_batch(*csr)
+        assert a.pair_set() == b.pair_set()
+        pf += a.postings_visited; pr += b.postings_visited
+    assert full.totals()["pairs"] > 0 and 0 < pr < pf and red.n_unindexed > 0
+    with pytest.raises(ValueError):
+        red.insert_batch(np.array([0, 1]), np.array([0], np.int32), np.array([2.0]))      # norm promise broken
+    with pytest.raises(ValueError):
+        orc.Oracle(D, t, algo=orc.ALGO_FAITHFUL, pruning=True)
