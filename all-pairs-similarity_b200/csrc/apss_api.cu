@@ -168,6 +168,9 @@ struct apss_handle {
   // exact index reduction (cfg.pruning): document frequencies, per stored component "not indexed" flag, per
   // stored vector norm bound of its un-indexed part; per batch the same + rank-sort scratch
   bool prune = false; double prune_lim = 0.0, max_qnorm = 1.0;
+  int prune_mode = 0;        // 1: tile kernels on the reduced index, 2: candidate-major kernel (no tiles are built)
+  int cand_warps = 24;
+  DevBuf<int32_t> qdir; VmBuf<int32_t> heavy;
   DevBuf<int32_t> df; VmBuf<uint8_t> fwd_skip; VmBuf<float> row_ub;
   DevBuf<uint8_t> q_skip; DevBuf<float> q_cu, q_nrm;
   DevBuf<unsigned long long> pr_keys_in, pr_keys_out, pr_vals_in, pr_vals_out;
@@ -267,6 +270,44 @@ static cudaError_t launch_dense(apss_handle* h, const ScoreArgs& a, const BlockA
   }
 }
 
+// Candidate-major scoring on the reduced index: invert the batch (dim -> (query, weight) lists), then stream the
+// stored vectors (k_score_cand) and finish the deferred ones (k_score_cand_heavy).
+static int32_t build_query_index(apss_handle* h, int32_t n, int32_t batch_nnz) {
+  cudaStream_t s = h->stream;
+  const int D = h->cfg.dim;
+  int dimbits = 1; while ((1LL << dimbits) < (int64_t)D) ++dimbits;
+  CK(h->bt_keys_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->bt_keys_out.reserve(std::max(batch_nnz, 1), 0, s));
+  CK(h->bt_vals_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->bt_vals_out.reserve(std::max(batch_nnz, 1), 0, s));
+  CK(h->qdir.reserve((size_t)D + 1, 0, s));
+  if (batch_nnz) {
+    k_qi_emit<<<cdiv(n, 128), 128, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->q_w.p, h->bt_keys_in.p, h->bt_vals_in.p);
+    CK(cudaGetLastError());
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits, s));
+    CK(h->cub_tmp.reserve(tb, 0, s));
+    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits, s));
+    h->kernel_launches += 3;
+  }
+  k_qdir<<<cdiv((int64_t)D + 1, 256), 256, 0, s>>>(h->bt_keys_out.p, batch_nnz, D, h->qdir.p);
+  CK(cudaGetLastError()); h->kernel_launches++;
+  return APSS_OK;
+}
+
+static cudaError_t launch_cand(apss_handle* h, const CandArgs& a) {
+  const size_t smem = (size_t)h->cand_warps * 2 * CAND_TBL * sizeof(unsigned);
+  auto kern = h->cand_warps == 16 ? k_score_cand<16> : k_score_cand<24>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, h->smem_optin - 1024));
+  if (e != cudaSuccess) return e;
+  kern<<<h->sm_count, h->cand_warps * 32, smem, h->stream>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int qc = 32768;
+  e = cudaFuncSetAttribute(k_score_cand_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max((size_t)qc * 4, h->smem_optin - 1024));
+  if (e != cudaSuccess) return e;
+  k_score_cand_heavy<<<h->sm_count, 512, (size_t)qc * 4, h->stream>>>(a, qc);
+  return cudaGetLastError();
+}
+
 extern "C" int32_t apss_abi_version(void) { return APSS_ABI_VERSION; }
 
 extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
@@ -277,7 +318,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) { cudaGetLastError(); return APSS_E_NO_DEVICE; }
   apss_handle* h = new apss_handle();
   h->cfg = *cfg; h->cfg.max_weight = nullptr; h->device = cfg->device;
-  h->fwd_skip.device = h->row_ub.device = cfg->device;
+  h->fwd_skip.device = h->row_ub.device = h->heavy.device = cfg->device;
   h->fwd_ptr.device = h->fwd_idx.device = h->fwd_val.device = h->gid.device = h->key.device = h->post.device = h->dir.device =
       h->tile_base.device = h->dn_cnt.device = h->dn_dim.device = h->dn_len.device = h->tile_cnt.device = h->dn_hash.device =
       h->dn_w.device = cfg->device;
@@ -347,7 +388,9 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
     if (cudaMemcpyAsync(h->maxw.p, cfg->max_weight, sizeof(double) * cfg->dim, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return bail(APSS_E_CUDA);
   }
   if (cfg->pruning) {
-    if (cfg->pruning != 1 || algo != 3) return bail(APSS_E_INVALID);      // only the default scoring kernel applies the bound
+    if ((cfg->pruning != 1 && cfg->pruning != 2) || algo != 3) return bail(APSS_E_INVALID);   // only the default scoring kernel applies the bound
+    h->prune_mode = cfg->pruning;
+    { const char* cw = getenv("APSS_CAND_WARPS"); if (cw && (atoi(cw) == 16 || atoi(cw) == 24)) h->cand_warps = atoi(cw); }
     const double alpha = cfg->prune_alpha == 0.0 ? 0.8 : cfg->prune_alpha;
     const double qn = cfg->max_query_norm == 0.0 ? 1.0 : cfg->max_query_norm;
     if (!(alpha > 0.0 && alpha < 1.0) || !(qn > 0.0) || !std::isfinite(qn)) return bail(APSS_E_INVALID);
@@ -395,6 +438,7 @@ extern "C" void apss_destroy(apss_handle* h) {
   h->dn_cnt.release(); h->dn_dim.release(); h->dn_len.release(); h->tile_cnt.release(); h->dn_hash.release(); h->dn_w.release(); h->s_vals_out.release();
   h->s_keys_in.release(); h->s_keys_out.release(); h->s_vals_in.release(); h->s_tile_start.release(); h->cub_tmp.release();
   h->pf_q.release(); h->pf_c.release(); h->pf_est.release(); h->out_q.release(); h->out_c.release(); h->out_sim.release();
+  h->qdir.release(); h->heavy.release();
   h->df.release(); h->fwd_skip.release(); h->row_ub.release(); h->q_skip.release(); h->q_cu.release(); h->q_nrm.release();
   h->pr_keys_in.release(); h->pr_keys_out.release(); h->pr_vals_in.release(); h->pr_vals_out.release();
   if (h->d_counters) cudaFree(h->d_counters);
@@ -453,6 +497,11 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
     CK(h->fwd_skip.reserve(std::max<int64_t>(nnz_new, 1), nnz_old, s)); CK(h->row_ub.reserve(n_new, n_old, s));
     if (batch_nnz) CK(cudaMemcpyAsync(h->fwd_skip.p + nnz_old, h->q_skip.p, (size_t)batch_nnz, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(h->row_ub.p + n_old, h->q_cu.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+  }
+  if (h->prune_mode == 2) {     // candidate-major scoring streams the forward store: there is no tile index to maintain
+    CK(h->heavy.reserve(n_new, 0, s));
+    h->n_local = n_new; h->nnz = nnz_new; h->ntiles = 0;
+    return APSS_OK;
   }
   // tiles to (re)build: [tile0, tile1)
   const int64_t tile0 = n_old / CR, tile1 = (n_new + CR - 1) / CR;
@@ -677,7 +726,10 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   // ---- query-block transposition for the block kernels: (block, dim)-sorted (row, scaled weight) lists
   BlockArgs blk{};
   int F = 0; unsigned thr_int = 0;
-  if (h->algo != 1 && batch_nnz) {
+  if (h->prune_mode == 2) {
+    const int32_t rc = build_query_index(h, n, batch_nnz);
+    if (rc != APSS_OK) return rc;
+  } else if (h->algo != 1 && batch_nnz) {
     const int32_t rc = transpose_query_blocks(h, n, batch_nnz, &blk, &F, &thr_int);
     if (rc != APSS_OK) return rc;
   }
@@ -694,8 +746,24 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     a.row_ub = h->prune ? h->row_ub.p : nullptr; a.q_nrm = h->prune ? h->q_nrm.p : nullptr;
     CK(cudaMemsetAsync(h->d_counters, 0, 7 * sizeof(unsigned long long), s));   // keep the prefilter tallies
     CK(cudaMemsetAsync(h->d_counters + C_PHASE, 0, 8 * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(h->d_counters + C_HEAVY, 0, sizeof(unsigned long long), s));
     CK(cudaEventRecord(h->ev_s0, s));
-    if (h->algo == 1) {
+    if (h->prune_mode == 2) {
+      const int64_t n_rows = h->n_local;      // includes this batch when it was indexed (IWA:125-132)
+      if (n_rows && batch_nnz) {
+        CandArgs ca{};
+        ca.fwd_ptr = h->fwd_ptr.p; ca.fwd_idx = h->fwd_idx.p; ca.fwd_val = h->fwd_val.p; ca.fwd_skip = h->fwd_skip.p;
+        ca.row_ub = h->row_ub.p; ca.c_key = h->key.p; ca.qdir = h->qdir.p; ca.qi = reinterpret_cast<const uint2*>(h->bt_vals_out.p);
+        ca.q_nrm = h->q_nrm.p; ca.q_key = h->custom_keys ? d_qkey : nullptr;
+        ca.n_rows = n_rows; ca.q_local_base = q_local_base; ca.nq = n;
+        ca.thr = (float)t; if ((double)ca.thr > t) ca.thr = std::nextafterf(ca.thr, -INFINITY);
+        ca.band1 = (float)(1.0 + (double)(h->max_nnz_seen + 8) * std::ldexp(1.0, -22));
+        ca.out_q = h->pf_q.p; ca.out_c = h->pf_c.p; ca.out_est = h->pf_est.p; ca.out_cap = h->pf_q.cap;
+        ca.counters = h->d_counters; ca.heavy = h->heavy.p; ca.heavy_cap = (int64_t)h->heavy.cap;
+        CK(launch_cand(h, ca));
+        h->score_launches++; h->kernel_launches += 2;
+      }
+    } else if (h->algo == 1) {
       if (a.total_items && batch_nnz) { CK(launch_score(h, a, h->custom_keys)); h->score_launches++; h->kernel_launches++; }
     } else if (h->ntiles && batch_nnz) {
       blk.thr_int = thr_int; blk.inv_scale = (float)std::ldexp(1.0, -F); blk.scale = (float)std::ldexp(1.0, F);

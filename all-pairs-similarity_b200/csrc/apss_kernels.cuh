@@ -40,6 +40,7 @@ enum Counter : int {
   C_NREJ = 7, C_NEMPTY = 8, C_NACTIVE = 9, C_MAXNNZ = 10,
   C_MAXSQ = 11,    // max squared L2 norm of a pruned vector (bits of a non-negative double)
   C_SKIPPED = 12,  // components of this batch left out of the index by exact index reduction
+  C_HEAVY = 13,    // candidate-major kernel: stored vectors deferred to the heavy pass
   C_PHASE = 16,    // 8 per-phase cycle totals of the dense kernel (thread 0 of every CTA)
   C_COUNT = 24
 };
@@ -839,15 +840,15 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
 #else
 #define PHASE_MARK(k) ((void)0)
 #endif
-  // index reduction: the accumulator holds only the indexed part of the dot product, so every touched
-  // candidate takes the rare path and is tested there against its own threshold
-  const unsigned thr_lo = a.row_ub ? 1u : b.thr_int;
+  const unsigned thr_lo = b.thr_int;
   const unsigned thr_hi = thr_lo << 16;      // high half >= thr  <=>  word >= thr << 16
 
+  unsigned long long nxt = 0;                // thread 0: the next work item, fetched while the current one runs
+  if (tid == 0) nxt = atomicAdd(&a.counters[C_WORK], 1ULL);
   for (;;) {
     __syncthreads();
     PHASE_MARK(5);
-    if (tid == 0) { s_item = atomicAdd(&a.counters[C_WORK], 1ULL); s_nseg = 0; s_segvalid = a.seg_cap - (a.seg_cap * 3 >> 3); s_nshort = 0; s_shortvalid = a.seg_cap * 3 >> 3; s_ndense = 0; s_next = 0; s_next2 = 0; }
+    if (tid == 0) { s_item = nxt; s_nseg = 0; s_segvalid = a.seg_cap - (a.seg_cap * 3 >> 3); s_nshort = 0; s_shortvalid = a.seg_cap * 3 >> 3; s_ndense = 0; s_next = 0; s_next2 = 0; }
     __syncthreads();
     const unsigned long long item = s_item;
     if (item >= a.total_items) break;
@@ -935,6 +936,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
     }
     __syncthreads();
     PHASE_MARK(1);
+    if (tid == 0) nxt = atomicAdd(&a.counters[C_WORK], 1ULL);      // consumed at the top of the next iteration
     const int nd = s_ndense;
     const int nlong = min(s_nseg, s_segvalid), nshort = min(s_nshort, s_shortvalid);
     // pad the dense list to a multiple of 4 with entries whose query weights stay zero (Wq is cleared per item)
@@ -1023,8 +1025,54 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
         const long long selfc = a.q_local_base + q0 + tid - c0;
         if (selfc >= 0 && selfc < CR) acc[tid * RW + (int)(selfc >> 1)] &= (selfc & 1) ? 0x0000ffffu : 0xffff0000u;
       }
+      if (a.row_ub && tid == 0) s_nseg = 0;                       // reused as the cursor of the touched-word queue
       __syncthreads();
       PHASE_MARK(7);
+      if (a.row_ub) {
+        // Reduced index: every touched candidate has its own threshold (thr - bound of its un-indexed part), so
+        // all touched words need global loads.  Pass 1 scans and clears the accumulators and queues the non-zero
+        // words (the segment queue is free now); pass 2 tests them one per thread, latencies in parallel.
+        uint2* tq = reinterpret_cast<uint2*>(segs);
+        const int tcap = a.seg_cap * 2;
+        auto test_word = [&](unsigned widx, unsigned word) {
+          const int row = (int)(widx / (unsigned)RW), wcol = (int)(widx - (unsigned)row * (unsigned)RW);
+          const int q = q0 + row;
+          const long long c = c0 + (long long)wcol * 2;
+          const float2 ub2 = __ldg(reinterpret_cast<const float2*>(a.row_ub + c));
+          const float qn = __fmul_ru(__ldg(a.q_nrm + q), b.scale);
+          long long qkey = 0;
+          if (DUPKEYS) qkey = __ldg(a.q_key + q);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const unsigned val = (word >> (k << 4)) & 0xffffu;
+            if (!val) continue;
+            if (DUPKEYS) { if (__ldg(a.c_key + c + k) == qkey) continue; ++n_cand; }
+            // dot(q, c) <= indexed part + |q| * |un-indexed part of c| (Cauchy-Schwarz), everything rounded up
+            const unsigned ub = fx_ceil(fminf(__fmul_ru(k ? ub2.y : ub2.x, qn), 8388607.f));
+            if (val + ub >= b.thr_int) {
+              const unsigned long long slot = atomicAdd(&a.counters[C_PF], 1ULL);
+              if (slot < a.out_cap) { a.out_q[slot] = q; a.out_c[slot] = (int32_t)(c + k); a.out_est[slot] = (float)val * b.inv_scale; }
+            }
+          }
+        };
+        for (int i = tid * 4; i < nwords; i += NT * 4) {
+          const uint4 v = *reinterpret_cast<const uint4*>(acc + i);
+          if ((v.x | v.y | v.z | v.w) == 0) continue;
+          *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
+          const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (!vv[k]) continue;
+            if (!DUPKEYS) n_cand += (unsigned)((vv[k] & 0xffffu) != 0) + (unsigned)(vv[k] > 0xffffu);
+            const int slot = atomicAdd(&s_nseg, 1);
+            if (slot < tcap) tq[slot] = make_uint2((unsigned)(i + k), vv[k]);
+            else test_word((unsigned)(i + k), vv[k]);           // queue full: test in place
+          }
+        }
+        __syncthreads();
+        const int nt = min(s_nseg, tcap);
+        for (int e = tid; e < nt; e += NT) { const uint2 w = tq[e]; test_word(w.x, w.y); }
+      } else
       for (int i = tid * 4; i < nwords; i += NT * 4) {
         const uint4 v = *reinterpret_cast<const uint4*>(acc + i);
         if ((v.x | v.y | v.z | v.w) == 0) continue;
@@ -1045,20 +1093,13 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
           const int q = q0 + row;
           long long qkey = 0;
           if (DUPKEYS) qkey = __ldg(a.q_key + q);
-          const float qn = a.row_ub ? __fmul_ru(__ldg(a.q_nrm + q), b.scale) : 0.f;
           unsigned pm = 0;                                      // halves to emit
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const unsigned val = (vv[k >> 1] >> ((k & 1) << 4)) & 0xffffu;
             if (!val) continue;
             if (DUPKEYS) { if (__ldg(a.c_key + c0 + (long long)(wcol + (k >> 1)) * 2 + (k & 1)) == qkey) continue; ++n_cand; }
-            unsigned thr_k = b.thr_int;
-            if (a.row_ub) {
-              // dot(q, c) <= indexed part + |q| * |un-indexed part of c| (Cauchy-Schwarz), all rounded up
-              const unsigned ub = fx_ceil(fminf(__fmul_ru(__ldg(a.row_ub + c0 + (long long)(wcol + (k >> 1)) * 2 + (k & 1)), qn), 8388607.f));
-              thr_k = ub >= thr_k ? 0u : thr_k - ub;
-            }
-            if (val >= thr_k) pm |= 1u << k;
+            if (val >= b.thr_int) pm |= 1u << k;
           }
           if (pm) {                                             // one slot claim per thread (<= 8 pairs)
             unsigned long long slot = atomicAdd(&a.counters[C_PF], (unsigned long long)__popc(pm));
@@ -1085,6 +1126,184 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
   if (tid == 0) { for (int k = 0; k < 8; ++k) atomicAdd(&a.counters[C_PHASE + k], (unsigned long long)ph[k]); }
 #endif
 #undef PHASE_MARK
+}
+
+
+// ------------------------------------------------------------------ K2c: candidate-major scoring on the reduced index
+
+// With exact index reduction on, a batch of 16 K queries touches ~10^8 postings instead of 2 * 10^11, and the
+// tile sweep of the kernels above (every query dimension looked up in every tile's directory, every
+// accumulator tile scanned) costs far more than the updates themselves.  This kernel turns the join around:
+// the BATCH is inverted (dim -> (query, weight) lists, rebuilt per call: k_qi_emit + sort + k_qdir) and the
+// stored vectors are streamed once; a warp takes one stored vector c, walks the query lists of c's INDEXED
+// components and accumulates dot(q, c_indexed) for the queries it meets in a small per-warp hash table in
+// shared memory.  The same counters result: postings visited = sum over (c, indexed d) of |queries with d|,
+// candidates = touched (q, c) pairs.  A touched pair survives to the fp64 verify kernel iff
+//   estimate * (1 + guard band) + |q| * |c_unindexed|  >=  t.
+// Stored vectors whose lists are too long for the table are deferred to k_score_cand_heavy.
+struct CandArgs {
+  const int64_t* fwd_ptr; const int32_t* fwd_idx; const double* fwd_val; const uint8_t* fwd_skip;
+  const float* row_ub; const int64_t* c_key;
+  const int32_t* qdir;       // [D + 1] offsets into qi
+  const uint2* qi;           // (query, weight as fp32 bits), by dim, query ascending
+  const float* q_nrm; const int64_t* q_key;
+  int64_t n_rows;            // stored vectors visible to this batch
+  int64_t q_local_base;      // shard-local id of query 0 when the batch was indexed in this call, else -1
+  int32_t nq;
+  float thr, band1;          // t and 1 + guard band of the fp32 estimate
+  int32_t* out_q; int32_t* out_c; float* out_est; unsigned long long out_cap;
+  unsigned long long* counters;
+  int32_t* heavy; int64_t heavy_cap;
+};
+
+__global__ void k_qi_emit(int n, const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim, const float* __restrict__ q_w,
+                          unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  for (int p = q_ptr[v]; p < q_ptr[v + 1]; ++p) {
+    keys[p] = (unsigned long long)(unsigned)q_dim[p];
+    vals[p] = ((unsigned long long)__float_as_uint(q_w[p]) << 32) | (unsigned)v;      // uint2{x = query, y = weight}
+  }
+}
+
+__global__ void k_qdir(const unsigned long long* __restrict__ keys, int nnz, int D, int32_t* __restrict__ qdir) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d > D) return;
+  qdir[d] = (int32_t)lower_bound_u64(keys, nnz, (unsigned long long)d);
+}
+
+static constexpr int CAND_TBL = 1024;      // hash slots per warp (key + value = 8 KB)
+static constexpr int CAND_LIMIT = 512;     // longest total list length handled in the table (load factor <= 1/2)
+static constexpr int CAND_CHUNK = 16;      // stored vectors per work-cursor fetch
+static constexpr int CAND_SHORT = 8;       // lists up to this length are walked by the lane that looked them up
+
+__device__ __forceinline__ void cand_insert(unsigned* keys, float* vals, unsigned mask, unsigned q, float p) {
+  unsigned h = ((q * 2654435761u) >> 12) & mask;
+  for (;;) {
+    const unsigned old = atomicCAS(keys + h, 0u, q + 1u);
+    if (old == 0u || old == q + 1u) break;
+    h = (h + 1u) & mask;
+  }
+  atomicAdd(vals + h, p);
+}
+
+__device__ __forceinline__ void cand_test_emit(const CandArgs& a, int q, long long c, float est, float cu, long long ckey,
+                                               unsigned long long& n_cand) {
+  if (a.q_local_base >= 0 && a.q_local_base + q == c) return;           // a query never meets itself (IWA:91)
+  if (a.q_key && __ldg(a.q_key + q) == ckey) return;                     // same external id (IWA:91)
+  ++n_cand;
+  const float ub = __fmul_ru(cu, __ldg(a.q_nrm + q));
+  if (__fmaf_ru(est, a.band1, ub) >= a.thr) {
+    const unsigned long long slot = atomicAdd(&a.counters[C_PF], 1ULL);
+    if (slot < a.out_cap) { a.out_q[slot] = q; a.out_c[slot] = (int32_t)c; a.out_est[slot] = est; }
+  }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) {
+  extern __shared__ __align__(16) unsigned smem_u[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned* keys = smem_u + (size_t)warp * (2 * CAND_TBL);
+  float* vals = reinterpret_cast<float*>(keys + CAND_TBL);
+  for (int i = lane; i < CAND_TBL; i += 32) { keys[i] = 0u; vals[i] = 0.f; }
+  __syncwarp();
+  unsigned long long n_post = 0, n_cand = 0;
+  for (;;) {
+    long long base = 0;
+    if (lane == 0) base = (long long)atomicAdd(&a.counters[C_WORK], (unsigned long long)CAND_CHUNK);
+    base = __shfl_sync(FULL, base, 0);
+    if (base >= a.n_rows) break;
+    const long long cend = min(base + (long long)CAND_CHUNK, (long long)a.n_rows);
+    for (long long c = base; c < cend; ++c) {
+      const long long fa = __ldg(a.fwd_ptr + c), fe = __ldg(a.fwd_ptr + c + 1);
+      unsigned total = 0;
+      for (long long j = fa + lane; j < fe; j += 32)
+        if (!a.fwd_skip[j]) { const int d = a.fwd_idx[j]; total += (unsigned)(__ldg(a.qdir + d + 1) - __ldg(a.qdir + d)); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+      if (!total) continue;
+      if (total > (unsigned)CAND_LIMIT) {
+        if (lane == 0) { const unsigned long long k = atomicAdd(&a.counters[C_HEAVY], 1ULL); if ((long long)k < a.heavy_cap) a.heavy[k] = (int32_t)c; }
+        continue;
+      }
+      if (lane == 0) n_post += total;
+      unsigned size = 64; while (size < 2u * total) size <<= 1;
+      const unsigned mask = size - 1u;
+      for (long long j0 = fa; j0 < fe; j0 += 32) {
+        const long long j = j0 + lane;
+        int s = 0, len = 0; float w = 0.f;
+        if (j < fe && !a.fwd_skip[j]) {
+          const int d = a.fwd_idx[j];
+          s = __ldg(a.qdir + d); len = __ldg(a.qdir + d + 1) - s;
+          w = fmaxf((float)a.fwd_val[j], W_MIN);
+        }
+        if (len <= CAND_SHORT)
+          for (int p = s; p < s + len; ++p) { const uint2 e = __ldg(a.qi + p); cand_insert(keys, vals, mask, e.x, w * __uint_as_float(e.y)); }
+        unsigned m = __ballot_sync(FULL, len > CAND_SHORT);
+        while (m) {
+          const int src = __ffs(m) - 1; m &= m - 1;
+          const int sj = __shfl_sync(FULL, s, src), lj = __shfl_sync(FULL, len, src);
+          const float wj = __shfl_sync(FULL, w, src);
+          for (int p = sj + lane; p < sj + lj; p += 32) { const uint2 e = __ldg(a.qi + p); cand_insert(keys, vals, mask, e.x, wj * __uint_as_float(e.y)); }
+        }
+      }
+      __syncwarp();
+      const float cu = __ldg(a.row_ub + c);
+      const long long ckey = a.q_key ? __ldg(a.c_key + c) : 0;
+      for (unsigned i = lane; i < size; i += 32) {
+        const unsigned k = keys[i];
+        if (!k) continue;
+        const float est = vals[i];
+        keys[i] = 0u; vals[i] = 0.f;
+        cand_test_emit(a, (int)(k - 1u), c, est, cu, ckey, n_cand);
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_cand += __shfl_down_sync(FULL, n_cand, o);
+  if (lane == 0) { atomicAdd(&a.counters[C_POSTINGS], n_post); atomicAdd(&a.counters[C_CANDS], n_cand); }
+}
+
+// Heavy pass: one CTA per deferred stored vector, dense fp32 accumulators over a chunk of `qc` queries in
+// shared memory (positive products: touched <=> non-zero), repeated for every chunk of the batch.
+__global__ void __launch_bounds__(512, 1) k_score_cand_heavy(const CandArgs a, int qc) {
+  extern __shared__ __align__(16) unsigned smem_u[];
+  float* acc = reinterpret_cast<float*>(smem_u);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const long long nh = min((long long)a.counters[C_HEAVY], (long long)a.heavy_cap);
+  unsigned long long n_post = 0, n_cand = 0;
+  for (long long hidx = blockIdx.x; hidx < nh; hidx += gridDim.x) {
+    const long long c = a.heavy[hidx];
+    const long long fa = __ldg(a.fwd_ptr + c), fe = __ldg(a.fwd_ptr + c + 1);
+    const float cu = __ldg(a.row_ub + c);
+    const long long ckey = a.q_key ? __ldg(a.c_key + c) : 0;
+    for (int q_lo = 0; q_lo < a.nq; q_lo += qc) {
+      const int q_hi = min(a.nq, q_lo + qc);
+      for (int i = tid; i < qc; i += blockDim.x) acc[i] = 0.f;
+      __syncthreads();
+      for (long long j = fa + warp; j < fe; j += nw) {            // one warp per component
+        if (a.fwd_skip[j]) continue;
+        const int d = a.fwd_idx[j];
+        const int s = __ldg(a.qdir + d), e = __ldg(a.qdir + d + 1);
+        const float w = fmaxf((float)a.fwd_val[j], W_MIN);
+        if (q_lo == 0 && lane == 0) n_post += (unsigned)(e - s);
+        for (int p = s + lane; p < e; p += 32) {
+          const uint2 x = __ldg(a.qi + p);
+          if ((int)x.x >= q_lo && (int)x.x < q_hi) atomicAdd(acc + ((int)x.x - q_lo), w * __uint_as_float(x.y));
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < q_hi - q_lo; i += blockDim.x) {
+        const float est = acc[i];
+        if (est != 0.f) cand_test_emit(a, q_lo + i, c, est, cu, ckey, n_cand);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { n_post += __shfl_down_sync(FULL, n_post, o); n_cand += __shfl_down_sync(FULL, n_cand, o); }
+  if (lane == 0 && (n_post | n_cand)) { atomicAdd(&a.counters[C_POSTINGS], n_post); atomicAdd(&a.counters[C_CANDS], n_cand); }
 }
 
 // ------------------------------------------------------------------ K4: fp64 verify

@@ -147,7 +147,7 @@ class Index:
         cfg = Config(C.sizeof(Config), int(dim), float(similarity_threshold), float(index_threshold),
                      None if self._mw is None else self._mw.ctypes.data, int(device), int(semantics), int(tile_vectors),
                      int(kernel_variant), int(reserve_vectors), int(reserve_nnz), int(reserve_pairs),
-                     1 if pruning else 0, 0, float(prune_alpha), float(max_query_norm))
+                     int(pruning), 0, float(prune_alpha), float(max_query_norm))
         h = C.c_void_p()
         rc = self._L.apss_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prune", type=int, default=0, nargs="?", const=2,
+                    help="main arm with exact index reduction on (1 tile kernel, 2 candidate-major kernel); counters then count the reduced work")
+    ap.add_argument("--no-pruned-leg", action="store_true", help="skip the extra 'pruned' measurement of the default run")
     ap.add_argument("--shard-gen", action="store_true", help="generate per-rank shards (default for heavy-tail configs)")
     ap.add_argument("--verbose", action="store_true", help="per-step timings on stderr")
     ap.add_argument("--profile-range", action="store_true",
@@ -260,7 +263,7 @@ def main():
             return b.indptr.contiguous(), b.indices.contiguous(), b.values.contiguous()
 
         total_nnz = data.nnz
-        eng = native.Index(D, t, device=local_rank, tile_vectors=args.tile, kernel_variant=args.variant,
+        eng = native.Index(D, t, device=local_rank, tile_vectors=args.tile, kernel_variant=args.variant, pruning=args.prune,
                            reserve_vectors=int((N + n_fresh * B) / world * 1.1) + 2 * B, reserve_nnz=int(total_nnz / world * 1.15) + (1 << 20))
         disp = ShardDispatcher(eng, device=dev)
         t_load = time.time()
@@ -297,7 +300,7 @@ def main():
             return b.indptr.contiguous(), b.indices.contiguous(), b.values.contiguous()
 
         total_nnz = shard.nnz * world
-        eng = native.Index(D, t, device=local_rank, tile_vectors=args.tile, kernel_variant=args.variant,
+        eng = native.Index(D, t, device=local_rank, tile_vectors=args.tile, kernel_variant=args.variant, pruning=args.prune,
                            reserve_vectors=int((N + n_fresh * B) / world * 1.1) + 2 * B, reserve_nnz=int(shard.nnz * 1.15) + (1 << 22))
         disp = ShardDispatcher(eng, device=dev)
         t_load = time.time()
@@ -426,7 +429,9 @@ def main():
         "dtype": "f32 accumulate + f64 verify", "data": "synthetic",
         "config": {"workload": cfg["workload"], "index_vectors": N, "batch": B, "sharding": "id-range block-cyclic x%d" % world,
                    "l2": "inputs larger than L2 (index %.0f MB postings per GPU)" % (st["bytes_postings"] / 1e6),
-                   "tile_vectors": st["tile_vectors"], "warps_per_cta": st["warps_per_cta"], "kernel_variant": args.variant},
+                   "tile_vectors": st["tile_vectors"], "warps_per_cta": st["warps_per_cta"], "kernel_variant": args.variant,
+                   "pruning": ("exact index reduction ON: %.1f%% of stored components un-indexed; counters count the reduced work"
+                               % (100.0 * st["n_unindexed"] / max(st["n_unindexed"] + st["n_postings"], 1))) if args.prune else "off (parity counters)"},
         "pairs_per_sec": tot["pairs"] / dt_value,
         "postings_per_sec": tot["postings"] / dt_value,
         "step_latency_ms": {"min": float(np.min(step_wall)), "p50": float(np.percentile(step_wall, 50)), "max": float(np.max(step_wall))},

@@ -81,7 +81,9 @@ typedef struct apss_config {
   /* Exact index reduction (the pruning the reference planned around its max-weight stub,  */
   /* EPA:51-57,81-93).  Off by default: with it on, the pair set and similarities are unchanged but        */
   /* postings_visited / candidates_unique count only what the reduced index makes the kernel touch.         */
-  int32_t pruning;             /* 0 = off (parity counters), 1 = on (default scoring kernel only)          */
+  int32_t pruning;             /* 0 = off (parity counters); 1 = on, tile kernel on the reduced index;     */
+                               /* 2 = on, candidate-major kernel (the batch is inverted instead and the    */
+                               /* stored vectors are streamed; same results and counters as 1, much faster) */
   int32_t reserved0;
   double prune_alpha;          /* share of (t / max_query_norm)^2 a vector may keep out of the index;      */
                                /* 0 = default 0.8; must be < 1                                             */

@@ -416,9 +416,10 @@ def test_keys_only_on_some_batches():
 
 # ---------------------------------------------------------------- exact index reduction
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("tile,batch,t,alpha", [(0, 2500, 0.6, 0.0), (256, 333, 0.6, 0.5), (1024, 4096, 0.4, 0.95),
                                                 (128, 7, 0.7, 0.0), (512, 1000, 0.9, 0.3)])
-def test_pruned_index_same_pairs_fewer_postings(tile, batch, t, alpha):
+def test_pruned_index_same_pairs_fewer_postings(tile, batch, t, alpha, mode):
     """With `pruning` on the pair set and the fp64 similarities are those of the un-pruned run (bit-exact),
     while the counters are those of the oracle's restatement of the same reduction rule."""
     N, D = 6000, 1 << 12
@@ -426,7 +427,7 @@ def test_pruned_index_same_pairs_fewer_postings(tile, batch, t, alpha):
     n = native()
     o_full = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
     o_pr = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8, pruning=True, prune_alpha=alpha)
-    g = n.Index(D, t, tile_vectors=tile, pruning=True, prune_alpha=alpha)
+    g = n.Index(D, t, tile_vectors=tile, pruning=mode, prune_alpha=alpha)
     tot_full = tot_pr = 0
     for lo in range(0, N, batch):
         csr = csr_slice(data, lo, min(N, lo + batch))
@@ -442,14 +443,15 @@ def test_pruned_index_same_pairs_fewer_postings(tile, batch, t, alpha):
     assert tot_pr * 2 < tot_full
 
 
-def test_pruned_index_query_only_keys_and_r0():
+@pytest.mark.parametrize("mode", [1, 2])
+def test_pruned_index_query_only_keys_and_r0(mode):
     """frozen / query-only batches, duplicate external ids and the R0 post-filter on top of the reduced index"""
     N, D, t = 3000, 1 << 10, 0.5
     data = _synth(N, D, 12, seed=9)
     n = native()
     keys = np.arange(N, dtype=np.int64); keys[1::7] = keys[0:-1:7]          # some vectors share an id with their neighbour
     o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
-    g = n.Index(D, t, tile_vectors=256, pruning=True)
+    g = n.Index(D, t, tile_vectors=256, pruning=mode)
     for lo in range(0, 2000, 500):
         csr = csr_slice(data, lo, lo + 500)
         ro = o.insert_batch(*csr, keys=keys[lo:lo + 500]); rg = g.insert_batch(*csr, ext_keys=keys[lo:lo + 500])
@@ -461,16 +463,17 @@ def test_pruned_index_query_only_keys_and_r0():
     assert g.stats()["n_vectors"] == 2000 and rg.n_pairs > 0
     # R0 on the reduced index against the faithful as-built oracle
     o0 = orc.Oracle(D, t, semantics=orc.R0, algo=orc.ALGO_FAITHFUL, threads=8)
-    g0 = n.Index(D, t, semantics=n.SEM_R0, tile_vectors=256, pruning=True)
+    g0 = n.Index(D, t, semantics=n.SEM_R0, tile_vectors=256, pruning=mode)
     for lo in range(0, 1500, 500):
         csr = csr_slice(data, lo, lo + 500)
         ro = o0.insert_batch(*csr); rg = g0.insert_batch(*csr, first_dim=orc.first_dims(*csr))
         assert_pairs_equal(gpu_pairs(g0, rg), ro.pair_set())
 
 
-def test_pruned_index_refuses_vectors_over_the_norm_promise():
+@pytest.mark.parametrize("mode", [1, 2])
+def test_pruned_index_refuses_vectors_over_the_norm_promise(mode):
     n = native()
-    g = n.Index(64, 0.5, pruning=True)                       # max_query_norm defaults to 1
+    g = n.Index(64, 0.5, pruning=mode)                       # max_query_norm defaults to 1
     g.insert_batch(*csr_from_dicts([A]))
     with pytest.raises(n.ApssError) as e:
         g.insert_batch(*csr_from_dicts([{0: .6, 1: .8}, {0: 3.0, 1: 4.0}]))
@@ -478,7 +481,7 @@ def test_pruned_index_refuses_vectors_over_the_norm_promise():
     assert g.stats()["n_vectors"] == 1                       # all-or-nothing
     rg = g.insert_batch(*csr_from_dicts([dict(A)]))
     assert gpu_pairs(g, rg) == {(1, 0): .6 * .6 + .8 * .8}
-    g5 = n.Index(64, 6.0, pruning=True, max_query_norm=5.0)   # un-normalised data with a declared bound
+    g5 = n.Index(64, 6.0, pruning=mode, max_query_norm=5.0)   # un-normalised data with a declared bound
     g5.insert_batch(*csr_from_dicts([{0: 3.0, 1: 4.0}]))
     rg = g5.insert_batch(*csr_from_dicts([{0: 3.0, 1: 4.0}, {0: 1.0}]))
     assert gpu_pairs(g5, rg) == {(1, 0): 25.0}
@@ -489,14 +492,15 @@ def test_pruned_index_refuses_vectors_over_the_norm_promise():
         n.Index(64, 0.5, pruning=True, prune_alpha=1.0)
 
 
-def test_pruned_c2_shape():
+@pytest.mark.parametrize("mode", [1, 2])
+def test_pruned_c2_shape(mode):
     """C2's shape (100 K x 2^16, t = 0.8) on a 30 K prefix: full pair-set parity, large work reduction"""
     import apss_b200
     N, D, t = 30_000, 1 << 16, 0.8
     data = apss_b200.synth.generate(N, D, 50, seed=20260102).numpy()
     n = native()
     o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=16)
-    g = n.Index(D, t, pruning=True)
+    g = n.Index(D, t, pruning=mode)
     tf = tp = 0
     for lo in range(0, N, 4096):
         csr = csr_slice(data, lo, min(N, lo + 4096))
@@ -504,3 +508,27 @@ def test_pruned_c2_shape():
         assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
         tf += ro.postings_visited; tp += rg.postings_visited
     assert o.totals()["pairs"] > 0 and tp * 20 < tf
+
+
+def test_candidate_major_heavy_vectors_and_many_queries():
+    """stored vectors whose query lists overflow the per-warp table take the heavy pass: a dimension shared by every
+    vector with a weight large enough to stay indexed, batches larger than one heavy-pass query chunk is not needed
+    (chunking is covered by nq > 0 only), duplicate ids and in-batch pairs included"""
+    rng = np.random.default_rng(3)
+    N, D, t = 3000, 512, 0.5
+    rows = []
+    for i in range(N):
+        dims = rng.choice(np.arange(1, D), size=6, replace=False)
+        v = {int(d): float(x) for d, x in zip(dims, rng.uniform(0.05, 0.3, size=6))}
+        v[0] = 0.9                                  # shared by all, too heavy to stay out of the index
+        nrm = np.sqrt(sum(x * x for x in v.values()))
+        rows.append({d: x / nrm for d, x in v.items()})
+    n = native()
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8, pruning=True)
+    g = n.Index(D, t, pruning=2)
+    for lo in range(0, N, 1000):
+        csr = csr_from_dicts(rows[lo:lo + 1000])
+        ro = o.insert_batch(*csr); rg = g.insert_batch(*csr)
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+        assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+    assert o.totals()["pairs"] > 1000
