@@ -294,7 +294,7 @@ static int32_t build_query_index(apss_handle* h, int32_t n, int32_t batch_nnz) {
 }
 
 static cudaError_t launch_cand(apss_handle* h, const CandArgs& a) {
-  const size_t smem = (size_t)h->cand_warps * 2 * CAND_TBL * sizeof(unsigned);
+  const size_t smem = (size_t)h->cand_warps * (2 * CAND_TBL + 3 * CAND_FEAT + 4) * sizeof(unsigned);
   auto kern = h->cand_warps == 16 ? k_score_cand<16> : k_score_cand<24>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, h->smem_optin - 1024));
   if (e != cudaSuccess) return e;
@@ -758,6 +758,10 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
         ca.n_rows = n_rows; ca.q_local_base = q_local_base; ca.nq = n;
         ca.thr = (float)t; if ((double)ca.thr > t) ca.thr = std::nextafterf(ca.thr, -INFINITY);
         ca.band1 = (float)(1.0 + (double)(h->max_nnz_seen + 8) * std::ldexp(1.0, -22));
+        {   // u32 fixed point: every dot product is <= the largest squared norm (Cauchy-Schwarz)
+          const int Fc = std::max(-100, std::min(100, (int)std::floor(std::log2(2147483648.0 / (std::max(h->max_sq, 1e-300) * (1.0 + 1e-6))))));
+          ca.scale = (float)std::ldexp(1.0, Fc); ca.inv_scale = (float)std::ldexp(1.0, -Fc);
+        }
         ca.out_q = h->pf_q.p; ca.out_c = h->pf_c.p; ca.out_est = h->pf_est.p; ca.out_cap = h->pf_q.cap;
         ca.counters = h->d_counters; ca.heavy = h->heavy.p; ca.heavy_cap = (int64_t)h->heavy.cap;
         CK(launch_cand(h, ca));
@@ -785,7 +789,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     CK(cudaEventRecord(h->ev_b1, s));
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->h_counters + C_PHASE, h->d_counters + C_PHASE, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    if (h->prune) CK(cudaMemcpyAsync(h->h_counters + C_SKIPPED, h->d_counters + C_SKIPPED, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if (h->prune) CK(cudaMemcpyAsync(h->h_counters + C_SKIPPED, h->d_counters + C_SKIPPED, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (h->h_counters[C_PF] <= h->pf_q.cap) break;
     if (attempt == 2) return h->fail(APSS_E_NOMEM, "pair buffer overflow persisted");
@@ -803,6 +807,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   for (int k = 0; k < 8; ++k) h->phase_cycles[k] = (int64_t)h->h_counters[C_PHASE + k];
   if (h->prune && !query_only) { h->tot_skipped += (int64_t)h->h_counters[C_SKIPPED]; h->n_post = h->nnz - h->tot_skipped; }
   res.work_items = (int64_t)((unsigned long long)h->ntiles * (unsigned long long)(h->algo == 1 ? n : (n + h->QB - 1) / h->QB));
+  if (h->prune_mode == 2) res.work_items = (int64_t)h->h_counters[C_HEAVY];      // stored vectors that took the heavy pass
   h->last_n = n; h->last_pairs = res.n_pairs;
   h->tot_postings += res.postings_visited; h->tot_cands += res.candidates_unique; h->tot_pairs += res.n_pairs; h->tot_pf += res.n_prefilter;
   h->tot_score_ms += res.score_ms;

@@ -1151,6 +1151,7 @@ struct CandArgs {
   int64_t q_local_base;      // shard-local id of query 0 when the batch was indexed in this call, else -1
   int32_t nq;
   float thr, band1;          // t and 1 + guard band of the fp32 estimate
+  float scale, inv_scale;    // 2^F, 2^-F: fixed-point accumulators of k_score_cand
   int32_t* out_q; int32_t* out_c; float* out_est; unsigned long long out_cap;
   unsigned long long* counters;
   int32_t* heavy; int64_t heavy_cap;
@@ -1177,48 +1178,82 @@ static constexpr int CAND_LIMIT = 512;     // longest total list length handled 
 static constexpr int CAND_CHUNK = 16;      // stored vectors per work-cursor fetch
 static constexpr int CAND_SHORT = 8;       // lists up to this length are walked by the lane that looked them up
 
-__device__ __forceinline__ void cand_insert(unsigned* keys, float* vals, unsigned mask, unsigned q, float p) {
+// fixed-point accumulation (native shared-memory atomic add; every contribution rounded up, so it is >= 1)
+__device__ __forceinline__ void cand_insert(unsigned* keys, unsigned* vals, unsigned mask, unsigned q, float p, float scale) {
   unsigned h = ((q * 2654435761u) >> 12) & mask;
   for (;;) {
     const unsigned old = atomicCAS(keys + h, 0u, q + 1u);
     if (old == 0u || old == q + 1u) break;
     h = (h + 1u) & mask;
   }
-  atomicAdd(vals + h, p);
+  atomicAdd(vals + h, __float2uint_ru(p * scale));
 }
 
-__device__ __forceinline__ void cand_test_emit(const CandArgs& a, int q, long long c, float est, float cu, long long ckey,
+__device__ __forceinline__ void cand_test_emit(const CandArgs& a, int q, long long c, float est, float cu, float qn, bool same_key,
                                                unsigned long long& n_cand) {
   if (a.q_local_base >= 0 && a.q_local_base + q == c) return;           // a query never meets itself (IWA:91)
-  if (a.q_key && __ldg(a.q_key + q) == ckey) return;                     // same external id (IWA:91)
+  if (same_key) return;                                                  // same external id (IWA:91)
   ++n_cand;
-  const float ub = __fmul_ru(cu, __ldg(a.q_nrm + q));
+  const float ub = __fmul_ru(cu, qn);
   if (__fmaf_ru(est, a.band1, ub) >= a.thr) {
     const unsigned long long slot = atomicAdd(&a.counters[C_PF], 1ULL);
     if (slot < a.out_cap) { a.out_q[slot] = q; a.out_c[slot] = (int32_t)c; a.out_est[slot] = est; }
   }
 }
 
+static constexpr int CAND_FEAT = 64;       // non-empty query lists per stored vector handled by the flat walk
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) {
   extern __shared__ __align__(16) unsigned smem_u[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned* keys = smem_u + (size_t)warp * (2 * CAND_TBL);
-  float* vals = reinterpret_cast<float*>(keys + CAND_TBL);
-  for (int i = lane; i < CAND_TBL; i += 32) { keys[i] = 0u; vals[i] = 0.f; }
+  unsigned* vals = keys + CAND_TBL;
+  // per-warp list of the vector's non-empty query lists: start offset in the flattened walk, list start, weight
+  int* pre = reinterpret_cast<int*>(smem_u + (size_t)WARPS * (2 * CAND_TBL)) + warp * (3 * CAND_FEAT + 4);
+  int* fs = pre + CAND_FEAT + 4;
+  float* fw = reinterpret_cast<float*>(fs + CAND_FEAT);
+  for (int i = lane; i < CAND_TBL; i += 32) { keys[i] = 0u; vals[i] = 0u; }
   __syncwarp();
   unsigned long long n_post = 0, n_cand = 0;
+  constexpr int RC = 4;                       // components per lane kept in registers between the two passes
+  // fallback walk of one component's query list: short lists by the owning lane, long ones by the whole warp
+  auto walk = [&](int s, int len, float w, unsigned mask) {
+    if (len <= CAND_SHORT)
+      for (int p = s; p < s + len; ++p) { const uint2 x = __ldg(a.qi + p); cand_insert(keys, vals, mask, x.x, w * __uint_as_float(x.y), a.scale); }
+    unsigned m = __ballot_sync(FULL, len > CAND_SHORT);
+    while (m) {
+      const int src = __ffs(m) - 1; m &= m - 1;
+      const int sj = __shfl_sync(FULL, s, src), lj = __shfl_sync(FULL, len, src);
+      const float wj = __shfl_sync(FULL, w, src);
+      for (int p = sj + lane; p < sj + lj; p += 32) { const uint2 x = __ldg(a.qi + p); cand_insert(keys, vals, mask, x.x, wj * __uint_as_float(x.y), a.scale); }
+    }
+  };
+  auto lookup = [&](long long j, long long fe, int& s, int& len, float& w) {
+    s = 0; len = 0; w = 0.f;
+    if (j < fe && !a.fwd_skip[j]) {
+      const int d = a.fwd_idx[j];
+      s = __ldg(a.qdir + d); len = __ldg(a.qdir + d + 1) - s;
+      w = fmaxf((float)a.fwd_val[j], W_MIN);
+    }
+  };
   for (;;) {
     long long base = 0;
     if (lane == 0) base = (long long)atomicAdd(&a.counters[C_WORK], (unsigned long long)CAND_CHUNK);
     base = __shfl_sync(FULL, base, 0);
     if (base >= a.n_rows) break;
-    const long long cend = min(base + (long long)CAND_CHUNK, (long long)a.n_rows);
-    for (long long c = base; c < cend; ++c) {
-      const long long fa = __ldg(a.fwd_ptr + c), fe = __ldg(a.fwd_ptr + c + 1);
+    const int nc = (int)min((long long)CAND_CHUNK, (long long)a.n_rows - base);
+    long long myptr = 0;
+    if (lane <= nc) myptr = __ldg(a.fwd_ptr + base + lane);        // the chunk's row pointers, one load
+    for (int ci = 0; ci < nc; ++ci) {
+      const long long c = base + ci;
+      const long long fa = __shfl_sync(FULL, myptr, ci), fe = __shfl_sync(FULL, myptr, ci + 1);
+      int s_[RC], len_[RC]; float w_[RC];
       unsigned total = 0;
-      for (long long j = fa + lane; j < fe; j += 32)
-        if (!a.fwd_skip[j]) { const int d = a.fwd_idx[j]; total += (unsigned)(__ldg(a.qdir + d + 1) - __ldg(a.qdir + d)); }
+#pragma unroll
+      for (int it = 0; it < RC; ++it) { lookup(fa + it * 32 + lane, fe, s_[it], len_[it], w_[it]); total += (unsigned)len_[it]; }
+      const bool tail = fe - fa > RC * 32;
+      if (tail) for (long long j = fa + RC * 32 + lane; j < fe; j += 32) { int s, len; float w; lookup(j, fe, s, len, w); total += (unsigned)len; }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
       if (!total) continue;
@@ -1229,33 +1264,61 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) 
       if (lane == 0) n_post += total;
       unsigned size = 64; while (size < 2u * total) size <<= 1;
       const unsigned mask = size - 1u;
-      for (long long j0 = fa; j0 < fe; j0 += 32) {
-        const long long j = j0 + lane;
-        int s = 0, len = 0; float w = 0.f;
-        if (j < fe && !a.fwd_skip[j]) {
-          const int d = a.fwd_idx[j];
-          s = __ldg(a.qdir + d); len = __ldg(a.qdir + d + 1) - s;
-          w = fmaxf((float)a.fwd_val[j], W_MIN);
+      // compact the non-empty lists: slot and exclusive prefix of the lengths
+      int nf = 0, run = 0;
+#pragma unroll
+      for (int it = 0; it < RC; ++it) {
+        const unsigned bal = __ballot_sync(FULL, len_[it] > 0);
+        int inc = len_[it];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        const int slot = nf + __popc(bal & ((1u << lane) - 1u));
+        if (len_[it] > 0 && slot < CAND_FEAT) { pre[slot] = run + inc - len_[it]; fs[slot] = s_[it]; fw[slot] = w_[it]; }
+        nf += __popc(bal); run += __shfl_sync(FULL, inc, 31);
+      }
+      if (!tail && nf <= CAND_FEAT) {
+        if (lane == 0) pre[nf] = (int)total;
+        __syncwarp();
+        // flat walk: item t of the concatenated lists -> (list, position); iterations are independent
+        for (int t0 = 0; t0 < (int)total; t0 += 64) {
+          int f_[2], t_[2]; uint2 x_[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            t_[u] = t0 + u * 32 + lane; f_[u] = 0;
+            if (t_[u] < (int)total) {
+              int lo = 0, hi = nf;                               // largest f with pre[f] <= t
+              while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= t_[u]) lo = mid; else hi = mid; }
+              f_[u] = lo;
+              x_[u] = __ldg(a.qi + fs[lo] + (t_[u] - pre[lo]));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (t_[u] < (int)total) cand_insert(keys, vals, mask, x_[u].x, fw[f_[u]] * __uint_as_float(x_[u].y), a.scale);
         }
-        if (len <= CAND_SHORT)
-          for (int p = s; p < s + len; ++p) { const uint2 e = __ldg(a.qi + p); cand_insert(keys, vals, mask, e.x, w * __uint_as_float(e.y)); }
-        unsigned m = __ballot_sync(FULL, len > CAND_SHORT);
-        while (m) {
-          const int src = __ffs(m) - 1; m &= m - 1;
-          const int sj = __shfl_sync(FULL, s, src), lj = __shfl_sync(FULL, len, src);
-          const float wj = __shfl_sync(FULL, w, src);
-          for (int p = sj + lane; p < sj + lj; p += 32) { const uint2 e = __ldg(a.qi + p); cand_insert(keys, vals, mask, e.x, wj * __uint_as_float(e.y)); }
-        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < RC; ++it) if (fa + it * 32 < fe) walk(s_[it], len_[it], w_[it], mask);
+        for (long long j0 = fa + RC * 32; j0 < fe; j0 += 32) { int s, len; float w; lookup(j0 + lane, fe, s, len, w); walk(s, len, w, mask); }
       }
       __syncwarp();
       const float cu = __ldg(a.row_ub + c);
       const long long ckey = a.q_key ? __ldg(a.c_key + c) : 0;
-      for (unsigned i = lane; i < size; i += 32) {
-        const unsigned k = keys[i];
-        if (!k) continue;
-        const float est = vals[i];
-        keys[i] = 0u; vals[i] = 0.f;
-        cand_test_emit(a, (int)(k - 1u), c, est, cu, ckey, n_cand);
+      for (unsigned i0 = 0; i0 < size; i0 += 128) {
+        unsigned k_[4], v_[4]; float qn_[4]; bool same_[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned i = i0 + u * 32 + lane;
+          k_[u] = i < size ? keys[i] : 0u; v_[u] = 0u; qn_[u] = 0.f; same_[u] = false;
+          if (k_[u]) {
+            v_[u] = vals[i]; keys[i] = 0u; vals[i] = 0u;
+            qn_[u] = __ldg(a.q_nrm + (k_[u] - 1u));
+            if (a.q_key) same_[u] = __ldg(a.q_key + (k_[u] - 1u)) == ckey;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (k_[u]) cand_test_emit(a, (int)(k_[u] - 1u), c, __uint2float_ru(v_[u]) * a.inv_scale, cu, qn_[u], same_[u], n_cand);
       }
       __syncwarp();
     }
@@ -1296,7 +1359,7 @@ __global__ void __launch_bounds__(512, 1) k_score_cand_heavy(const CandArgs a, i
       __syncthreads();
       for (int i = tid; i < q_hi - q_lo; i += blockDim.x) {
         const float est = acc[i];
-        if (est != 0.f) cand_test_emit(a, q_lo + i, c, est, cu, ckey, n_cand);
+        if (est != 0.f) cand_test_emit(a, q_lo + i, c, est, cu, __ldg(a.q_nrm + q_lo + i), a.q_key && __ldg(a.q_key + q_lo + i) == ckey, n_cand);
       }
       __syncthreads();
     }

@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prune", type=int, default=0, nargs="?", const=2,
                     help="main arm with exact index reduction on (1 tile kernel, 2 candidate-major kernel); counters then count the reduced work")
+    ap.add_argument("--prune-alpha", type=float, default=0.0)
     ap.add_argument("--no-pruned-leg", action="store_true", help="skip the extra 'pruned' measurement of the default run")
     ap.add_argument("--shard-gen", action="store_true", help="generate per-rank shards (default for heavy-tail configs)")
     ap.add_argument("--verbose", action="store_true", help="per-step timings on stderr")
@@ -263,7 +264,7 @@ def main():
             return b.indptr.contiguous(), b.indices.contiguous(), b.values.contiguous()
 
         total_nnz = data.nnz
-        eng = native.Index(D, t, device=local_rank, tile_vectors=args.tile, kernel_variant=args.variant, pruning=args.prune,
+        eng = native.Index(D, t, device=local_rank, tile_vectors=args.tile, kernel_variant=args.variant, pruning=args.prune, prune_alpha=args.prune_alpha,
                            reserve_vectors=int((N + n_fresh * B) / world * 1.1) + 2 * B, reserve_nnz=int(total_nnz / world * 1.15) + (1 << 20))
         disp = ShardDispatcher(eng, device=dev)
         t_load = time.time()
@@ -300,7 +301,7 @@ def main():
             return b.indptr.contiguous(), b.indices.contiguous(), b.values.contiguous()
 
         total_nnz = shard.nnz * world
-        eng = native.Index(D, t, device=local_rank, tile_vectors=args.tile, kernel_variant=args.variant, pruning=args.prune,
+        eng = native.Index(D, t, device=local_rank, tile_vectors=args.tile, kernel_variant=args.variant, pruning=args.prune, prune_alpha=args.prune_alpha,
                            reserve_vectors=int((N + n_fresh * B) / world * 1.1) + 2 * B, reserve_nnz=int(shard.nnz * 1.15) + (1 << 22))
         disp = ShardDispatcher(eng, device=dev)
         t_load = time.time()
@@ -359,8 +360,8 @@ def main():
         r = step_device(cursor); cursor += B
         step_wall.append((time.time() - ts_) * 1e3)
         if args.verbose and rank == 0:
-            print("value step: wall %.1f ms score %.1f ms device %.1f ms pairs %d prefilter %d" % (
-                (time.time() - ts_) * 1e3, r.local.score_ms, r.local.device_ms, r.n_pairs, r.local.n_prefilter), file=sys.stderr, flush=True)
+            print("value step: wall %.1f ms score %.1f ms device %.1f ms pairs %d prefilter %d items %d" % (
+                (time.time() - ts_) * 1e3, r.local.score_ms, r.local.device_ms, r.n_pairs, r.local.n_prefilter, r.local.work_items), file=sys.stderr, flush=True)
         tot["cands"] += r.candidates_unique; tot["pairs"] += r.n_pairs; tot["postings"] += r.postings_visited
         tot["score_ms"] += r.local.score_ms; tot["local_postings"] += r.local.postings_visited; tot["items"] += r.local.work_items
     ev1.record(lib_stream)

@@ -103,7 +103,8 @@ typedef struct apss_batch_result {
   int64_t n_prefilter;       /* fp32 guard-band survivors handed to the fp64 verify kernel           */
   int64_t postings_visited;  /* sum over query terms of visible posting-list lengths (IWA:86)        */
   int64_t candidates_unique; /* (q, c) with >= 1 shared dim, c.id != q.id: "candidate dot-products"  */
-  int64_t work_items;        /* (query, index tile) items the scoring kernel processed               */
+  int64_t work_items;        /* (query, index tile) items the scoring kernel processed; pruning = 2: stored   */
+                             /* vectors that took the heavy pass                                             */
   double score_ms;           /* CUDA-event time of the scoring kernel(s), on the handle's stream     */
   double device_ms;          /* CUDA-event time first kernel -> last kernel of the call              */
 } apss_batch_result;
