@@ -171,6 +171,7 @@ struct apss_handle {
   int prune_mode = 0;        // 1: tile kernels on the reduced index, 2: candidate-major kernel (no tiles are built)
   int cand_warps = 24;
   DevBuf<int32_t> qdir; VmBuf<int32_t> heavy;
+  VmBuf<int64_t> ifw_ptr; VmBuf<uint2> ifw; DevBuf<int32_t> q_icnt, q_iptr;   // compact store of the indexed components
   DevBuf<int32_t> df; VmBuf<uint8_t> fwd_skip; VmBuf<float> row_ub;
   DevBuf<uint8_t> q_skip; DevBuf<float> q_cu, q_nrm;
   DevBuf<unsigned long long> pr_keys_in, pr_keys_out, pr_vals_in, pr_vals_out;
@@ -318,7 +319,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) { cudaGetLastError(); return APSS_E_NO_DEVICE; }
   apss_handle* h = new apss_handle();
   h->cfg = *cfg; h->cfg.max_weight = nullptr; h->device = cfg->device;
-  h->fwd_skip.device = h->row_ub.device = h->heavy.device = cfg->device;
+  h->fwd_skip.device = h->row_ub.device = h->heavy.device = h->ifw_ptr.device = h->ifw.device = cfg->device;
   h->fwd_ptr.device = h->fwd_idx.device = h->fwd_val.device = h->gid.device = h->key.device = h->post.device = h->dir.device =
       h->tile_base.device = h->dn_cnt.device = h->dn_dim.device = h->dn_len.device = h->tile_cnt.device = h->dn_hash.device =
       h->dn_w.device = cfg->device;
@@ -438,7 +439,7 @@ extern "C" void apss_destroy(apss_handle* h) {
   h->dn_cnt.release(); h->dn_dim.release(); h->dn_len.release(); h->tile_cnt.release(); h->dn_hash.release(); h->dn_w.release(); h->s_vals_out.release();
   h->s_keys_in.release(); h->s_keys_out.release(); h->s_vals_in.release(); h->s_tile_start.release(); h->cub_tmp.release();
   h->pf_q.release(); h->pf_c.release(); h->pf_est.release(); h->out_q.release(); h->out_c.release(); h->out_sim.release();
-  h->qdir.release(); h->heavy.release();
+  h->qdir.release(); h->heavy.release(); h->ifw_ptr.release(); h->ifw.release(); h->q_icnt.release(); h->q_iptr.release();
   h->df.release(); h->fwd_skip.release(); h->row_ub.release(); h->q_skip.release(); h->q_cu.release(); h->q_nrm.release();
   h->pr_keys_in.release(); h->pr_keys_out.release(); h->pr_vals_in.release(); h->pr_vals_out.release();
   if (h->d_counters) cudaFree(h->d_counters);
@@ -459,6 +460,7 @@ extern "C" void apss_destroy(apss_handle* h) {
 static int32_t prune_select(apss_handle* h, int32_t n, int32_t batch_nnz) {
   cudaStream_t s = h->stream;
   CK(h->q_skip.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_cu.reserve(n, 0, s));
+  CK(h->q_icnt.reserve(n + 1, 0, s)); CK(h->q_iptr.reserve(n + 1, 0, s));
   CK(h->pr_keys_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_keys_out.reserve(std::max(batch_nnz, 1), 0, s));
   CK(h->pr_vals_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_vals_out.reserve(std::max(batch_nnz, 1), 0, s));
   if (batch_nnz) {
@@ -473,8 +475,15 @@ static int32_t prune_select(apss_handle* h, int32_t n, int32_t batch_nnz) {
     CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->pr_keys_in.p, h->pr_keys_out.p, h->pr_vals_in.p, h->pr_vals_out.p, batch_nnz, 0, 31 + rowbits, s));
     h->kernel_launches += 4;
   }
-  k_prune_mark<<<cdiv(n, 128), 128, 0, s>>>(n, h->q_ptr.p, h->q_val.p, h->pr_vals_out.p, h->prune_lim, h->q_skip.p, h->q_cu.p, h->d_counters);
+  k_prune_mark<<<cdiv(n + 1, 128), 128, 0, s>>>(n, h->q_ptr.p, h->q_val.p, h->pr_vals_out.p, h->prune_lim, h->q_skip.p, h->q_cu.p, h->q_icnt.p, h->d_counters);
   CK(cudaGetLastError()); h->kernel_launches++;
+  if (h->prune_mode == 2) {
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, h->q_icnt.p, h->q_iptr.p, n + 1, s));
+    CK(h->cub_tmp.reserve(tb, 0, s));
+    CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tb, h->q_icnt.p, h->q_iptr.p, n + 1, s));
+    h->kernel_launches++;
+  }
   return APSS_OK;
 }
 
@@ -500,6 +509,11 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
   }
   if (h->prune_mode == 2) {     // candidate-major scoring streams the forward store: there is no tile index to maintain
     CK(h->heavy.reserve(n_new, 0, s));
+    // indexed components so far: known on the host up to the previous batch; this batch adds at most batch_nnz
+    const int64_t ifw_old = nnz_old - h->tot_skipped;
+    CK(h->ifw_ptr.reserve(n_new + 1, n_old ? n_old + 1 : 0, s)); CK(h->ifw.reserve(std::max<int64_t>(ifw_old + batch_nnz, 1), ifw_old, s));
+    k_ifw_append<<<cdiv(n, 128), 128, 0, s>>>(n, n_old, h->q_ptr.p, h->q_dim.p, h->q_w.p, h->q_skip.p, h->q_iptr.p, h->ifw_ptr.p, h->ifw.p);
+    CK(cudaGetLastError()); h->kernel_launches++;
     h->n_local = n_new; h->nnz = nnz_new; h->ntiles = 0;
     return APSS_OK;
   }
@@ -752,7 +766,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
       const int64_t n_rows = h->n_local;      // includes this batch when it was indexed (IWA:125-132)
       if (n_rows && batch_nnz) {
         CandArgs ca{};
-        ca.fwd_ptr = h->fwd_ptr.p; ca.fwd_idx = h->fwd_idx.p; ca.fwd_val = h->fwd_val.p; ca.fwd_skip = h->fwd_skip.p;
+        ca.ifw_ptr = h->ifw_ptr.p; ca.ifw = h->ifw.p;
         ca.row_ub = h->row_ub.p; ca.c_key = h->key.p; ca.qdir = h->qdir.p; ca.qi = reinterpret_cast<const uint2*>(h->bt_vals_out.p);
         ca.q_nrm = h->q_nrm.p; ca.q_key = h->custom_keys ? d_qkey : nullptr;
         ca.n_rows = n_rows; ca.q_local_base = q_local_base; ca.nq = n;

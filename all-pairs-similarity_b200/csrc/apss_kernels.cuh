@@ -141,9 +141,11 @@ __global__ void k_rank_keys(int n, const int32_t* __restrict__ q_ptr, const int3
 // multiply and add, like the oracle), mark the prefix, record |c_U| rounded up
 __global__ void k_prune_mark(int n, const int32_t* __restrict__ q_ptr, const double* __restrict__ q_val,
                              const unsigned long long* __restrict__ ranked, double lim,
-                             uint8_t* __restrict__ skip, float* __restrict__ cu, unsigned long long* counters) {
+                             uint8_t* __restrict__ skip, float* __restrict__ cu, int32_t* __restrict__ icnt,
+                             unsigned long long* counters) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n) return;
+  if (v > n) return;
+  if (v == n) { icnt[n] = 0; return; }
   const int a = q_ptr[v], b = q_ptr[v + 1];
   double s = 0.0; int k = a;
   for (; k < b; ++k) {
@@ -156,6 +158,22 @@ __global__ void k_prune_mark(int n, const int32_t* __restrict__ q_ptr, const dou
   if (k > a) atomicAdd(&counters[C_SKIPPED], (unsigned long long)(k - a));
   for (int j = k; j < b; ++j) skip[(int)ranked[j]] = 0;
   cu[v] = s > 0.0 ? __double2float_ru(sqrt(s) * (1.0 + 1e-9)) : 0.f;
+  icnt[v] = b - k;
+}
+
+// compact forward store of the INDEXED components only, (dim, fp32 weight), for the candidate-major kernel:
+// appended behind the current end, which lives on the device in ifw_ptr[n_old]
+__global__ void k_ifw_append(int n, int64_t n_old, const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim,
+                             const float* __restrict__ q_w, const uint8_t* __restrict__ skip, const int32_t* __restrict__ iptr,
+                             int64_t* __restrict__ ifw_ptr, uint2* __restrict__ ifw) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int64_t base = n_old ? ifw_ptr[n_old] : 0;
+  if (v == 0 && n_old == 0) ifw_ptr[0] = 0;
+  int64_t o = base + iptr[v];
+  for (int p = q_ptr[v]; p < q_ptr[v + 1]; ++p)
+    if (!skip[p]) ifw[o++] = make_uint2((unsigned)q_dim[p], __float_as_uint(q_w[p]));
+  ifw_ptr[n_old + v + 1] = base + iptr[v + 1];
 }
 
 // ------------------------------------------------------------------ K1: index append
@@ -1142,7 +1160,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
 //   estimate * (1 + guard band) + |q| * |c_unindexed|  >=  t.
 // Stored vectors whose lists are too long for the table are deferred to k_score_cand_heavy.
 struct CandArgs {
-  const int64_t* fwd_ptr; const int32_t* fwd_idx; const double* fwd_val; const uint8_t* fwd_skip;
+  const int64_t* ifw_ptr; const uint2* ifw;     // indexed components of the stored vectors: (dim, fp32 weight)
   const float* row_ub; const int64_t* c_key;
   const int32_t* qdir;       // [D + 1] offsets into qi
   const uint2* qi;           // (query, weight as fp32 bits), by dim, query ascending
@@ -1231,10 +1249,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) 
   };
   auto lookup = [&](long long j, long long fe, int& s, int& len, float& w) {
     s = 0; len = 0; w = 0.f;
-    if (j < fe && !a.fwd_skip[j]) {
-      const int d = a.fwd_idx[j];
-      s = __ldg(a.qdir + d); len = __ldg(a.qdir + d + 1) - s;
-      w = fmaxf((float)a.fwd_val[j], W_MIN);
+    if (j < fe) {
+      const uint2 f = __ldg(a.ifw + j);
+      s = __ldg(a.qdir + f.x); len = __ldg(a.qdir + f.x + 1) - s;
+      w = __uint_as_float(f.y);
     }
   };
   for (;;) {
@@ -1244,7 +1262,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) 
     if (base >= a.n_rows) break;
     const int nc = (int)min((long long)CAND_CHUNK, (long long)a.n_rows - base);
     long long myptr = 0;
-    if (lane <= nc) myptr = __ldg(a.fwd_ptr + base + lane);        // the chunk's row pointers, one load
+    if (lane <= nc) myptr = __ldg(a.ifw_ptr + base + lane);        // the chunk's row pointers, one load
     for (int ci = 0; ci < nc; ++ci) {
       const long long c = base + ci;
       const long long fa = __shfl_sync(FULL, myptr, ci), fe = __shfl_sync(FULL, myptr, ci + 1);
@@ -1277,7 +1295,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) 
         nf += __popc(bal); run += __shfl_sync(FULL, inc, 31);
       }
       if (!tail && nf <= CAND_FEAT) {
-        if (lane == 0) pre[nf] = (int)total;
+        for (int i = nf + lane; i < CAND_FEAT + 1; i += 32) pre[i] = 0x7fffffff;      // padding for the fixed-depth search
         __syncwarp();
         // flat walk: item t of the concatenated lists -> (list, position); iterations are independent
         for (int t0 = 0; t0 < (int)total; t0 += 64) {
@@ -1286,8 +1304,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) 
           for (int u = 0; u < 2; ++u) {
             t_[u] = t0 + u * 32 + lane; f_[u] = 0;
             if (t_[u] < (int)total) {
-              int lo = 0, hi = nf;                               // largest f with pre[f] <= t
-              while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= t_[u]) lo = mid; else hi = mid; }
+              int lo = 0;                                        // largest f with pre[f] <= t (pre[0] = 0, padded with INT_MAX)
+#pragma unroll
+              for (int st = CAND_FEAT / 2; st > 0; st >>= 1) lo += (pre[lo + st] <= t_[u]) ? st : 0;
               f_[u] = lo;
               x_[u] = __ldg(a.qi + fs[lo] + (t_[u] - pre[lo]));
             }
@@ -1338,7 +1357,7 @@ __global__ void __launch_bounds__(512, 1) k_score_cand_heavy(const CandArgs a, i
   unsigned long long n_post = 0, n_cand = 0;
   for (long long hidx = blockIdx.x; hidx < nh; hidx += gridDim.x) {
     const long long c = a.heavy[hidx];
-    const long long fa = __ldg(a.fwd_ptr + c), fe = __ldg(a.fwd_ptr + c + 1);
+    const long long fa = __ldg(a.ifw_ptr + c), fe = __ldg(a.ifw_ptr + c + 1);
     const float cu = __ldg(a.row_ub + c);
     const long long ckey = a.q_key ? __ldg(a.c_key + c) : 0;
     for (int q_lo = 0; q_lo < a.nq; q_lo += qc) {
@@ -1346,10 +1365,9 @@ __global__ void __launch_bounds__(512, 1) k_score_cand_heavy(const CandArgs a, i
       for (int i = tid; i < qc; i += blockDim.x) acc[i] = 0.f;
       __syncthreads();
       for (long long j = fa + warp; j < fe; j += nw) {            // one warp per component
-        if (a.fwd_skip[j]) continue;
-        const int d = a.fwd_idx[j];
-        const int s = __ldg(a.qdir + d), e = __ldg(a.qdir + d + 1);
-        const float w = fmaxf((float)a.fwd_val[j], W_MIN);
+        const uint2 f = __ldg(a.ifw + j);
+        const int s = __ldg(a.qdir + f.x), e = __ldg(a.qdir + f.x + 1);
+        const float w = __uint_as_float(f.y);
         if (q_lo == 0 && lane == 0) n_post += (unsigned)(e - s);
         for (int p = s + lane; p < e; p += 32) {
           const uint2 x = __ldg(a.qi + p);

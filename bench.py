@@ -369,7 +369,8 @@ def main():
     w1 = time.time()
     if args.profile_range:
         torch.cuda.profiler.stop()
-    launches = eng.stats()["kernel_launches"] - launches0
+    st = eng.stats()
+    launches = st["kernel_launches"] - launches0
     score_launches = K
     dt_value = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
     wall_value = w1 - w0
@@ -413,6 +414,49 @@ def main():
     w3 = time.time()
     dt_e2e = max_over_ranks(max(ev2.elapsed_time(ev3) * 1e-3, 0.0))
     wall_e2e = w3 - w2
+
+    # ------------------------------------------------------------ pruned leg: the same W + K batches of the value phase
+    # through a second engine with exact index reduction on.  Same pairs, far less work; its
+    # counters count the reduced work, so it is reported beside the parity-mode headline, not instead of it.
+    pruned = None
+    if not args.prune and not args.no_pruned_leg and not shard_gen:
+        eng.close()
+        del disp
+        eng2 = native.Index(D, t, device=local_rank, pruning=2, prune_alpha=args.prune_alpha,
+                            reserve_vectors=int((N + n_fresh * B) / world * 1.1) + 2 * B, reserve_nnz=int(total_nnz / world * 1.15) + (1 << 20))
+        disp2 = ShardDispatcher(eng2, device=dev)
+        for lo in range(0, N, B):
+            disp2.preload(*dev_rows(lo, min(N, lo + B)))
+        lib_stream2 = torch.cuda.ExternalStream(eng2.stream_ptr, device=dev)
+        p_tot = dict(cands=0, pairs=0, postings=0, score_ms=0.0, prefilter=0)
+        for i in range(W):
+            disp2.insert_batch(*(fresh_rows(i) if rank == 0 else (None, None, None)))
+        ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        w4 = time.time()
+        ev4.record(lib_stream2)
+        for i in range(W, W + K):
+            r = disp2.insert_batch(*(fresh_rows(i) if rank == 0 else (None, None, None)))
+            p_tot["cands"] += r.candidates_unique; p_tot["pairs"] += r.n_pairs; p_tot["postings"] += r.postings_visited
+            p_tot["score_ms"] += r.local.score_ms; p_tot["prefilter"] += r.local.n_prefilter
+        ev5.record(lib_stream2)
+        barrier()
+        w5 = time.time()
+        dt_pr = max_over_ranks(ev4.elapsed_time(ev5) * 1e-3)
+        st2 = eng2.stats()
+        pruned = {"kernel": "apss::k_score_cand (candidate-major, reduced index)", "ms_per_step": dt_pr / K * 1e3,
+                  "pairs_per_sec": p_tot["pairs"] / dt_pr, "pairs_identical_to_parity_run": p_tot["pairs"] == tot["pairs"],
+                  "speedup_vs_parity_run": dt_value / dt_pr,
+                  "equivalent_candidates_per_sec": tot["cands"] / dt_pr,
+                  "postings_visited_per_step": p_tot["postings"] / K, "candidates_touched_per_step": p_tot["cands"] / K,
+                  "verify_records_per_step": p_tot["prefilter"] / K, "score_kernel_ms_per_step": p_tot["score_ms"] / K,
+                  "unindexed_fraction": st2["n_unindexed"] / max(st2["n_unindexed"] + st2["n_postings"], 1),
+                  "work_reduction_postings": tot["postings"] / max(p_tot["postings"], 1),
+                  "note": "exact index reduction (include/apss.h `pruning` = 2): same batches as the value phase, same pair set; "
+                          "equivalent_candidates_per_sec = candidates of the parity run / time of this run"}
+        windows_extra = [(w4, w5)]
+    else:
+        windows_extra = []
     sampler.stop()
 
     if rank != 0:
@@ -422,7 +466,6 @@ def main():
 
     peak, peak_src = measured_peak()
     achieved = 8.0 * tot["local_postings"] / (tot["score_ms"] * 1e-3) / 1e9 if tot["score_ms"] > 0 else 0.0
-    st = eng.stats()
     traffic = known_traffic()
     line = {
         "metric": METRIC, "value": tot["cands"] / dt_value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -454,8 +497,10 @@ def main():
                              "from L2/shared memory across the queries of a batch, so DRAM traffic << algorithmic bytes "
                              "and achieved may exceed the HBM copy peak; the binding resource is on-chip (instruction issue / "
                              "shared-memory atomics), see the ncu figures"},
-        "clocks": sampler.summary([(w0, w1), (w2, w3)]),
+        "clocks": sampler.summary([(w0, w1), (w2, w3)] + windows_extra),
     }
+    if pruned is not None:
+        line["pruned"] = pruned
     if not args.no_cpu_baseline and not shard_gen:
         threads = host_threads()
         nq = args.cpu_queries or 2 * threads
