@@ -1269,7 +1269,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) 
       int s_[RC], len_[RC]; float w_[RC];
       unsigned total = 0;
 #pragma unroll
-      for (int it = 0; it < RC; ++it) { lookup(fa + it * 32 + lane, fe, s_[it], len_[it], w_[it]); total += (unsigned)len_[it]; }
+      for (int it = 0; it < RC; ++it) {
+        s_[it] = 0; len_[it] = 0; w_[it] = 0.f;
+        if (fa + it * 32 < fe) { lookup(fa + it * 32 + lane, fe, s_[it], len_[it], w_[it]); total += (unsigned)len_[it]; }
+      }
       const bool tail = fe - fa > RC * 32;
       if (tail) for (long long j = fa + RC * 32 + lane; j < fe; j += 32) { int s, len; float w; lookup(j, fe, s, len, w); total += (unsigned)len; }
 #pragma unroll
@@ -1286,6 +1289,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) 
       int nf = 0, run = 0;
 #pragma unroll
       for (int it = 0; it < RC; ++it) {
+        if (fa + it * 32 >= fe) break;                           // warp-uniform
         const unsigned bal = __ballot_sync(FULL, len_[it] > 0);
         int inc = len_[it];
 #pragma unroll
@@ -1389,10 +1393,12 @@ __global__ void __launch_bounds__(512, 1) k_score_cand_heavy(const CandArgs a, i
 
 // ------------------------------------------------------------------ K4: fp64 verify
 
-// One thread per pre-filter record: exact sparse dot of the query and the stored candidate in
-// ascending dimension order, fp64, multiply and add rounded separately (CU:98-117; bit-identical to
-// the CPU oracle).  Applies `sim >= similarityThreshold` (IWA:93) and, for the as-built semantics
-// R0, drops pairs whose shared dims all equal first(q) (IWA:89 + IWA:106-107).
+// One WARP per pre-filter record: exact sparse dot of the query and the stored candidate in ascending
+// dimension order, fp64, multiply and add rounded separately (CU:98-117; bit-identical to the CPU oracle).
+// The lanes look the query's dimensions up in the candidate's (binary search, 32 at a time); the matched
+// products are then added one by one in lane order = ascending dimension, the same chain on every lane.
+// Applies `sim >= similarityThreshold` (IWA:93) and, for the as-built semantics R0, drops pairs whose
+// shared dims all equal first(q) (IWA:89 + IWA:106-107).
 __global__ void k_verify(const unsigned long long* counters, unsigned long long pf_cap,
                          const int32_t* __restrict__ pf_q, const int32_t* __restrict__ pf_c,
                          const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim, const double* __restrict__ q_val,
@@ -1402,18 +1408,33 @@ __global__ void k_verify(const unsigned long long* counters, unsigned long long 
                          unsigned long long* wcounters) {
   unsigned long long n = counters[C_PF];
   if (n > pf_cap) n = pf_cap;
-  for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (unsigned long long)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long wid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long r = wid; r < n; r += nw) {
     const int q = pf_q[r], c = pf_c[r];
-    int i = q_ptr[q]; const int ie = q_ptr[q + 1];
-    int64_t j = fwd_ptr[c]; const int64_t je = fwd_ptr[c + 1];
+    const int i0 = q_ptr[q], ie = q_ptr[q + 1];
+    const int64_t j0 = fwd_ptr[c], je = fwd_ptr[c + 1];
     const int fd = (sem_r0 && first_dim) ? first_dim[q] : -1;
     double s = 0.0; int nonfirst = 0;
-    while (i < ie && j < je) {
-      const int di = q_dim[i], dj = fwd_idx[j];
-      if (di < dj) ++i; else if (di > dj) ++j;
-      else { s = __dadd_rn(s, __dmul_rn(fwd_val[j], q_val[i])); nonfirst += (di != fd); ++i; ++j; }
+    for (int ib = i0; ib < ie; ib += 32) {
+      const int i = ib + lane;
+      double p = 0.0; bool hit = false;
+      if (i < ie) {
+        const int di = q_dim[i];
+        int64_t lo = j0, hi = je;                    // first j with fwd_idx[j] >= di
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (fwd_idx[mid] < di) lo = mid + 1; else hi = mid; }
+        if (lo < je && fwd_idx[lo] == di) { hit = true; p = __dmul_rn(fwd_val[lo], q_val[i]); nonfirst += (di != fd); }
+      }
+      unsigned m = __ballot_sync(FULL, hit);
+      while (m) {                                    // ascending lane = ascending dimension
+        const int src = __ffs(m) - 1; m &= m - 1;
+        s = __dadd_rn(s, __shfl_sync(FULL, p, src));
+      }
     }
-    if (s >= thr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nonfirst += __shfl_xor_sync(FULL, nonfirst, o);
+    if (lane == 0 && s >= thr) {
       atomicAdd(&wcounters[C_R1], 1ULL);
       if (!sem_r0 || nonfirst > 0) {
         const unsigned long long slot = atomicAdd(&wcounters[C_FINAL], 1ULL);

@@ -87,7 +87,8 @@ class GpuIndexingWorkerActor:
         self._dups = False
         if engine is None:                        # the product path: CUDA or nothing
             engine = native.Index(self.vectorDim, self.similarityThreshold, self.indexThreshold, device=device,
-                                  semantics=native.SEM_R0 if self.as_built else native.SEM_R1)
+                                  semantics=native.SEM_R0 if self.as_built else native.SEM_R1,
+                                  pruning=int(conf_get(conf, "cpslab.allpair.gpu.pruning", 0)))   # 0 parity counters, 2 exact index reduction
         self.engine = engine
 
     # -- IWA:122-148

@@ -29,12 +29,13 @@ static void throw_rt(JNIEnv *env, apss_handle *h, int32_t rc) {
 }
 
 JNIEXPORT jlong JNICALL Java_cpslab_gpu_ApssNative_create(JNIEnv *env, jclass cls, jint dim, jdouble sim_thr,
-                                                          jdouble idx_thr, jint device, jint semantics) {
+                                                          jdouble idx_thr, jint device, jint semantics, jint pruning) {
   apss_config cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.struct_size = (int32_t)sizeof cfg;
   cfg.dim = dim; cfg.similarity_threshold = sim_thr; cfg.index_threshold = idx_thr;
   cfg.device = device; cfg.semantics = semantics;
+  cfg.pruning = pruning;   /* 0 parity counters, 2 exact index reduction (same pairs, far less work); see include/apss.h */
   apss_handle *h = NULL;
   int32_t rc = apss_create(&cfg, &h);
   if (rc != APSS_OK) { throw_rt(env, NULL, rc); return 0; }

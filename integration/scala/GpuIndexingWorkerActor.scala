@@ -29,7 +29,7 @@ package object gpu {}
 
 object ApssNative {
   System.loadLibrary("apss_jni")
-  @native def create(dim: Int, simThr: Double, idxThr: Double, device: Int, semantics: Int): Long
+  @native def create(dim: Int, simThr: Double, idxThr: Double, device: Int, semantics: Int, pruning: Int): Long
   @native def destroy(h: Long): Unit
   @native def insertBatch(h: Long, indptr: Array[Long], indices: Array[Int], values: Array[Double],
                           extKeys: Array[Long], firstDim: Array[Int], flags: Int): Array[Long]
@@ -48,6 +48,8 @@ private class GpuIndexingWorkerActor(conf: Config) extends Actor {
   private val indexThreshold =
     if (conf.hasPath("cpslab.allpair.indexThreshold")) conf.getDouble("cpslab.allpair.indexThreshold") else 0.0
   private val device = if (conf.hasPath("cpslab.allpair.gpu.device")) conf.getInt("cpslab.allpair.gpu.device") else 0
+  // 0 = every posting visited (counters as in the reference); 2 = exact index reduction, same pairs (include/apss.h)
+  private val pruning = if (conf.hasPath("cpslab.allpair.gpu.pruning")) conf.getInt("cpslab.allpair.gpu.pruning") else 0
 
   val writeBuffer = new mutable.HashMap[String, mutable.HashMap[String, Double]]
   var replyTo: Option[ActorSelection] = None
@@ -56,7 +58,7 @@ private class GpuIndexingWorkerActor(conf: Config) extends Actor {
   private val ids = new ArrayBuffer[String]                       // internal id -> caller's String id
   private val firstOf = new mutable.HashMap[String, Long]         // String id -> key (first internal id)
   private var dups = false
-  private val handle = ApssNative.create(vectorDim, similarityThreshold, indexThreshold, device, 0 /* R1 */)
+  private val handle = ApssNative.create(vectorDim, similarityThreshold, indexThreshold, device, 0 /* R1 */, pruning)
 
   if (expDuration > 0) context.setReceiveTimeout(expDuration milliseconds)   // IWA:37-39
 

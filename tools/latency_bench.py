@@ -33,6 +33,7 @@ ap.add_argument("--messages", type=int, default=500)
 ap.add_argument("--bulk", action="store_true")
 ap.add_argument("--out", default="")
 ap.add_argument("--ccweb", default="")
+ap.add_argument("--prune", type=int, default=0, help="cpslab.allpair.gpu.pruning: 0 off, 2 exact index reduction")
 ap.add_argument("--threshold", type=float, default=0.0)
 args = ap.parse_args()
 cfg = synth.CONFIGS[args.config]
@@ -54,7 +55,8 @@ else:
     vec = lambda i: M.SparkSparseVector(D, ix[ip[i]:ip[i + 1]], v[ip[i]:ip[i + 1]])
 
 conf = {"cpslab.allpair.similarityThreshold": t, "cpslab.allpair.outputIODuration": 0, "cpslab.allpair.benchmark.expDuration": 30000,
-        "cpslab.allpair.vectorDim": D, "cpslab.allpair.indexThreshold": 0.0, "cpslab.allpair.ioTriggerPeriod": 0}
+        "cpslab.allpair.vectorDim": D, "cpslab.allpair.indexThreshold": 0.0, "cpslab.allpair.ioTriggerPeriod": 0,
+        "cpslab.allpair.gpu.pruning": args.prune}
 outputs = []
 worker = GpuIndexingWorkerActor(conf, replyTo=outputs.append)
 system = LocalActorSystem()
@@ -88,7 +90,7 @@ for k in range(args.messages):
     lat.append((time.perf_counter() - start) * 1e3)
     neighbours += sum(len(m) for m in out.output.values())
 lat = np.array(lat)
-res = {"config": args.ccweb or args.config, "index_vectors": N, "messages": args.messages, "warmup_s": warm_s,
+res = {"config": args.ccweb or args.config, "pruning": args.prune, "index_vectors": N, "messages": args.messages, "warmup_s": warm_s,
        "warmup_mode": "bulk batches of 4096" if args.bulk else "one vector per message",
        "warmup_ms_per_message": (float(np.mean(warm_lat)) if warm_lat else None),
        "avg_ms": float(lat.mean()), "max_ms": float(lat.max()), "min_ms": float(lat.min()),
