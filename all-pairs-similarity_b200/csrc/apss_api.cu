@@ -256,8 +256,17 @@ static cudaError_t launch_dense_t(apss_handle* h, const ScoreArgs& a, const Bloc
   return cudaGetLastError();
 }
 
+static cudaError_t launch_dense_pruned(apss_handle* h, const ScoreArgs& a, const BlockArgs& b, const DenseTiles& d, bool dup) {
+  auto kern = dup ? k_score_dense<16, 16, 4, true, true> : k_score_dense<16, 16, 4, false, true>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(h->smem_bytes, h->smem_optin - 1024));
+  if (e != cudaSuccess) return e;
+  kern<<<h->sm_count * h->ctas_per_sm, 16 * 32, h->smem_bytes, h->stream>>>(a, b, d);
+  return cudaGetLastError();
+}
+
 static cudaError_t launch_dense(apss_handle* h, const ScoreArgs& a, const BlockArgs& b, const DenseTiles& d, bool dup) {
   const int key = h->QB * 10000 + h->WARPS * 100 + h->COLS;
+  if (h->prune_mode == 1) return key == 161604 ? launch_dense_pruned(h, a, b, d, dup) : cudaErrorInvalidValue;
   switch (key) {
     case 321602: return launch_dense_t<32, 16, 2>(h, a, b, d, dup);
     case 321202: return launch_dense_t<32, 12, 2>(h, a, b, d, dup);
@@ -391,6 +400,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (cfg->pruning) {
     if ((cfg->pruning != 1 && cfg->pruning != 2) || algo != 3) return bail(APSS_E_INVALID);   // only the default scoring kernel applies the bound
     h->prune_mode = cfg->pruning;
+    if (cfg->pruning == 1 && (QB != 16 || warps != 16 || h->COLS != 4)) return bail(APSS_E_INVALID);   // tile kernel: default shape only
     { const char* cw = getenv("APSS_CAND_WARPS"); if (cw && (atoi(cw) == 16 || atoi(cw) == 24)) h->cand_warps = atoi(cw); }
     const double alpha = cfg->prune_alpha == 0.0 ? 0.8 : cfg->prune_alpha;
     const double qn = cfg->max_query_norm == 0.0 ? 1.0 : cfg->max_query_norm;

@@ -835,7 +835,7 @@ __device__ __forceinline__ void process_pieces(unsigned* acc, const int4* segs, 
 //   phase 3  epilogue: count candidates (non-zero halves), emit those >= thr by warp-aggregated
 //            compaction, clear
 // bt entries for this kernel hold (row * CR / 2, weight * 2^F).
-template <int QB, int WARPS, int COLS, bool DUPKEYS>
+template <int QB, int WARPS, int COLS, bool DUPKEYS, bool PRUNED = false>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dense(const ScoreArgs a, const BlockArgs b, const DenseTiles dt) {
   extern __shared__ __align__(16) unsigned smem_u[];
   const int CR = a.CR;
@@ -861,12 +861,10 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
   const unsigned thr_lo = b.thr_int;
   const unsigned thr_hi = thr_lo << 16;      // high half >= thr  <=>  word >= thr << 16
 
-  unsigned long long nxt = 0;                // thread 0: the next work item, fetched while the current one runs
-  if (tid == 0) nxt = atomicAdd(&a.counters[C_WORK], 1ULL);
   for (;;) {
     __syncthreads();
     PHASE_MARK(5);
-    if (tid == 0) { s_item = nxt; s_nseg = 0; s_segvalid = a.seg_cap - (a.seg_cap * 3 >> 3); s_nshort = 0; s_shortvalid = a.seg_cap * 3 >> 3; s_ndense = 0; s_next = 0; s_next2 = 0; }
+    if (tid == 0) { s_item = atomicAdd(&a.counters[C_WORK], 1ULL); s_nseg = 0; s_segvalid = a.seg_cap - (a.seg_cap * 3 >> 3); s_nshort = 0; s_shortvalid = a.seg_cap * 3 >> 3; s_ndense = 0; s_next = 0; s_next2 = 0; }
     __syncthreads();
     const unsigned long long item = s_item;
     if (item >= a.total_items) break;
@@ -954,7 +952,6 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
     }
     __syncthreads();
     PHASE_MARK(1);
-    if (tid == 0) nxt = atomicAdd(&a.counters[C_WORK], 1ULL);      // consumed at the top of the next iteration
     const int nd = s_ndense;
     const int nlong = min(s_nseg, s_segvalid), nshort = min(s_nshort, s_shortvalid);
     // pad the dense list to a multiple of 4 with entries whose query weights stay zero (Wq is cleared per item)
@@ -1043,10 +1040,10 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
         const long long selfc = a.q_local_base + q0 + tid - c0;
         if (selfc >= 0 && selfc < CR) acc[tid * RW + (int)(selfc >> 1)] &= (selfc & 1) ? 0x0000ffffu : 0xffff0000u;
       }
-      if (a.row_ub && tid == 0) s_nseg = 0;                       // reused as the cursor of the touched-word queue
+      if (PRUNED && tid == 0) s_nseg = 0;                       // reused as the cursor of the touched-word queue
       __syncthreads();
       PHASE_MARK(7);
-      if (a.row_ub) {
+      if (PRUNED) {
         // Reduced index: every touched candidate has its own threshold (thr - bound of its un-indexed part), so
         // all touched words need global loads.  Pass 1 scans and clears the accumulators and queues the non-zero
         // words (the segment queue is free now); pass 2 tests them one per thread, latencies in parallel.
