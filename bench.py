@@ -444,6 +444,26 @@ def main():
         w5 = time.time()
         dt_pr = max_over_ranks(ev4.elapsed_time(ev5) * 1e-3)
         st2 = eng2.stats()
+        # the same K host batches as the e2e phase above, through host buffers (H2D and result fetch inside the call)
+        pe = None
+        if world == 1:
+            ip, ix, v = host_batches[0]
+            eng2.insert_batch(ip.numpy(), ix.numpy(), v.numpy()); eng2.fetch_pairs(out_q.numpy(), out_c.numpy(), out_s.numpy())
+            torch.cuda.synchronize()
+            ev6, ev7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w6 = time.time()
+            ev6.record(lib_stream2)
+            pe_pairs = 0
+            for k in range(1, 1 + K):
+                ip, ix, v = host_batches[k]
+                r = eng2.insert_batch(ip.numpy(), ix.numpy(), v.numpy())
+                eng2.fetch_pairs(out_q.numpy(), out_c.numpy(), out_s.numpy())
+                pe_pairs += r.n_pairs
+            ev7.record(lib_stream2)
+            torch.cuda.synchronize()
+            w7 = time.time()
+            pe = {"ms_per_step": ev6.elapsed_time(ev7) / K, "wall_ms_per_step": (w7 - w6) * 1e3 / K,
+                  "pairs_per_sec": pe_pairs / (ev6.elapsed_time(ev7) * 1e-3), "pairs_identical_to_parity_run": pe_pairs == e_p}
         pruned = {"kernel": "apss::k_score_cand (candidate-major, reduced index)", "ms_per_step": dt_pr / K * 1e3,
                   "pairs_per_sec": p_tot["pairs"] / dt_pr, "pairs_identical_to_parity_run": p_tot["pairs"] == tot["pairs"],
                   "speedup_vs_parity_run": dt_value / dt_pr,
@@ -452,6 +472,7 @@ def main():
                   "verify_records_per_step": p_tot["prefilter"] / K, "score_kernel_ms_per_step": p_tot["score_ms"] / K,
                   "unindexed_fraction": st2["n_unindexed"] / max(st2["n_unindexed"] + st2["n_postings"], 1),
                   "work_reduction_postings": tot["postings"] / max(p_tot["postings"], 1),
+                  "e2e": pe,
                   "note": "exact index reduction (include/apss.h `pruning` = 2): same batches as the value phase, same pair set; "
                           "equivalent_candidates_per_sec = candidates of the parity run / time of this run"}
         windows_extra = [(w4, w5)]
