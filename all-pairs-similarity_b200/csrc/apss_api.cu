@@ -290,7 +290,7 @@ static int32_t build_query_index(apss_handle* h, int32_t n, int32_t batch_nnz) {
   CK(h->bt_vals_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->bt_vals_out.reserve(std::max(batch_nnz, 1), 0, s));
   CK(h->qdir.reserve((size_t)D + 1, 0, s));
   if (batch_nnz) {
-    k_qi_emit<<<cdiv(n, 128), 128, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->q_w.p, h->bt_keys_in.p, h->bt_vals_in.p);
+    k_qi_emit<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->q_w.p, h->bt_keys_in.p, h->bt_vals_in.p);
     CK(cudaGetLastError());
     size_t tb = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits, s));
@@ -476,7 +476,7 @@ static int32_t prune_select(apss_handle* h, int32_t n, int32_t batch_nnz) {
   if (batch_nnz) {
     k_df_update<<<cdiv(batch_nnz, 256), 256, 0, s>>>(batch_nnz, h->q_dim.p, h->df.p);
     CK(cudaGetLastError());
-    k_rank_keys<<<cdiv(n, 128), 128, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->df.p, h->pr_keys_in.p, h->pr_vals_in.p);
+    k_rank_keys<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->df.p, h->pr_keys_in.p, h->pr_vals_in.p);
     CK(cudaGetLastError());
     int rowbits = 1; while ((1LL << rowbits) < n) ++rowbits;
     size_t tb = 0;
@@ -485,7 +485,7 @@ static int32_t prune_select(apss_handle* h, int32_t n, int32_t batch_nnz) {
     CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->pr_keys_in.p, h->pr_keys_out.p, h->pr_vals_in.p, h->pr_vals_out.p, batch_nnz, 0, 31 + rowbits, s));
     h->kernel_launches += 4;
   }
-  k_prune_mark<<<cdiv(n + 1, 128), 128, 0, s>>>(n, h->q_ptr.p, h->q_val.p, h->pr_vals_out.p, h->prune_lim, h->q_skip.p, h->q_cu.p, h->q_icnt.p, h->d_counters);
+  k_prune_mark<<<cdiv(((int64_t)n + 1) * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_val.p, h->pr_vals_out.p, h->prune_lim, h->q_skip.p, h->q_cu.p, h->q_icnt.p, h->d_counters);
   CK(cudaGetLastError()); h->kernel_launches++;
   if (h->prune_mode == 2) {
     size_t tb = 0;
@@ -522,7 +522,7 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
     // indexed components so far: known on the host up to the previous batch; this batch adds at most batch_nnz
     const int64_t ifw_old = nnz_old - h->tot_skipped;
     CK(h->ifw_ptr.reserve(n_new + 1, n_old ? n_old + 1 : 0, s)); CK(h->ifw.reserve(std::max<int64_t>(ifw_old + batch_nnz, 1), ifw_old, s));
-    k_ifw_append<<<cdiv(n, 128), 128, 0, s>>>(n, n_old, h->q_ptr.p, h->q_dim.p, h->q_w.p, h->q_skip.p, h->q_iptr.p, h->ifw_ptr.p, h->ifw.p);
+    k_ifw_append<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, n_old, h->q_ptr.p, h->q_dim.p, h->q_w.p, h->q_skip.p, h->q_iptr.p, h->ifw_ptr.p, h->ifw.p);
     CK(cudaGetLastError()); h->kernel_launches++;
     h->n_local = n_new; h->nnz = nnz_new; h->ntiles = 0;
     return APSS_OK;
@@ -679,7 +679,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   if (h->prune) CK(h->q_nrm.reserve(n, 0, s));
   CK(cudaMemsetAsync(h->d_counters, 0, C_COUNT * sizeof(unsigned long long), s));
   const double admit_thr = (flags & APSS_BATCH_SKIP_ADMIT) ? -INFINITY : h->cfg.similarity_threshold;
-  k_prefilter_count<<<cdiv(n + 1, 128), 128, 0, s>>>(n, d_ptr, d_idx, d_val, D, h->maxw.p, admit_thr, h->cfg.index_threshold,
+  k_prefilter_count<<<cdiv(((int64_t)n + 1) * 32, 256), 256, 0, s>>>(n, d_ptr, d_idx, d_val, D, h->maxw.p, admit_thr, h->cfg.index_threshold,
                                                      h->q_cnt.p, h->q_status.p, h->prune ? h->q_nrm.p : nullptr, h->d_counters);
   CK(cudaGetLastError());
   size_t tmp = 0;
@@ -707,7 +707,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     if (sq > h->max_sq) h->max_sq = sq;
   }
   CK(h->q_dim.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_val.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_w.reserve(std::max(batch_nnz, 1), 0, s));
-  k_prefilter_write<<<cdiv(n, 128), 128, 0, s>>>(n, d_ptr, d_idx, d_val, h->cfg.index_threshold, h->q_status.p, h->q_ptr.p, h->q_dim.p, h->q_val.p, h->q_w.p);
+  k_prefilter_write<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, d_ptr, d_idx, d_val, h->cfg.index_threshold, h->q_status.p, h->q_ptr.p, h->q_dim.p, h->q_val.p, h->q_w.p);
   CK(cudaGetLastError()); h->kernel_launches++;
   if (d_keys) h->custom_keys = true;
 

@@ -59,28 +59,43 @@ __device__ __forceinline__ uint2 ld_stream(const uint2* p) {
 
 // ------------------------------------------------------------------ K5: admission + value prune
 
-// One thread per input vector.  Validates (SparseVector.scala:96-108: strictly increasing indices,
+// One WARP per input vector.  Validates (SparseVector.scala:96-108: strictly increasing indices,
 // all < size), evaluates the admission predicate of EPA:81-93 on the UN-pruned vector in ascending
-// index order (fp64, separate multiply and add) and counts the components that survive
-// `value > indexThreshold` (strict; WWA:192).
+// index order (fp64, separate multiply and add: the lanes load 32 components at a time, the sum is
+// then chained through them in lane order, the same chain on every lane) and counts the components
+// that survive `value > indexThreshold` (strict; WWA:192).
 __global__ void k_prefilter_count(int n, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                                   const double* __restrict__ val, int D, const double* __restrict__ maxw,
                                   double sim_thr, double idx_thr, int32_t* __restrict__ cnt,
                                   uint8_t* __restrict__ status, float* __restrict__ q_nrm, unsigned long long* counters) {
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (v > n) return;
-  if (v == n) { cnt[n] = 0; return; }
-  int64_t a = ptr[v], b = ptr[v + 1];
-  if (b < a || (v == 0 && a != 0)) { atomicMax(&counters[C_ERR], 2ULL); cnt[v] = 0; status[v] = 0; return; }
+  if (v == n) { if (lane == 0) cnt[n] = 0; return; }
+  const int64_t a = ptr[v], b = ptr[v + 1];
+  if (b < a || (v == 0 && a != 0)) { if (lane == 0) { atomicMax(&counters[C_ERR], 2ULL); cnt[v] = 0; status[v] = 0; } return; }
   double s = 0.0, sq = 0.0; int kept = 0; int prev = -1; bool bad = false;
-  for (int64_t p = a; p < b; ++p) {
-    int d = idx[p]; double x = val[p];
-    if (d <= prev || d >= D) { bad = true; break; }
-    prev = d;
-    double mw = maxw ? maxw[d] : 1.0;
-    s = __dadd_rn(s, __dmul_rn(mw, x));
-    if (x > idx_thr) { ++kept; sq = fma(x, x, sq); }
+  for (int64_t p0 = a; p0 < b; p0 += 32) {
+    const int64_t p = p0 + lane;
+    const bool on = p < b;
+    const int d = on ? idx[p] : 0x7fffffff;
+    const double x = on ? val[p] : 0.0;
+    int before = __shfl_up_sync(FULL, d, 1);
+    if (lane == 0) before = prev;
+    bad |= __any_sync(FULL, on && (d <= before || d >= D));
+    if (bad) break;
+    prev = __shfl_sync(FULL, d, 31);
+    const bool keep = on && x > idx_thr;
+    kept += __popc(__ballot_sync(FULL, keep));
+    const double t = on ? __dmul_rn((maxw ? maxw[d] : 1.0), x) : 0.0;
+    const int cntl = (int)min((int64_t)32, b - p0);
+    for (int k = 0; k < cntl; ++k) {
+      s = __dadd_rn(s, __shfl_sync(FULL, t, k));
+      const double xk = __shfl_sync(FULL, x, k);
+      if (xk > idx_thr) sq = fma(xk, xk, sq);
+    }
   }
+  if (lane) return;
   if (bad) { atomicMax(&counters[C_ERR], 3ULL); cnt[v] = 0; status[v] = 0; return; }
   uint8_t st;
   if (!(s >= sim_thr)) { st = 0; kept = 0; atomicAdd(&counters[C_NREJ], 1ULL); }
@@ -94,16 +109,23 @@ __global__ void k_prefilter_count(int n, const int64_t* __restrict__ ptr, const 
   if (q_nrm) q_nrm[v] = st == 2 ? __double2float_ru(sqrt(sq) * (1.0 + 1e-9)) : 0.f;
 }
 
+// warp per vector: the surviving components, compacted in order
 __global__ void k_prefilter_write(int n, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                                   const double* __restrict__ val, double idx_thr, const uint8_t* __restrict__ status,
                                   const int32_t* __restrict__ q_ptr, int32_t* __restrict__ q_dim,
                                   double* __restrict__ q_val, float* __restrict__ q_w) {
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (v >= n || status[v] != 2) return;
   int o = q_ptr[v];
-  for (int64_t p = ptr[v]; p < ptr[v + 1]; ++p) {
-    double x = val[p];
-    if (x > idx_thr) { q_dim[o] = idx[p]; q_val[o] = x; q_w[o] = fmaxf((float)x, W_MIN); ++o; }
+  const int64_t a = ptr[v], b = ptr[v + 1];
+  for (int64_t p0 = a; p0 < b; p0 += 32) {
+    const int64_t p = p0 + lane;
+    const double x = p < b ? val[p] : 0.0;
+    const bool keep = p < b && x > idx_thr;
+    const unsigned bal = __ballot_sync(FULL, keep);
+    if (keep) { const int k = o + __popc(bal & ((1u << lane) - 1u)); q_dim[k] = idx[p]; q_val[k] = x; q_w[k] = fmaxf((float)x, W_MIN); }
+    o += __popc(bal);
   }
 }
 
@@ -129,34 +151,46 @@ __global__ void k_df_update(int nnz, const int32_t* __restrict__ q_dim, int32_t*
 // sort key (row, max_df - df): a stable sort keeps ascending dims among equal frequencies
 __global__ void k_rank_keys(int n, const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim,
                             const int32_t* __restrict__ df, unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (v >= n) return;
-  for (int p = q_ptr[v]; p < q_ptr[v + 1]; ++p) {
+  for (int p = q_ptr[v] + (threadIdx.x & 31); p < q_ptr[v + 1]; p += 32) {      // warp per vector
     keys[p] = ((unsigned long long)(unsigned)v << 31) | (unsigned long long)(0x7fffffff - df[q_dim[p]]);
     vals[p] = (unsigned long long)(unsigned)p;
   }
 }
 
-// one thread per vector: walk its components in rank order, fp64 running sum of squares (separate
-// multiply and add, like the oracle), mark the prefix, record |c_U| rounded up
+// one warp per vector: walk its components in rank order, fp64 running sum of squares (separate multiply and
+// add, like the oracle; 32 components loaded at a time, the sum chained through them in lane order), mark the
+// prefix, record |c_U| rounded up and the number of indexed components
 __global__ void k_prune_mark(int n, const int32_t* __restrict__ q_ptr, const double* __restrict__ q_val,
                              const unsigned long long* __restrict__ ranked, double lim,
                              uint8_t* __restrict__ skip, float* __restrict__ cu, int32_t* __restrict__ icnt,
                              unsigned long long* counters) {
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (v > n) return;
-  if (v == n) { icnt[n] = 0; return; }
+  if (v == n) { if (lane == 0) icnt[n] = 0; return; }
   const int a = q_ptr[v], b = q_ptr[v + 1];
-  double s = 0.0; int k = a;
-  for (; k < b; ++k) {
-    const double x = q_val[(int)ranked[k]];
-    const double s2 = __dadd_rn(s, __dmul_rn(x, x));
-    if (!(s2 <= lim)) break;
-    s = s2;
-    skip[(int)ranked[k]] = 1;
+  double s = 0.0; int k = a; bool open = true;          // k: first component (in rank order) that stays indexed
+  for (int p0 = a; p0 < b; p0 += 32) {
+    const int p = p0 + lane;
+    const int pos = p < b ? (int)ranked[p] : -1;
+    const double x = p < b ? q_val[pos] : 0.0;
+    const double xx = __dmul_rn(x, x);
+    int nskip = 0;
+    if (open) {
+      const int cntl = min(32, b - p0);
+      for (int j = 0; j < cntl; ++j) {
+        const double s2 = __dadd_rn(s, __shfl_sync(FULL, xx, j));
+        if (!(s2 <= lim)) { open = false; break; }
+        s = s2; ++nskip;
+      }
+      k = p0 + nskip;
+    }
+    if (p < b) skip[pos] = lane < nskip ? 1 : 0;
   }
+  if (lane) return;
   if (k > a) atomicAdd(&counters[C_SKIPPED], (unsigned long long)(k - a));
-  for (int j = k; j < b; ++j) skip[(int)ranked[j]] = 0;
   cu[v] = s > 0.0 ? __double2float_ru(sqrt(s) * (1.0 + 1e-9)) : 0.f;
   icnt[v] = b - k;
 }
@@ -166,14 +200,20 @@ __global__ void k_prune_mark(int n, const int32_t* __restrict__ q_ptr, const dou
 __global__ void k_ifw_append(int n, int64_t n_old, const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim,
                              const float* __restrict__ q_w, const uint8_t* __restrict__ skip, const int32_t* __restrict__ iptr,
                              int64_t* __restrict__ ifw_ptr, uint2* __restrict__ ifw) {
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (v >= n) return;
   const int64_t base = n_old ? ifw_ptr[n_old] : 0;
-  if (v == 0 && n_old == 0) ifw_ptr[0] = 0;
+  if (v == 0 && n_old == 0 && lane == 0) ifw_ptr[0] = 0;
   int64_t o = base + iptr[v];
-  for (int p = q_ptr[v]; p < q_ptr[v + 1]; ++p)
-    if (!skip[p]) ifw[o++] = make_uint2((unsigned)q_dim[p], __float_as_uint(q_w[p]));
-  ifw_ptr[n_old + v + 1] = base + iptr[v + 1];
+  for (int p0 = q_ptr[v]; p0 < q_ptr[v + 1]; p0 += 32) {       // warp per vector, compaction in order
+    const int p = p0 + lane;
+    const bool keep = p < q_ptr[v + 1] && !skip[p];
+    const unsigned bal = __ballot_sync(FULL, keep);
+    if (keep) ifw[o + __popc(bal & ((1u << lane) - 1u))] = make_uint2((unsigned)q_dim[p], __float_as_uint(q_w[p]));
+    o += __popc(bal);
+  }
+  if (lane == 0) ifw_ptr[n_old + v + 1] = base + iptr[v + 1];
 }
 
 // ------------------------------------------------------------------ K1: index append
@@ -1174,9 +1214,9 @@ struct CandArgs {
 
 __global__ void k_qi_emit(int n, const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim, const float* __restrict__ q_w,
                           unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (v >= n) return;
-  for (int p = q_ptr[v]; p < q_ptr[v + 1]; ++p) {
+  for (int p = q_ptr[v] + (threadIdx.x & 31); p < q_ptr[v + 1]; p += 32) {      // warp per vector
     keys[p] = (unsigned long long)(unsigned)q_dim[p];
     vals[p] = ((unsigned long long)__float_as_uint(q_w[p]) << 32) | (unsigned)v;      // uint2{x = query, y = weight}
   }
