@@ -170,6 +170,8 @@ struct apss_handle {
   bool prune = false; double prune_lim = 0.0, max_qnorm = 1.0;
   int prune_mode = 0;        // 1: tile kernels on the reduced index, 2: candidate-major kernel (no tiles are built)
   int cand_warps = 24;
+  double cand_rate = -1.0;   // query-list entries met per stored vector per query, from the previous batch (-1: unknown)
+  int cand_slices_env = 0;
   DevBuf<int32_t> qdir; VmBuf<int32_t> heavy;
   VmBuf<int64_t> ifw_ptr; VmBuf<uint2> ifw; DevBuf<int32_t> q_icnt, q_iptr;   // compact store of the indexed components
   DevBuf<int32_t> df; VmBuf<uint8_t> fwd_skip; VmBuf<float> row_ub;
@@ -282,23 +284,24 @@ static cudaError_t launch_dense(apss_handle* h, const ScoreArgs& a, const BlockA
 
 // Candidate-major scoring on the reduced index: invert the batch (dim -> (query, weight) lists), then stream the
 // stored vectors (k_score_cand) and finish the deferred ones (k_score_cand_heavy).
-static int32_t build_query_index(apss_handle* h, int32_t n, int32_t batch_nnz) {
+static int32_t build_query_index(apss_handle* h, int32_t n, int32_t batch_nnz, int slices, int qsub) {
   cudaStream_t s = h->stream;
   const int D = h->cfg.dim;
-  int dimbits = 1; while ((1LL << dimbits) < (int64_t)D) ++dimbits;
+  int dimbits = 1; while ((1LL << dimbits) < (int64_t)D + 1) ++dimbits;
+  int sbits = 0; while ((1 << sbits) < slices) ++sbits;
   CK(h->bt_keys_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->bt_keys_out.reserve(std::max(batch_nnz, 1), 0, s));
   CK(h->bt_vals_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->bt_vals_out.reserve(std::max(batch_nnz, 1), 0, s));
-  CK(h->qdir.reserve((size_t)D + 1, 0, s));
+  CK(h->qdir.reserve(((size_t)D + 1) * slices, 0, s));
   if (batch_nnz) {
-    k_qi_emit<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->q_w.p, h->bt_keys_in.p, h->bt_vals_in.p);
+    k_qi_emit<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->q_w.p, qsub, dimbits, h->bt_keys_in.p, h->bt_vals_in.p);
     CK(cudaGetLastError());
     size_t tb = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits, s));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits + sbits, s));
     CK(h->cub_tmp.reserve(tb, 0, s));
-    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits, s));
+    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->bt_keys_in.p, h->bt_keys_out.p, h->bt_vals_in.p, h->bt_vals_out.p, batch_nnz, 0, dimbits + sbits, s));
     h->kernel_launches += 3;
   }
-  k_qdir<<<cdiv((int64_t)D + 1, 256), 256, 0, s>>>(h->bt_keys_out.p, batch_nnz, D, h->qdir.p);
+  k_qdir<<<cdiv(((int64_t)D + 1) * slices, 256), 256, 0, s>>>(h->bt_keys_out.p, batch_nnz, D, dimbits, slices, h->qdir.p);
   CK(cudaGetLastError()); h->kernel_launches++;
   return APSS_OK;
 }
@@ -402,6 +405,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
     h->prune_mode = cfg->pruning;
     if (cfg->pruning == 1 && (QB != 16 || warps != 16 || h->COLS != 4)) return bail(APSS_E_INVALID);   // tile kernel: default shape only
     { const char* cw = getenv("APSS_CAND_WARPS"); if (cw && (atoi(cw) == 16 || atoi(cw) == 24)) h->cand_warps = atoi(cw); }
+    { const char* cs = getenv("APSS_CAND_SLICES"); if (cs && atoi(cs) >= 1 && atoi(cs) <= 256) h->cand_slices_env = atoi(cs); }
     const double alpha = cfg->prune_alpha == 0.0 ? 0.8 : cfg->prune_alpha;
     const double qn = cfg->max_query_norm == 0.0 ? 1.0 : cfg->max_query_norm;
     if (!(alpha > 0.0 && alpha < 1.0) || !(qn > 0.0) || !std::isfinite(qn)) return bail(APSS_E_INVALID);
@@ -750,8 +754,17 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   // ---- query-block transposition for the block kernels: (block, dim)-sorted (row, scaled weight) lists
   BlockArgs blk{};
   int F = 0; unsigned thr_int = 0;
+  // candidate-major kernel: the batch is scored in slices of `qsub` queries, sized so that a stored vector meets
+  // ~160 query-list entries per slice on average (the per-warp table takes 512; the rate is the previous batch's)
+  int slices = 1, qsub = n;
   if (h->prune_mode == 2) {
-    const int32_t rc = build_query_index(h, n, batch_nnz);
+    if (h->cand_slices_env) slices = h->cand_slices_env;
+    else if (h->cand_rate > 0) slices = (int)std::ceil(h->cand_rate * n / 160.0);
+    const int64_t max_by_mem = std::max<int64_t>(1, ((int64_t)256 << 20) / (((int64_t)D + 1) * 4));
+    slices = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(slices, 256), std::min<int64_t>(max_by_mem, (n + 31) / 32)));
+    qsub = (n + slices - 1) / slices;
+    slices = (n + qsub - 1) / qsub;
+    const int32_t rc = build_query_index(h, n, batch_nnz, slices, qsub);
     if (rc != APSS_OK) return rc;
   } else if (h->algo != 1 && batch_nnz) {
     const int32_t rc = transpose_query_blocks(h, n, batch_nnz, &blk, &F, &thr_int);
@@ -788,8 +801,15 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
         }
         ca.out_q = h->pf_q.p; ca.out_c = h->pf_c.p; ca.out_est = h->pf_est.p; ca.out_cap = h->pf_q.cap;
         ca.counters = h->d_counters; ca.heavy = h->heavy.p; ca.heavy_cap = (int64_t)h->heavy.cap;
-        CK(launch_cand(h, ca));
-        h->score_launches++; h->kernel_launches += 2;
+        CK(cudaMemsetAsync(h->d_counters + C_HEAVY_TOT, 0, sizeof(unsigned long long), s));
+        for (int sl = 0; sl < slices; ++sl) {
+          if (sl) { CK(cudaMemsetAsync(h->d_counters + C_WORK, 0, sizeof(unsigned long long), s)); CK(cudaMemsetAsync(h->d_counters + C_HEAVY, 0, sizeof(unsigned long long), s)); }
+          ca.qdir = h->qdir.p + (size_t)sl * ((size_t)D + 1);
+          ca.q_lo = sl * qsub; ca.q_hi = std::min(n, (sl + 1) * qsub);
+          CK(launch_cand(h, ca));
+          h->kernel_launches += 2;
+        }
+        h->score_launches++;
       }
     } else if (h->algo == 1) {
       if (a.total_items && batch_nnz) { CK(launch_score(h, a, h->custom_keys)); h->score_launches++; h->kernel_launches++; }
@@ -813,7 +833,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     CK(cudaEventRecord(h->ev_b1, s));
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->h_counters + C_PHASE, h->d_counters + C_PHASE, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    if (h->prune) CK(cudaMemcpyAsync(h->h_counters + C_SKIPPED, h->d_counters + C_SKIPPED, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if (h->prune) CK(cudaMemcpyAsync(h->h_counters + C_SKIPPED, h->d_counters + C_SKIPPED, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (h->h_counters[C_PF] <= h->pf_q.cap) break;
     if (attempt == 2) return h->fail(APSS_E_NOMEM, "pair buffer overflow persisted");
@@ -831,7 +851,10 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   for (int k = 0; k < 8; ++k) h->phase_cycles[k] = (int64_t)h->h_counters[C_PHASE + k];
   if (h->prune && !query_only) { h->tot_skipped += (int64_t)h->h_counters[C_SKIPPED]; h->n_post = h->nnz - h->tot_skipped; }
   res.work_items = (int64_t)((unsigned long long)h->ntiles * (unsigned long long)(h->algo == 1 ? n : (n + h->QB - 1) / h->QB));
-  if (h->prune_mode == 2) res.work_items = (int64_t)h->h_counters[C_HEAVY];      // stored vectors that took the heavy pass
+  if (h->prune_mode == 2) {
+    res.work_items = (int64_t)h->h_counters[C_HEAVY_TOT];      // (stored vector, query slice) pairs that took the heavy pass
+    if (h->n_local > 0 && res.n_active > 0) h->cand_rate = (double)res.postings_visited / ((double)h->n_local * (double)res.n_active);
+  }
   h->last_n = n; h->last_pairs = res.n_pairs;
   h->tot_postings += res.postings_visited; h->tot_cands += res.candidates_unique; h->tot_pairs += res.n_pairs; h->tot_pf += res.n_prefilter;
   h->tot_score_ms += res.score_ms;

@@ -40,7 +40,8 @@ enum Counter : int {
   C_NREJ = 7, C_NEMPTY = 8, C_NACTIVE = 9, C_MAXNNZ = 10,
   C_MAXSQ = 11,    // max squared L2 norm of a pruned vector (bits of a non-negative double)
   C_SKIPPED = 12,  // components of this batch left out of the index by exact index reduction
-  C_HEAVY = 13,    // candidate-major kernel: stored vectors deferred to the heavy pass
+  C_HEAVY = 13,    // candidate-major kernel: stored vectors deferred to the heavy pass (this launch)
+  C_HEAVY_TOT = 14, // same, summed over the query slices of the batch
   C_PHASE = 16,    // 8 per-phase cycle totals of the dense kernel (thread 0 of every CTA)
   C_COUNT = 24
 };
@@ -1205,6 +1206,7 @@ struct CandArgs {
   int64_t n_rows;            // stored vectors visible to this batch
   int64_t q_local_base;      // shard-local id of query 0 when the batch was indexed in this call, else -1
   int32_t nq;
+  int32_t q_lo, q_hi;        // the query slice this launch scores (its lists are what qdir points at)
   float thr, band1;          // t and 1 + guard band of the fp32 estimate
   float scale, inv_scale;    // 2^F, 2^-F: fixed-point accumulators of k_score_cand
   int32_t* out_q; int32_t* out_c; float* out_est; unsigned long long out_cap;
@@ -1213,19 +1215,23 @@ struct CandArgs {
 };
 
 __global__ void k_qi_emit(int n, const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim, const float* __restrict__ q_w,
-                          unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
+                          int qsub, int dimbits, unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
   const int v = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (v >= n) return;
+  const unsigned long long slice = (unsigned long long)(v / qsub) << dimbits;
   for (int p = q_ptr[v] + (threadIdx.x & 31); p < q_ptr[v + 1]; p += 32) {      // warp per vector
-    keys[p] = (unsigned long long)(unsigned)q_dim[p];
+    keys[p] = slice | (unsigned long long)(unsigned)q_dim[p];
     vals[p] = ((unsigned long long)__float_as_uint(q_w[p]) << 32) | (unsigned)v;      // uint2{x = query, y = weight}
   }
 }
 
-__global__ void k_qdir(const unsigned long long* __restrict__ keys, int nnz, int D, int32_t* __restrict__ qdir) {
-  int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d > D) return;
-  qdir[d] = (int32_t)lower_bound_u64(keys, nnz, (unsigned long long)d);
+// one directory of D + 1 offsets per query slice
+__global__ void k_qdir(const unsigned long long* __restrict__ keys, int nnz, int D, int dimbits, int slices, int32_t* __restrict__ qdir) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (long long)D + 1;
+  if (i >= per * slices) return;
+  const long long sl = i / per, d = i - sl * per;
+  qdir[i] = (int32_t)lower_bound_u64(keys, nnz, ((unsigned long long)sl << dimbits) + (unsigned long long)d);
 }
 
 static constexpr int CAND_TBL = 1024;      // hash slots per warp (key + value = 8 KB)
@@ -1316,7 +1322,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) 
       for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
       if (!total) continue;
       if (total > (unsigned)CAND_LIMIT) {
-        if (lane == 0) { const unsigned long long k = atomicAdd(&a.counters[C_HEAVY], 1ULL); if ((long long)k < a.heavy_cap) a.heavy[k] = (int32_t)c; }
+        if (lane == 0) {
+          const unsigned long long k = atomicAdd(&a.counters[C_HEAVY], 1ULL); atomicAdd(&a.counters[C_HEAVY_TOT], 1ULL);
+          if ((long long)k < a.heavy_cap) a.heavy[k] = (int32_t)c;
+        }
         continue;
       }
       if (lane == 0) n_post += total;
@@ -1401,18 +1410,34 @@ __global__ void __launch_bounds__(512, 1) k_score_cand_heavy(const CandArgs a, i
     const long long fa = __ldg(a.ifw_ptr + c), fe = __ldg(a.ifw_ptr + c + 1);
     const float cu = __ldg(a.row_ub + c);
     const long long ckey = a.q_key ? __ldg(a.c_key + c) : 0;
-    for (int q_lo = 0; q_lo < a.nq; q_lo += qc) {
-      const int q_hi = min(a.nq, q_lo + qc);
-      for (int i = tid; i < qc; i += blockDim.x) acc[i] = 0.f;
+    for (int q_lo = a.q_lo; q_lo < a.q_hi; q_lo += qc) {
+      const int q_hi = min(a.q_hi, q_lo + qc);
+      for (int i = tid; i < q_hi - q_lo; i += blockDim.x) acc[i] = 0.f;
       __syncthreads();
-      for (long long j = fa + warp; j < fe; j += nw) {            // one warp per component
-        const uint2 f = __ldg(a.ifw + j);
-        const int s = __ldg(a.qdir + f.x), e = __ldg(a.qdir + f.x + 1);
-        const float w = __uint_as_float(f.y);
-        if (q_lo == 0 && lane == 0) n_post += (unsigned)(e - s);
-        for (int p = s + lane; p < e; p += 32) {
-          const uint2 x = __ldg(a.qi + p);
-          if ((int)x.x >= q_lo && (int)x.x < q_hi) atomicAdd(acc + ((int)x.x - q_lo), w * __uint_as_float(x.y));
+      for (long long j0 = fa + (long long)warp * 32; j0 < fe; j0 += (long long)nw * 32) {      // 32 components per warp step
+        const long long j = j0 + lane;
+        int s = 0, e = 0; float w = 0.f;
+        if (j < fe) {
+          const uint2 f = __ldg(a.ifw + j);
+          s = __ldg(a.qdir + f.x); e = __ldg(a.qdir + f.x + 1);
+          w = __uint_as_float(f.y);
+        }
+        if (q_lo == a.q_lo) n_post += (unsigned)(e - s);
+        const bool longl = e - s > 32;
+        if (!longl)                                            // short list: the lane that looked it up
+          for (int p = s; p < e; ++p) {
+            const uint2 x = __ldg(a.qi + p);
+            if ((int)x.x >= q_lo && (int)x.x < q_hi) atomicAdd(acc + ((int)x.x - q_lo), w * __uint_as_float(x.y));
+          }
+        unsigned m = __ballot_sync(FULL, longl);
+        while (m) {                                            // long list: the whole warp
+          const int src = __ffs(m) - 1; m &= m - 1;
+          const int sj = __shfl_sync(FULL, s, src), ej = __shfl_sync(FULL, e, src);
+          const float wj = __shfl_sync(FULL, w, src);
+          for (int p = sj + lane; p < ej; p += 32) {
+            const uint2 x = __ldg(a.qi + p);
+            if ((int)x.x >= q_lo && (int)x.x < q_hi) atomicAdd(acc + ((int)x.x - q_lo), wj * __uint_as_float(x.y));
+          }
         }
       }
       __syncthreads();

@@ -510,7 +510,8 @@ def test_pruned_c2_shape(mode):
     assert o.totals()["pairs"] > 0 and tp * 20 < tf
 
 
-def test_candidate_major_heavy_vectors_and_many_queries():
+@pytest.mark.parametrize("slices", [0, 3, 16])
+def test_candidate_major_heavy_vectors_and_many_queries(slices, monkeypatch):
     """stored vectors whose query lists overflow the per-warp table take the heavy pass: a dimension shared by every
     vector with a weight large enough to stay indexed, batches larger than one heavy-pass query chunk is not needed
     (chunking is covered by nq > 0 only), duplicate ids and in-batch pairs included"""
@@ -524,6 +525,8 @@ def test_candidate_major_heavy_vectors_and_many_queries():
         nrm = np.sqrt(sum(x * x for x in v.values()))
         rows.append({d: x / nrm for d, x in v.items()})
     n = native()
+    if slices:
+        monkeypatch.setenv("APSS_CAND_SLICES", str(slices))      # force the query-slice path (normally sized from the previous batch)
     o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8, pruning=True)
     g = n.Index(D, t, pruning=2)
     for lo in range(0, N, 1000):
