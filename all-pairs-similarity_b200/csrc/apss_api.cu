@@ -307,8 +307,10 @@ static int32_t build_query_index(apss_handle* h, int32_t n, int32_t batch_nnz, i
 }
 
 static cudaError_t launch_cand(apss_handle* h, const CandArgs& a) {
-  const size_t smem = (size_t)h->cand_warps * (2 * CAND_TBL + 3 * CAND_FEAT + 4) * sizeof(unsigned);
-  auto kern = h->cand_warps == 16 ? k_score_cand<16> : k_score_cand<24>;
+  // 24 warps with 1024-slot tables (default) or 32 warps with 512-slot tables
+  const int tbl = h->cand_warps == 32 ? 512 : 1024;
+  const size_t smem = (size_t)h->cand_warps * (2 * tbl + 3 * CAND_FEAT + 4) * sizeof(unsigned);
+  auto kern = h->cand_warps == 16 ? k_score_cand<16, 1024> : h->cand_warps == 32 ? k_score_cand<32, 512> : k_score_cand<24, 1024>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, h->smem_optin - 1024));
   if (e != cudaSuccess) return e;
   kern<<<h->sm_count, h->cand_warps * 32, smem, h->stream>>>(a);
@@ -404,7 +406,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
     if ((cfg->pruning != 1 && cfg->pruning != 2) || algo != 3) return bail(APSS_E_INVALID);   // only the default scoring kernel applies the bound
     h->prune_mode = cfg->pruning;
     if (cfg->pruning == 1 && (QB != 16 || warps != 16 || h->COLS != 4)) return bail(APSS_E_INVALID);   // tile kernel: default shape only
-    { const char* cw = getenv("APSS_CAND_WARPS"); if (cw && (atoi(cw) == 16 || atoi(cw) == 24)) h->cand_warps = atoi(cw); }
+    { const char* cw = getenv("APSS_CAND_WARPS"); if (cw && (atoi(cw) == 16 || atoi(cw) == 24 || atoi(cw) == 32)) h->cand_warps = atoi(cw); }
     { const char* cs = getenv("APSS_CAND_SLICES"); if (cs && atoi(cs) >= 1 && atoi(cs) <= 256) h->cand_slices_env = atoi(cs); }
     const double alpha = cfg->prune_alpha == 0.0 ? 0.8 : cfg->prune_alpha;
     const double qn = cfg->max_query_norm == 0.0 ? 1.0 : cfg->max_query_norm;
@@ -759,7 +761,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   int slices = 1, qsub = n;
   if (h->prune_mode == 2) {
     if (h->cand_slices_env) slices = h->cand_slices_env;
-    else if (h->cand_rate > 0) slices = (int)std::ceil(h->cand_rate * n / 160.0);
+    else if (h->cand_rate > 0) slices = (int)std::ceil(h->cand_rate * n / (h->cand_warps == 32 ? 80.0 : 160.0));
     const int64_t max_by_mem = std::max<int64_t>(1, ((int64_t)256 << 20) / (((int64_t)D + 1) * 4));
     slices = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(slices, 256), std::min<int64_t>(max_by_mem, (n + 31) / 32)));
     qsub = (n + slices - 1) / slices;

@@ -1234,8 +1234,6 @@ __global__ void k_qdir(const unsigned long long* __restrict__ keys, int nnz, int
   qdir[i] = (int32_t)lower_bound_u64(keys, nnz, ((unsigned long long)sl << dimbits) + (unsigned long long)d);
 }
 
-static constexpr int CAND_TBL = 1024;      // hash slots per warp (key + value = 8 KB)
-static constexpr int CAND_LIMIT = 512;     // longest total list length handled in the table (load factor <= 1/2)
 static constexpr int CAND_CHUNK = 16;      // stored vectors per work-cursor fetch
 static constexpr int CAND_SHORT = 8;       // lists up to this length are walked by the lane that looked them up
 
@@ -1264,17 +1262,18 @@ __device__ __forceinline__ void cand_test_emit(const CandArgs& a, int q, long lo
 
 static constexpr int CAND_FEAT = 64;       // non-empty query lists per stored vector handled by the flat walk
 
-template <int WARPS>
+template <int WARPS, int TBL>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) {
+  constexpr int LIMIT = TBL / 2;              // longest total list length handled in the table (load factor <= 1/2)
   extern __shared__ __align__(16) unsigned smem_u[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned* keys = smem_u + (size_t)warp * (2 * CAND_TBL);
-  unsigned* vals = keys + CAND_TBL;
+  unsigned* keys = smem_u + (size_t)warp * (2 * TBL);
+  unsigned* vals = keys + TBL;
   // per-warp list of the vector's non-empty query lists: start offset in the flattened walk, list start, weight
-  int* pre = reinterpret_cast<int*>(smem_u + (size_t)WARPS * (2 * CAND_TBL)) + warp * (3 * CAND_FEAT + 4);
+  int* pre = reinterpret_cast<int*>(smem_u + (size_t)WARPS * (2 * TBL)) + warp * (3 * CAND_FEAT + 4);
   int* fs = pre + CAND_FEAT + 4;
   float* fw = reinterpret_cast<float*>(fs + CAND_FEAT);
-  for (int i = lane; i < CAND_TBL; i += 32) { keys[i] = 0u; vals[i] = 0u; }
+  for (int i = lane; i < TBL; i += 32) { keys[i] = 0u; vals[i] = 0u; }
   __syncwarp();
   unsigned long long n_post = 0, n_cand = 0;
   constexpr int RC = 4;                       // components per lane kept in registers between the two passes
@@ -1321,7 +1320,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_cand(const CandArgs a) 
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
       if (!total) continue;
-      if (total > (unsigned)CAND_LIMIT) {
+      if (total > (unsigned)LIMIT) {
         if (lane == 0) {
           const unsigned long long k = atomicAdd(&a.counters[C_HEAVY], 1ULL); atomicAdd(&a.counters[C_HEAVY_TOT], 1ULL);
           if ((long long)k < a.heavy_cap) a.heavy[k] = (int32_t)c;
