@@ -642,6 +642,84 @@ static int32_t transpose_query_blocks(apss_handle* h, int32_t n, int32_t batch_n
   return APSS_OK;
 }
 
+// How many query slices the candidate-major kernel scores this batch in: sized so that a stored vector meets
+// ~160 query-list entries per slice on average (the per-warp table takes 512; the rate is the previous batch's).
+static void plan_query_slices(const apss_handle* h, int32_t n, int* slices_out, int* qsub_out) {
+  const int D = h->cfg.dim;
+  int slices = 1;
+  if (h->cand_slices_env) slices = h->cand_slices_env;
+  else if (h->cand_rate > 0) slices = (int)std::ceil(h->cand_rate * n / (h->cand_warps == 32 ? 80.0 : 160.0));
+  const int64_t max_by_mem = std::max<int64_t>(1, ((int64_t)256 << 20) / (((int64_t)D + 1) * 4));     // directories: <= 256 MB
+  slices = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(slices, 256), std::min<int64_t>(max_by_mem, (n + 31) / 32)));
+  const int qsub = (n + slices - 1) / slices;
+  *slices_out = (n + qsub - 1) / qsub; *qsub_out = qsub;
+}
+
+// One scoring attempt of the candidate-major path: k_score_cand + k_score_cand_heavy per query slice.
+static int32_t score_candidate_major(apss_handle* h, int32_t n, int32_t batch_nnz, int slices, int qsub, int64_t q_local_base,
+                                     const int64_t* d_qkey) {
+  cudaStream_t s = h->stream;
+  const int D = h->cfg.dim;
+  const double t = h->cfg.similarity_threshold;
+  const int64_t n_rows = h->n_local;      // includes this batch when it was indexed (IWA:125-132)
+  if (!n_rows || !batch_nnz) return APSS_OK;
+  CandArgs ca{};
+  ca.ifw_ptr = h->ifw_ptr.p; ca.ifw = h->ifw.p;
+  ca.row_ub = h->row_ub.p; ca.c_key = h->key.p; ca.qi = reinterpret_cast<const uint2*>(h->bt_vals_out.p);
+  ca.q_nrm = h->q_nrm.p; ca.q_key = h->custom_keys ? d_qkey : nullptr;
+  ca.n_rows = n_rows; ca.q_local_base = q_local_base; ca.nq = n;
+  ca.thr = (float)t; if ((double)ca.thr > t) ca.thr = std::nextafterf(ca.thr, -INFINITY);
+  ca.band1 = (float)(1.0 + (double)(h->max_nnz_seen + 8) * std::ldexp(1.0, -22));
+  {   // u32 fixed point: every dot product is <= the largest squared norm (Cauchy-Schwarz)
+    const int Fc = std::max(-100, std::min(100, (int)std::floor(std::log2(2147483648.0 / (std::max(h->max_sq, 1e-300) * (1.0 + 1e-6))))));
+    ca.scale = (float)std::ldexp(1.0, Fc); ca.inv_scale = (float)std::ldexp(1.0, -Fc);
+  }
+  ca.out_q = h->pf_q.p; ca.out_c = h->pf_c.p; ca.out_est = h->pf_est.p; ca.out_cap = h->pf_q.cap;
+  ca.counters = h->d_counters; ca.heavy = h->heavy.p; ca.heavy_cap = (int64_t)h->heavy.cap;
+  CK(cudaMemsetAsync(h->d_counters + C_HEAVY, 0, 2 * sizeof(unsigned long long), s));      // C_HEAVY, C_HEAVY_TOT
+  for (int sl = 0; sl < slices; ++sl) {
+    if (sl) { CK(cudaMemsetAsync(h->d_counters + C_WORK, 0, sizeof(unsigned long long), s)); CK(cudaMemsetAsync(h->d_counters + C_HEAVY, 0, sizeof(unsigned long long), s)); }
+    ca.qdir = h->qdir.p + (size_t)sl * ((size_t)D + 1);
+    ca.q_lo = sl * qsub; ca.q_hi = std::min(n, (sl + 1) * qsub);
+    CK(launch_cand(h, ca));
+    h->kernel_launches += 2;
+  }
+  h->score_launches++;
+  return APSS_OK;
+}
+
+// One scoring attempt of the tile kernels (K2/K3): the row kernel, the query-block kernel or the dense-head kernel.
+static int32_t score_tiles(apss_handle* h, int32_t n, int32_t batch_nnz, BlockArgs blk, int F, unsigned thr_int, int64_t q_local_base,
+                           const int64_t* d_qkey) {
+  const int D = h->cfg.dim;
+  const double t = h->cfg.similarity_threshold;
+  ScoreArgs a{};
+  a.q_ptr = h->q_ptr.p; a.q_dim = h->q_dim.p; a.q_w = h->q_w.p; a.q_key = d_qkey;
+  a.post = h->post.p; a.dir = h->dir.p; a.tile_base = h->tile_base.p; a.c_key = h->key.p;
+  a.nq = n; a.ntiles = (int32_t)h->ntiles; a.D = D; a.CR = h->CR; a.q_local_base = q_local_base;
+  if (t > 0) {     // fp32 estimate of the row kernel: guard band of one rounding per component
+    const double band = (double)(h->max_nnz_seen + 8) * std::ldexp(1.0, -23);
+    a.thr_emit = std::nextafterf((float)(t * (1.0 - band)), -INFINITY);
+  } else a.thr_emit = -INFINITY;
+  a.out_q = h->pf_q.p; a.out_c = h->pf_c.p; a.out_est = h->pf_est.p; a.out_cap = h->pf_q.cap;
+  a.counters = h->d_counters;
+  a.tile_cnt = h->algo == 3 ? h->tile_cnt.p : nullptr; a.post_cap = (long long)h->post.cap; a.seg_cap = h->seg_cap;
+  a.total_items = (unsigned long long)h->ntiles * (unsigned long long)n;
+  a.row_ub = h->prune ? h->row_ub.p : nullptr; a.q_nrm = h->prune ? h->q_nrm.p : nullptr;
+  if (h->algo == 1) {
+    if (a.total_items && batch_nnz) { CK(launch_score(h, a, h->custom_keys)); h->score_launches++; h->kernel_launches++; }
+  } else if (h->ntiles && batch_nnz) {
+    blk.thr_int = thr_int; blk.inv_scale = (float)std::ldexp(1.0, -F); blk.scale = (float)std::ldexp(1.0, F);
+    a.total_items = (unsigned long long)h->ntiles * (unsigned long long)blk.n_qblocks;
+    if (h->algo == 3) {
+      DenseTiles dtl{h->dn_cnt.p, h->dn_dim.p, h->dn_len.p, h->dn_hash.p, h->dn_w.p};
+      CK(launch_dense(h, a, blk, dtl, h->custom_keys));
+    } else CK(launch_blk(h, a, blk, h->custom_keys));
+    h->score_launches++; h->kernel_launches++;
+  }
+  return APSS_OK;
+}
+
 extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* indptr, const int32_t* indices, const double* values,
                                      const int64_t* ext_keys, const int32_t* first_dim, uint32_t flags, apss_batch_result* out) {
   if (!h) return APSS_E_INVALID;
@@ -740,11 +818,6 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
 
   // ---- K2/K3: scoring + threshold/compaction, K4: fp64 verify.  Re-run on output overflow.
   const double t = h->cfg.similarity_threshold;
-  float thr_emit;
-  if (t > 0) {
-    const double band = (double)(h->max_nnz_seen + 8) * std::ldexp(1.0, -23);
-    thr_emit = std::nextafterf((float)(t * (1.0 - band)), -INFINITY);
-  } else thr_emit = -INFINITY;
   // when keys are supplied, q_key lives in b_key (host path) or the caller's buffer (device path)
   const int64_t* d_qkey = d_keys;
   if (h->custom_keys && !d_qkey) {     // keys were used before: this batch gets the default keys (its internal ids)
@@ -753,19 +826,13 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     CK(cudaGetLastError()); h->kernel_launches++;
     d_qkey = h->b_key.p;
   }
-  // ---- query-block transposition for the block kernels: (block, dim)-sorted (row, scaled weight) lists
+  // per-batch query structure: the batch inverted by dimension (candidate-major kernel) or transposed into
+  // query blocks (block kernels); the row kernel reads the CSR batch as it is
   BlockArgs blk{};
   int F = 0; unsigned thr_int = 0;
-  // candidate-major kernel: the batch is scored in slices of `qsub` queries, sized so that a stored vector meets
-  // ~160 query-list entries per slice on average (the per-warp table takes 512; the rate is the previous batch's)
   int slices = 1, qsub = n;
   if (h->prune_mode == 2) {
-    if (h->cand_slices_env) slices = h->cand_slices_env;
-    else if (h->cand_rate > 0) slices = (int)std::ceil(h->cand_rate * n / (h->cand_warps == 32 ? 80.0 : 160.0));
-    const int64_t max_by_mem = std::max<int64_t>(1, ((int64_t)256 << 20) / (((int64_t)D + 1) * 4));
-    slices = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(slices, 256), std::min<int64_t>(max_by_mem, (n + 31) / 32)));
-    qsub = (n + slices - 1) / slices;
-    slices = (n + qsub - 1) / qsub;
+    plan_query_slices(h, n, &slices, &qsub);
     const int32_t rc = build_query_index(h, n, batch_nnz, slices, qsub);
     if (rc != APSS_OK) return rc;
   } else if (h->algo != 1 && batch_nnz) {
@@ -773,57 +840,12 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     if (rc != APSS_OK) return rc;
   }
   for (int attempt = 0; attempt < 3; ++attempt) {
-    ScoreArgs a{};
-    a.q_ptr = h->q_ptr.p; a.q_dim = h->q_dim.p; a.q_w = h->q_w.p; a.q_key = d_qkey;
-    a.post = h->post.p; a.dir = h->dir.p; a.tile_base = h->tile_base.p; a.c_key = h->key.p;
-    a.nq = n; a.ntiles = (int32_t)h->ntiles; a.D = D; a.CR = h->CR; a.q_local_base = q_local_base;
-    a.thr_emit = thr_emit;
-    a.out_q = h->pf_q.p; a.out_c = h->pf_c.p; a.out_est = h->pf_est.p; a.out_cap = h->pf_q.cap;
-    a.counters = h->d_counters;
-    a.tile_cnt = h->algo == 3 ? h->tile_cnt.p : nullptr; a.post_cap = (long long)h->post.cap; a.seg_cap = h->seg_cap;
-    a.total_items = (unsigned long long)h->ntiles * (unsigned long long)n;
-    a.row_ub = h->prune ? h->row_ub.p : nullptr; a.q_nrm = h->prune ? h->q_nrm.p : nullptr;
     CK(cudaMemsetAsync(h->d_counters, 0, 7 * sizeof(unsigned long long), s));   // keep the prefilter tallies
     CK(cudaMemsetAsync(h->d_counters + C_PHASE, 0, 8 * sizeof(unsigned long long), s));
-    CK(cudaMemsetAsync(h->d_counters + C_HEAVY, 0, sizeof(unsigned long long), s));
     CK(cudaEventRecord(h->ev_s0, s));
-    if (h->prune_mode == 2) {
-      const int64_t n_rows = h->n_local;      // includes this batch when it was indexed (IWA:125-132)
-      if (n_rows && batch_nnz) {
-        CandArgs ca{};
-        ca.ifw_ptr = h->ifw_ptr.p; ca.ifw = h->ifw.p;
-        ca.row_ub = h->row_ub.p; ca.c_key = h->key.p; ca.qdir = h->qdir.p; ca.qi = reinterpret_cast<const uint2*>(h->bt_vals_out.p);
-        ca.q_nrm = h->q_nrm.p; ca.q_key = h->custom_keys ? d_qkey : nullptr;
-        ca.n_rows = n_rows; ca.q_local_base = q_local_base; ca.nq = n;
-        ca.thr = (float)t; if ((double)ca.thr > t) ca.thr = std::nextafterf(ca.thr, -INFINITY);
-        ca.band1 = (float)(1.0 + (double)(h->max_nnz_seen + 8) * std::ldexp(1.0, -22));
-        {   // u32 fixed point: every dot product is <= the largest squared norm (Cauchy-Schwarz)
-          const int Fc = std::max(-100, std::min(100, (int)std::floor(std::log2(2147483648.0 / (std::max(h->max_sq, 1e-300) * (1.0 + 1e-6))))));
-          ca.scale = (float)std::ldexp(1.0, Fc); ca.inv_scale = (float)std::ldexp(1.0, -Fc);
-        }
-        ca.out_q = h->pf_q.p; ca.out_c = h->pf_c.p; ca.out_est = h->pf_est.p; ca.out_cap = h->pf_q.cap;
-        ca.counters = h->d_counters; ca.heavy = h->heavy.p; ca.heavy_cap = (int64_t)h->heavy.cap;
-        CK(cudaMemsetAsync(h->d_counters + C_HEAVY_TOT, 0, sizeof(unsigned long long), s));
-        for (int sl = 0; sl < slices; ++sl) {
-          if (sl) { CK(cudaMemsetAsync(h->d_counters + C_WORK, 0, sizeof(unsigned long long), s)); CK(cudaMemsetAsync(h->d_counters + C_HEAVY, 0, sizeof(unsigned long long), s)); }
-          ca.qdir = h->qdir.p + (size_t)sl * ((size_t)D + 1);
-          ca.q_lo = sl * qsub; ca.q_hi = std::min(n, (sl + 1) * qsub);
-          CK(launch_cand(h, ca));
-          h->kernel_launches += 2;
-        }
-        h->score_launches++;
-      }
-    } else if (h->algo == 1) {
-      if (a.total_items && batch_nnz) { CK(launch_score(h, a, h->custom_keys)); h->score_launches++; h->kernel_launches++; }
-    } else if (h->ntiles && batch_nnz) {
-      blk.thr_int = thr_int; blk.inv_scale = (float)std::ldexp(1.0, -F); blk.scale = (float)std::ldexp(1.0, F);
-      a.total_items = (unsigned long long)h->ntiles * (unsigned long long)blk.n_qblocks;
-      if (h->algo == 3) {
-        DenseTiles dtl{h->dn_cnt.p, h->dn_dim.p, h->dn_len.p, h->dn_hash.p, h->dn_w.p};
-        CK(launch_dense(h, a, blk, dtl, h->custom_keys));
-      } else CK(launch_blk(h, a, blk, h->custom_keys));
-      h->score_launches++; h->kernel_launches++;
-    }
+    const int32_t rcs = h->prune_mode == 2 ? score_candidate_major(h, n, batch_nnz, slices, qsub, q_local_base, d_qkey)
+                                           : score_tiles(h, n, batch_nnz, blk, F, thr_int, q_local_base, d_qkey);
+    if (rcs != APSS_OK) return rcs;
     CK(cudaEventRecord(h->ev_s1, s));
     CK(h->out_q.reserve(h->pf_q.cap, 0, s)); CK(h->out_c.reserve(h->pf_q.cap, 0, s)); CK(h->out_sim.reserve(h->pf_q.cap, 0, s));
     if (h->n_local) {
