@@ -233,6 +233,23 @@ def test_pair_buffer_overflow_grows_and_replays(algo):
     assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_pruned_pair_buffer_overflow_and_zero_threshold(mode):
+    """a low threshold with a tiny pair buffer: the reduced-index kernels replay after growing it; t = 0 keeps
+    everything indexed (nothing may be left out when any shared dim makes a pair)"""
+    N, D = 1500, 1 << 8
+    data = _synth(N, D, 10, seed=2, dup_frac=0.0)
+    n = native()
+    for t in (0.05, 0.0):
+        o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
+        g = n.Index(D, t, tile_vectors=256, reserve_pairs=1024, pruning=mode)
+        ro = o.insert_batch(*data); rg = g.insert_batch(*data)
+        assert rg.n_pairs == len(ro.sim) > 1024
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+        if t == 0.0:
+            assert g.stats()["n_unindexed"] == 0 and rg.candidates_unique == ro.candidates_unique
+
+
 def test_device_pointer_entry_matches_host_entry():
     import torch
     N, D, t = 3000, 1 << 11, 0.5
