@@ -79,21 +79,28 @@ class ShardDispatcher:
         """One insertNewVector batch.  Rank 0 passes the batch (torch tensors on self.device, or
         anything torch.as_tensor accepts); other ranks pass nothing."""
         dev = self.device
-        # 1. broadcast: sizes, then the three CSR arrays
-        hdr = torch.zeros(2, dtype=torch.int64, device=dev)
+        # 1. broadcast: sizes, then ONE payload holding the three CSR arrays (indptr | values | indices: every
+        #    part starts 8-byte aligned), so a batch costs two collectives instead of four
         if self.rank == 0:
-            indptr = torch.as_tensor(indptr, dtype=torch.int64).to(dev)
-            indices = torch.as_tensor(indices, dtype=torch.int32).to(dev)
-            values = torch.as_tensor(values, dtype=torch.float64).to(dev)
-            hdr[0] = indptr.numel() - 1
-            hdr[1] = indices.numel()
-        self._bcast(hdr)
-        n, nnz = int(hdr[0]), int(hdr[1])
-        if self.rank != 0:
-            indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
-            indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
-            values = torch.empty(max(nnz, 1), dtype=torch.float64, device=dev)[:nnz]
-        self._bcast(indptr); self._bcast(indices); self._bcast(values)
+            indptr = torch.as_tensor(indptr, dtype=torch.int64).to(dev).contiguous()
+            indices = torch.as_tensor(indices, dtype=torch.int32).to(dev).contiguous()
+            values = torch.as_tensor(values, dtype=torch.float64).to(dev).contiguous()
+        if self.world > 1:
+            hdr = torch.tensor([indptr.numel() - 1, indices.numel()] if self.rank == 0 else [0, 0], dtype=torch.int64, device=dev)
+            self._bcast(hdr)
+            n, nnz = (int(x) for x in hdr.tolist())
+            b0, b1 = 8 * (n + 1), 8 * (n + 1) + 8 * nnz
+            if self.rank == 0:
+                payload = torch.cat([indptr.view(torch.uint8), values.view(torch.uint8), indices.view(torch.uint8)])
+            else:
+                payload = torch.empty(b1 + 4 * nnz, dtype=torch.uint8, device=dev)
+            self._bcast(payload)
+            if self.rank != 0:
+                indptr = payload[:b0].view(torch.int64)
+                values = payload[b0:b1].view(torch.float64)
+                indices = payload[b1:].view(torch.int32)
+        else:
+            n = int(indptr.numel()) - 1
         if dev.type == "cuda":
             torch.cuda.current_stream().synchronize()      # the engine runs on its own stream
 
@@ -109,29 +116,30 @@ class ShardDispatcher:
             self.next_id += n
             self.batch_no += 1
 
-        # 3. gather pair lists to rank 0
+        # 3. gather pair lists to rank 0: one all_gather of (pairs, postings, candidates) per rank, then ONE gather
+        #    of a packed buffer (sim fp64 | q int32 | c int32, padded to the largest list)
         q, c, s = self._local_pairs(res.n_pairs)
         tot = torch.tensor([res.n_pairs, res.postings_visited, res.candidates_unique], dtype=torch.int64, device=dev)
         if self.world > 1:
-            counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
-            dist.all_gather(counts, tot[:1].clone(), group=self.group)
-            counts = [int(x) for x in counts]
-            dist.all_reduce(tot, group=self.group)
+            allc = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(self.world)]
+            dist.all_gather(allc, tot, group=self.group)
+            allc = torch.stack(allc)
+            tot = allc.sum(dim=0)
+            counts = allc[:, 0].tolist()
             mx = max(counts)
             if mx > 0:
-                def pad(t):
-                    out = torch.zeros(mx, dtype=t.dtype, device=dev)
-                    out[:t.numel()] = t
-                    return out
-                bufs = []
-                for t in (q, c, s):
-                    gl = [torch.empty(mx, dtype=t.dtype, device=dev) for _ in range(self.world)] if self.rank == 0 else None
-                    dist.gather(pad(t), gl, dst=0, group=self.group)
-                    bufs.append(gl)
+                m = int(q.numel())
+                buf = torch.zeros(16 * mx, dtype=torch.uint8, device=dev)
+                buf[:8 * mx].view(torch.float64)[:m] = s
+                buf[8 * mx:12 * mx].view(torch.int32)[:m] = q
+                buf[12 * mx:].view(torch.int32)[:m] = c
+                gl = [torch.empty(16 * mx, dtype=torch.uint8, device=dev) for _ in range(self.world)] if self.rank == 0 else None
+                dist.gather(buf, gl, dst=0, group=self.group)
                 if self.rank == 0:
-                    q = torch.cat([b[:k] for b, k in zip(bufs[0], counts)])
-                    c = torch.cat([b[:k] for b, k in zip(bufs[1], counts)])
-                    s = torch.cat([b[:k] for b, k in zip(bufs[2], counts)])
+                    s = torch.cat([b[:8 * mx].view(torch.float64)[:k] for b, k in zip(gl, counts)])
+                    q = torch.cat([b[8 * mx:12 * mx].view(torch.int32)[:k] for b, k in zip(gl, counts)])
+                    c = torch.cat([b[12 * mx:].view(torch.int32)[:k] for b, k in zip(gl, counts)])
+        tot = tot.tolist()
         if self.rank == 0:
             qn, cn, sn = q.cpu().numpy(), c.cpu().numpy(), s.cpu().numpy()
         else:
