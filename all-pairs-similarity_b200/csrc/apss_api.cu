@@ -576,7 +576,7 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
     CK(h->dn_dim.reserve((size_t)tile1 * KD, (size_t)tile0 * KD, s)); CK(h->dn_len.reserve((size_t)tile1 * KD, (size_t)tile0 * KD, s));
     CK(h->dn_hash.reserve((size_t)tile1 * HS, (size_t)tile0 * HS, s));
     CK(h->dn_w.reserve((size_t)tile1 * KD * CR, (size_t)tile0 * KD * CR, s));
-    k_dense_select<<<ntiles_aff, 256, 0, s>>>(D, CR, tile0, n_new, h->dense_shift, h->dir.p, h->dn_cnt.p, h->dn_dim.p, h->dn_len.p, h->dn_hash.p, h->tile_cnt.p);
+    k_dense_select<<<ntiles_aff, 1024, 0, s>>>(D, CR, tile0, n_new, h->dense_shift, h->dir.p, h->dn_cnt.p, h->dn_dim.p, h->dn_len.p, h->dn_hash.p, h->tile_cnt.p);
     CK(cudaGetLastError());
     k_tile_bases<<<1, 32, 0, s>>>(tile0, ntiles_aff, h->tile_cnt.p, h->tile_base.p);
     CK(cudaGetLastError());

@@ -664,43 +664,69 @@ struct DenseTiles {
 
 __device__ __forceinline__ unsigned dense_hash_fn(int d) { return ((unsigned)d * 2654435761u) >> 25; }   // 7 bits
 
-// one CTA per affected tile: pick the dense dims (ascending dim order, first KD that qualify)
-__global__ void k_dense_select(int D, int CR, int64_t tile0, int64_t n_local, int dense_shift, const int32_t* __restrict__ dir,
+// one CTA (1024 threads) per affected tile: pick the dense dims (ascending dim order, first KD that qualify).
+// The directory is read in super-chunks of 64 x 1024 dims: pass 1 counts the qualifying dims per (step, warp),
+// a block scan turns the counts into slot offsets, pass 2 assigns the slots -- three barriers per 65 536 dims.
+__global__ void __launch_bounds__(1024) k_dense_select(int D, int CR, int64_t tile0, int64_t n_local, int dense_shift, const int32_t* __restrict__ dir,
                                int32_t* __restrict__ d_cnt, int32_t* __restrict__ d_dim, int32_t* __restrict__ d_len,
                                int2* __restrict__ d_hash, int32_t* __restrict__ tile_cnt) {
+  constexpr int NT = 1024, NW = 32, IT = 64;
   const int64_t tile = tile0 + blockIdx.x;
   const int32_t* dirt = dir + (size_t)tile * ((size_t)D + 1);
-  __shared__ int s_run, s_warp[32], s_removed;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  __shared__ int s_cnt[IT * NW];
+  __shared__ int s_wtot[NW];
+  __shared__ int s_run, s_removed;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t nt = min((int64_t)CR, n_local - tile * CR);
   // dense_shift < 16: threshold nt / 2^shift; otherwise (dense_shift - 16) sixteenths of the tile
   const int thr = dense_shift < 16 ? max(8, (int)((nt + (1 << dense_shift) - 1) >> dense_shift))
                                    : max(8, (int)((nt * (dense_shift - 16) + 15) / 16));
   if (tid == 0) { s_run = 0; s_removed = 0; }
-  for (int h = tid; h < HS; h += blockDim.x) d_hash[tile * HS + h] = make_int2(-1, -1);
+  for (int h = tid; h < HS; h += NT) d_hash[tile * HS + h] = make_int2(-1, -1);
   __syncthreads();
-  for (int d0 = 0; d0 < D; d0 += blockDim.x) {
-    const int d = d0 + tid;
-    int len = 0;
-    if (d < D) len = dirt[d + 1] - dirt[d];
-    const bool q = len >= thr;
-    const unsigned bal = __ballot_sync(FULL, q);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    int before = s_run;
-    for (int w = 0; w < warp; ++w) before += s_warp[w];
-    const int slot = before + __popc(bal & ((1u << lane) - 1));
-    if (q && slot < KD) {
-      d_dim[tile * KD + slot] = d; d_len[tile * KD + slot] = len;
-      atomicAdd(&s_removed, len);
-      unsigned h = dense_hash_fn(d);
-      while (atomicCAS(&d_hash[tile * HS + h].x, -1, d) != -1) h = (h + 1) & (HS - 1);
-      d_hash[tile * HS + h].y = slot;
+  for (int64_t base = 0; base < D; base += (int64_t)NT * IT) {
+    const int run0 = s_run;
+    if (run0 >= KD) break;
+    for (int it = 0; it < IT; ++it) {
+      const int64_t d = base + (int64_t)it * NT + tid;
+      int len = 0;
+      if (d < D) len = dirt[d + 1] - dirt[d];
+      const unsigned bal = __ballot_sync(FULL, len >= thr);
+      if (lane == 0) s_cnt[it * NW + warp] = __popc(bal);
     }
     __syncthreads();
-    if (tid == 0) { int t = s_run; for (int w = 0; w < nw; ++w) t += s_warp[w]; s_run = t; }
+    // exclusive scan of the IT * NW = 2 * NT counts: two per thread
+    const int a0 = s_cnt[2 * tid], a1 = s_cnt[2 * tid + 1];
+    int inc = a0 + a1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_wtot[warp] = inc;
     __syncthreads();
-    if (s_run >= KD) break;
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_wtot[w];
+    const int excl = before + inc - (a0 + a1);
+    s_cnt[2 * tid] = excl; s_cnt[2 * tid + 1] = excl + a0;
+    __syncthreads();
+    int total = 0;
+    for (int w = 0; w < NW; ++w) total += s_wtot[w];
+    for (int it = 0; it < IT; ++it) {
+      const int64_t d = base + (int64_t)it * NT + tid;
+      int len = 0;
+      if (d < D) len = dirt[d + 1] - dirt[d];
+      const bool q = len >= thr;
+      const unsigned bal = __ballot_sync(FULL, q);
+      const int slot = run0 + s_cnt[it * NW + warp] + __popc(bal & ((1u << lane) - 1));
+      if (q && slot < KD) {
+        d_dim[tile * KD + slot] = (int)d; d_len[tile * KD + slot] = len;
+        atomicAdd(&s_removed, len);
+        unsigned h = dense_hash_fn((int)d);
+        while (atomicCAS(&d_hash[tile * HS + h].x, -1, (int)d) != -1) h = (h + 1) & (HS - 1);
+        d_hash[tile * HS + h].y = slot;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_run = run0 + total;
+    __syncthreads();
   }
   if (tid == 0) { d_cnt[tile] = min(s_run, KD); tile_cnt[tile] = dirt[D] - s_removed; }
 }

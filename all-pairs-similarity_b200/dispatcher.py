@@ -51,6 +51,9 @@ class ShardDispatcher:
         self.next_id = 0
         self.batch_no = 0
         self.frozen = False
+        # APSS_DISPATCH_TIMING=1: wall-clock per phase (broadcast, local scoring, gather), summed over the calls
+        import os
+        self.timing = {"bcast": 0.0, "score": 0.0, "gather": 0.0, "calls": 0} if os.environ.get("APSS_DISPATCH_TIMING") else None
 
     # ---- helpers
     def _bcast(self, t, src=0):
@@ -79,6 +82,8 @@ class ShardDispatcher:
         """One insertNewVector batch.  Rank 0 passes the batch (torch tensors on self.device, or
         anything torch.as_tensor accepts); other ranks pass nothing."""
         dev = self.device
+        import time
+        t0 = time.perf_counter()
         # 1. broadcast: sizes, then ONE payload holding the three CSR arrays (indptr | values | indices: every
         #    part starts 8-byte aligned), so a batch costs two collectives instead of four
         if self.rank == 0:
@@ -104,6 +109,7 @@ class ShardDispatcher:
         if dev.type == "cuda":
             torch.cuda.current_stream().synchronize()      # the engine runs on its own stream
 
+        t1 = time.perf_counter()
         # 2. local scoring; the owner indexes
         query_only = query_only or self.frozen
         owner = self.owner_of(self.batch_no)
@@ -116,6 +122,7 @@ class ShardDispatcher:
             self.next_id += n
             self.batch_no += 1
 
+        t2 = time.perf_counter()
         # 3. gather pair lists to rank 0: one all_gather of (pairs, postings, candidates) per rank, then ONE gather
         #    of a packed buffer (sim fp64 | q int32 | c int32, padded to the largest list)
         q, c, s = self._local_pairs(res.n_pairs)
@@ -144,6 +151,9 @@ class ShardDispatcher:
             qn, cn, sn = q.cpu().numpy(), c.cpu().numpy(), s.cpu().numpy()
         else:
             qn = cn = sn = None
+        if self.timing is not None:
+            t3 = time.perf_counter()
+            self.timing["bcast"] += t1 - t0; self.timing["score"] += t2 - t1; self.timing["gather"] += t3 - t2; self.timing["calls"] += 1
         return DispatchResult(id_base, owner, int(tot[0]), int(tot[1]), int(tot[2]), qn, cn, sn, res)
 
     def _local_pairs(self, n_pairs):

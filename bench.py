@@ -371,6 +371,10 @@ def main():
         torch.cuda.profiler.stop()
     st = eng.stats()
     launches = st["kernel_launches"] - launches0
+    if disp.timing is not None and rank == 0:
+        tm = disp.timing
+        print("dispatcher timing per call (ms): bcast %.3f score %.3f gather %.3f | kernel %.3f" % (
+            1e3 * tm["bcast"] / tm["calls"], 1e3 * tm["score"] / tm["calls"], 1e3 * tm["gather"] / tm["calls"], tot["score_ms"] / K), file=sys.stderr, flush=True)
     score_launches = K
     dt_value = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
     wall_value = w1 - w0
