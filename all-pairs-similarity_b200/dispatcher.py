@@ -8,7 +8,7 @@ block-cyclic range of internal ids (block = one insert batch, owner = batch_no m
   1. rank 0 broadcasts the query batch (CSR) to all ranks          -- torch.distributed.broadcast
   2. every rank scores the batch against its own shard; the owner also indexes it (it alone sees
      the in-batch pairs, IWA:125-132)                              -- include/apss.h
-  3. per-shard pair lists are gathered back to rank 0              -- all_gather(counts) + gather
+  3. per-shard pair lists are gathered back to rank 0              -- one all_gather (counters + pairs)
 
 Every pair is scored exactly once (a vector lives on exactly one shard).  The dispatcher owns the
 global id space (apss_set_next_id), so shards report global candidate ids.  Backend-agnostic: with
@@ -39,6 +39,8 @@ class DispatchResult:
 
 
 class ShardDispatcher:
+    PAIR_SLOT = 8192          # pairs per rank that travel with the counters (16 B each)
+
     def __init__(self, engine, group=None, device=None):
         """engine: this rank's index worker (native.Index on the rank's GPU)."""
         self.engine = engine
@@ -123,19 +125,32 @@ class ShardDispatcher:
             self.batch_no += 1
 
         t2 = time.perf_counter()
-        # 3. gather pair lists to rank 0: one all_gather of (pairs, postings, candidates) per rank, then ONE gather
-        #    of a packed buffer (sim fp64 | q int32 | c int32, padded to the largest list)
+        # 3. pair lists to rank 0.  One all_gather of a fixed-size slot per rank carries the counters AND up to
+        #    PAIR_SLOT pairs (sim fp64 | q int32 | c int32), so the usual batch needs a single collective; only when a
+        #    rank reports more pairs than fit is a second, exactly sized gather issued.
         q, c, s = self._local_pairs(res.n_pairs)
         tot = torch.tensor([res.n_pairs, res.postings_visited, res.candidates_unique], dtype=torch.int64, device=dev)
         if self.world > 1:
-            allc = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(self.world)]
-            dist.all_gather(allc, tot, group=self.group)
-            allc = torch.stack(allc)
+            cap = self.PAIR_SLOT
+            m = int(q.numel())
+            k = min(m, cap)
+            slot = torch.zeros(24 + 16 * cap, dtype=torch.uint8, device=dev)
+            slot[:24] = tot.view(torch.uint8)
+            slot[24:24 + 8 * cap].view(torch.float64)[:k] = s[:k]
+            slot[24 + 8 * cap:24 + 12 * cap].view(torch.int32)[:k] = q[:k]
+            slot[24 + 12 * cap:].view(torch.int32)[:k] = c[:k]
+            slots = [torch.empty_like(slot) for _ in range(self.world)]
+            dist.all_gather(slots, slot, group=self.group)
+            allc = torch.stack([x[:24].view(torch.int64) for x in slots])
             tot = allc.sum(dim=0)
             counts = allc[:, 0].tolist()
             mx = max(counts)
-            if mx > 0:
-                m = int(q.numel())
+            if mx <= cap:
+                if self.rank == 0:
+                    s = torch.cat([x[24:24 + 8 * cap].view(torch.float64)[:k] for x, k in zip(slots, counts)])
+                    q = torch.cat([x[24 + 8 * cap:24 + 12 * cap].view(torch.int32)[:k] for x, k in zip(slots, counts)])
+                    c = torch.cat([x[24 + 12 * cap:].view(torch.int32)[:k] for x, k in zip(slots, counts)])
+            else:
                 buf = torch.zeros(16 * mx, dtype=torch.uint8, device=dev)
                 buf[:8 * mx].view(torch.float64)[:m] = s
                 buf[8 * mx:12 * mx].view(torch.int32)[:m] = q

@@ -17,12 +17,14 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, N, D, t, B, ret):
+def _worker(rank, world, port, N, D, t, B, ret, pair_slot=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import apss_b200
     from apss_b200.dispatcher import ShardDispatcher
     data = apss_b200.synth.generate(N, D, 20, seed=4).numpy()
+    if pair_slot:
+        ShardDispatcher.PAIR_SLOT = pair_slot        # force the second, exactly sized gather
     disp = ShardDispatcher(OracleEngine(D, t), device="cpu")
     # bulk-load the first two batches without scoring, then dispatch the rest
     for lo in (0, B):
@@ -48,12 +50,13 @@ def _worker(rank, world, port, N, D, t, B, ret):
     dist.destroy_process_group()
 
 
-def test_dispatcher_world2_matches_single_oracle():
+@pytest.mark.parametrize("pair_slot", [0, 2])
+def test_dispatcher_world2_matches_single_oracle(pair_slot):
     from oracle import oracle as orc
     import apss_b200
     N, D, t, B = 1200, 512, 0.5, 200
     mgr = mp.Manager(); ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), N, D, t, B, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), N, D, t, B, ret, pair_slot), nprocs=2, join=True)
     data = apss_b200.synth.generate(N, D, 20, seed=4).numpy()
     o = orc.Oracle(D, t, algo=orc.ALGO_FAST)
     want = {}; tot = [0, 0]
