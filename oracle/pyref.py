@@ -179,3 +179,72 @@ def similarity_output_to_string(output: Dict[str, Dict[str, float]]) -> str:
             sb.append(c + "," + repr(float(s)) + ";")
         sb.append("\n")
     return "".join(sb)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Exact index reduction -- NOT reference behaviour: a second, pure-Python restatement of the
+# rule the GPU library applies with `pruning` on (include/apss.h) and oracle/apss_oracle.c restates in C
+# (oracle_set_pruning), so that the two can be cross-checked on small inputs.
+
+def index_reduction_limit(similarity_threshold: float, alpha: float = 0.8, max_query_norm: float = 1.0) -> float:
+    t = similarity_threshold
+    return alpha * t * t / (max_query_norm * max_query_norm) * (1.0 - 2.0 ** -20) if t > 0 else 0.0
+
+
+def index_reduction_select(indices: Sequence[int], values: Sequence[float], df: Dict[int, int], lim: float) -> List[bool]:
+    """skip[i] = True when component i stays OUT of the index: the longest prefix, in (document frequency
+    descending, dim ascending) order, whose squared weights sum (left to right, fp64) to <= lim."""
+    order = sorted(range(len(indices)), key=lambda i: (-df[int(indices[i])], int(indices[i])))
+    skip = [False] * len(indices)
+    s = 0.0
+    for i in order:
+        s2 = s + float(values[i]) * float(values[i])
+        if not s2 <= lim:
+            break
+        s = s2
+        skip[i] = True
+    return skip
+
+
+class ReducedIndexPipeline:
+    """R1 scoring over the reduced index, batch by batch: returns pairs plus the two counters the library reports
+    with pruning on (postings visited / candidates touched through INDEXED components only)."""
+
+    def __init__(self, similarity_threshold: float, alpha: float = 0.8, max_query_norm: float = 1.0):
+        self.t = similarity_threshold
+        self.lim = index_reduction_limit(similarity_threshold, alpha, max_query_norm)
+        self.df: Dict[int, int] = {}
+        self.vectors: List[Tuple[List[int], List[float]]] = []
+        self.postings: Dict[int, List[int]] = {}            # dim -> ids of the vectors that INDEX it
+        self.n_unindexed = 0
+
+    def insert_batch(self, batch: Sequence[Tuple[Sequence[int], Sequence[float]]]):
+        base = len(self.vectors)
+        for idx, _ in batch:                                # document frequencies include the whole batch
+            for d in idx:
+                self.df[int(d)] = self.df.get(int(d), 0) + 1
+        for idx, val in batch:
+            skip = index_reduction_select(idx, val, self.df, self.lim)
+            self.n_unindexed += sum(skip)
+            vid = len(self.vectors)
+            self.vectors.append(([int(d) for d in idx], [float(x) for x in val]))
+            for d, sk in zip(idx, skip):
+                if not sk:
+                    self.postings.setdefault(int(d), []).append(vid)
+        pairs, postings, cands = {}, 0, 0
+        for k, (idx, val) in enumerate(batch):
+            q = base + k
+            touched = set()
+            for d in idx:
+                lst = self.postings.get(int(d), [])
+                postings += len(lst)
+                touched.update(lst)
+            touched.discard(q)
+            cands += len(touched)
+            qv = SparseVector(1 << 30, [int(d) for d in idx], [float(x) for x in val])
+            for c in touched:
+                cv = SparseVector(1 << 30, *self.vectors[c])
+                sim = calculate_similarity(cv, qv)
+                if sim >= self.t:
+                    pairs[(q, c)] = sim
+        return pairs, postings, cands

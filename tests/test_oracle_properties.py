@@ -125,3 +125,21 @@ def test_index_reduction_keeps_the_pair_set(t, alpha):
         red.insert_batch(np.array([0, 1]), np.array([0], np.int32), np.array([2.0]))      # norm promise broken
     with pytest.raises(ValueError):
         orc.Oracle(D, t, algo=orc.ALGO_FAITHFUL, pruning=True)
+
+
+@pytest.mark.parametrize("t,alpha", [(0.5, 0.8), (0.7, 0.5)])
+def test_index_reduction_c_oracle_against_python_restatement(t, alpha):
+    """two independent restatements of the reduction rule (C and pure Python) agree on pairs, similarities,
+    postings visited, candidates touched and the number of un-indexed components"""
+    import apss_b200
+    N, D = 400, 256
+    ip, ix, v = apss_b200.synth.generate(N, D, 12, seed=21).numpy()
+    c_or = orc.Oracle(D, t, algo=orc.ALGO_FAST, pruning=True, prune_alpha=alpha)
+    py = pyref.ReducedIndexPipeline(t, alpha)
+    for lo in range(0, N, 100):
+        hi = lo + 100
+        rc = c_or.insert_batch(ip[lo:hi + 1] - ip[lo], ix[ip[lo]:ip[hi]], v[ip[lo]:ip[hi]])
+        pairs, postings, cands = py.insert_batch([(ix[ip[i]:ip[i + 1]], v[ip[i]:ip[i + 1]]) for i in range(lo, hi)])
+        assert rc.pair_set() == pairs
+        assert (rc.postings_visited, rc.candidates_unique) == (postings, cands)
+    assert c_or.n_unindexed == py.n_unindexed > 0
