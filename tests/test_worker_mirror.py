@@ -20,8 +20,8 @@ def mk(conf=CONF, gpu=False, **over):
     return GpuIndexingWorkerActor(c, replyTo=out.append, engine=eng), out, apss_b200
 
 
-def scenario(gpu):
-    w, out, pkg = mk(gpu=gpu)
+def scenario(gpu, **over):
+    w, out, pkg = mk(gpu=gpu, **over)
     M = pkg.messages
     V = lambda d: M.SparkSparseVector.sparse(64, list(d.items()))
     w.receive(M.VectorIOMsg({("a", V({0: .6, 1: .8}))}))
@@ -120,5 +120,7 @@ def test_vector_text_format_roundtrip():
 
 
 @pytest.mark.gpu
-def test_worker_messages_gpu():
-    scenario(gpu=True)
+@pytest.mark.parametrize("pruning", [0, 2])
+def test_worker_messages_gpu(pruning):
+    # same messages, same SimilarityOutput with exact index reduction switched on through the config
+    scenario(gpu=True, **{"cpslab.allpair.gpu.pruning": pruning})
