@@ -526,6 +526,21 @@ def main():
     }
     if pruned is not None:
         line["pruned"] = pruned
+    try:
+        # the binding resource is on-chip: one shared-memory accumulator update per posting visited, measured against
+        # the micro-benchmarked peak of native u32 shared-memory atomic adds (random addresses, 16 warps per SM)
+        peak_upd = 2.547e12
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_probe_microbench_and_v1_sweep.json")) as f:
+                peak_upd = float(json.load(f)["microbench"]["atoms_u32_random_w16"])
+        except Exception:
+            pass
+        upd = tot["local_postings"] / (tot["score_ms"] * 1e-3) if tot["score_ms"] > 0 else 0.0
+        line["roofline"]["onchip"] = {"what": "accumulator updates/s per GPU (one per posting visited; dense dims go through FFMA instead)",
+                                      "achieved": upd, "peak": peak_upd, "frac": upd / peak_upd,
+                                      "peak_source": "measured ATOMS.ADD.U32 throughput, profiles/r01_probe_microbench_and_v1_sweep.json"}
+    except Exception:
+        pass
     if not args.no_cpu_baseline and not shard_gen:
         threads = host_threads()
         nq = args.cpu_queries or 2 * threads
