@@ -69,3 +69,48 @@ for frac in (0.5, 0.8, 0.9, 1.0):
     touched_set = set(zip(coo.row.tolist(), coo.col.tolist()))
     miss = sum(1 for r, c in zip(F.row[m].tolist(), F.col[m].tolist()) if (r, c) not in touched_set and qs[r] != c)
     print("true pairs not touched through the reduced index:", miss)
+
+# ---- would a position-based admission filter (L2AP's "remaining score" bound) shrink the candidate tables?
+# A pair (q, c) first met at c's indexed component k (components taken in descending weight) can only reach t if
+# |q| * sqrt(|c_U|^2 + sum_{indexed j with w_j <= w_k} w_j^2) >= t.  Count the touched pairs that pass.
+if True:
+    frac = 0.8
+    lim = frac * (t * t) * (1 - 2.0 ** -20)
+    unindexed = run <= lim
+    keep = ~unindexed
+    cu2 = np.bincount(r_s[unindexed], weights=sq[unindexed], minlength=N)
+    # per vector: indexed weights sorted descending and the mass of the components not heavier than each
+    ri, wi, di = r_s[keep], v_s[keep], ix_s[keep]
+    o2 = np.lexsort((-wi, ri))
+    ri, wi, di = ri[o2], wi[o2], di[o2]
+    cnt = np.bincount(ri, minlength=N); ptr = np.concatenate([[0], np.cumsum(cnt)])
+    csq = np.cumsum(wi * wi)
+    tot_row = csq[ptr[1:] - 1] - (csq[ptr[:-1]] - (wi * wi)[ptr[:-1]]) if len(wi) else np.zeros(N)
+    # suffix mass from position p (inclusive) in descending order
+    start_c = np.repeat(csq[ptr[:-1]] - (wi * wi)[ptr[:-1]], cnt)
+    suf = np.repeat(tot_row, cnt) - (csq - wi * wi - start_c)
+    # inverted (reduced) index with the suffix mass attached to every posting
+    oi = np.argsort(di, kind="stable")
+    pd, pr, ps = di[oi], ri[oi], suf[oi]
+    pptr = np.concatenate([[0], np.cumsum(np.bincount(pd, minlength=D))])
+    rng = np.random.default_rng(7)
+    qs = rng.choice(N, min(args.queries, 256), replace=False)
+    touched_n = admitted_n = 0
+    best = np.zeros(N)
+    for qi_ in qs:
+        a, b = ip[qi_], ip[qi_ + 1]
+        qn_ = float(np.sqrt(np.sum(v[a:b] ** 2)))
+        cands = []
+        for d in ix[a:b]:
+            s0, s1 = pptr[d], pptr[d + 1]
+            if s1 > s0:
+                np.maximum.at(best, pr[s0:s1], ps[s0:s1])        # the heaviest shared component has the largest suffix mass
+                cands.append(pr[s0:s1])
+        if not cands:
+            continue
+        cs_ = np.unique(np.concatenate(cands)); cs_ = cs_[cs_ != qi_]
+        touched_n += len(cs_)
+        admitted_n += int(np.sum(qn_ * np.sqrt(cu2[cs_] + best[cs_]) >= t))
+        best[cs_] = 0.0; best[qi_] = 0.0
+    print("---- position-based admission (alpha 0.8): touched %.0f per query, admitted by the remaining-score bound %.0f per query (%.1f%%)" % (
+        touched_n / len(qs), admitted_n / len(qs), 100.0 * admitted_n / max(touched_n, 1)))
