@@ -1,0 +1,158 @@
+// Drives apss_host::GpuIndexingWorkerActor / RegionRouter / ClientConnection like the reference's actors are
+// driven (same scenario as tests/test_worker_mirror.py).  Built twice by tests/test_cpp_host.py:
+//   -DUSE_ORACLE_ENGINE  against the CPU oracle (test double)          -- runs anywhere
+//   (default)            against libapss_b200.so through include/apss.h -- needs a GPU
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "apss_actor.hpp"
+#ifdef USE_ORACLE_ENGINE
+#include "oracle_engine.hpp"
+using Engine = OracleEngine;
+#else
+using Engine = apss_host::CApiEngine;
+#endif
+
+using namespace apss_host;
+
+static int failures = 0;
+#define CHECK(cond) do { if (!(cond)) { std::fprintf(stderr, "CHECK failed at line %d: %s\n", __LINE__, #cond); ++failures; } } while (0)
+
+static SparkSparseVector V(std::vector<std::pair<int32_t, double>> e, int size = 64) { return SparkSparseVector::sparse(size, std::move(e)); }
+
+static Engine* make_engine(int dim, double t, double idx_thr, bool as_built, int pruning) {
+#ifdef USE_ORACLE_ENGINE
+  (void)pruning;
+  return new Engine(dim, t, idx_thr, as_built);
+#else
+  return new Engine(dim, t, idx_thr, 0, as_built ? APSS_SEM_R0 : APSS_SEM_R1, pruning);
+#endif
+}
+
+static Config base_conf() {
+  return Config{{"cpslab.allpair.similarityThreshold", "0.5"}, {"cpslab.allpair.outputIODuration", "0"},
+                {"cpslab.allpair.benchmark.expDuration", "0"}, {"cpslab.allpair.vectorDim", "64"}, {"cpslab.allpair.indexThreshold", "0.0"}};
+}
+
+static void scenario(int pruning) {
+  Config conf = base_conf();
+  Engine* eng = make_engine(64, 0.5, 0.0, false, pruning);
+  std::vector<OutMessage> out;
+  GpuIndexingWorkerActor<Engine> w(conf, *eng, [&](const OutMessage& m) { out.push_back(m); });
+  w.receive(VectorIOMsg{{{"a", V({{0, .6}, {1, .8}})}}});
+  w.receive(VectorIOMsg{{{"b", V({{1, .8}, {2, .6}})}, {"c", V({{0, .6}, {1, .8}})}, {"tiny", V({{5, .1}})}}});
+  CHECK(out.size() == 2);
+  const auto& o0 = std::get<SimilarityOutput>(out[0]).output;
+  CHECK(o0.size() == 1 && o0.count("a") && o0.at("a").empty());
+  const auto& o1 = std::get<SimilarityOutput>(out[1]).output;
+  CHECK(o1.size() == 2 && o1.count("b") && o1.count("c"));              // "tiny" fails the admission filter: no entry
+  CHECK(o1.at("c").at("a") == .6 * .6 + .8 * .8 && o1.at("b").at("a") == .8 * .8);
+  CHECK(o1.at("b").at("c") == .8 * .8 && o1.at("c").at("b") == .8 * .8);  // in-batch pairs, both orders (IWA:125-132)
+  CHECK(std::get<SimilarityOutput>(out[0]).toString() == "---------------------------------a:\n");
+  CHECK(std::get<SimilarityOutput>(out[1]).toString() ==
+        "---------------------------------b:a,0.6400000000000001;c,0.6400000000000001;\n---------------------------------c:a,1.0;b,0.6400000000000001;\n");
+  // same external id is never paired with itself (IWA:91)
+  w.receive(VectorIOMsg{{{"a", V({{0, .6}, {1, .8}})}}});
+  const auto& o2 = std::get<SimilarityOutput>(out[2]).output;
+  CHECK(o2.at("a").count("a") == 0 && o2.at("a").size() == 2 && o2.at("a").count("b") && o2.at("a").count("c"));
+  // Test echo (IWA:145-147) and ReceiveTimeout freeze (IWA:143-144)
+  w.receive(Test{"ping"});
+  CHECK(std::get<Test>(out[3]) == Test{"ping"});
+  w.receive(ReceiveTimeout{});
+  w.receive(VectorIOMsg{{{"z1", V({{0, .6}, {1, .8}})}, {"z2", V({{0, .6}, {1, .8}})}}});
+  const auto& o4 = std::get<SimilarityOutput>(out[4]).output;
+  CHECK(o4.at("z1").count("z2") == 0 && o4.at("z1").count("a") == 1);
+  // a batch with a wrong-size vector is dropped whole, like the swallowed exception at IWA:135-137
+  const size_t n_before = out.size();
+  w.receive(VectorIOMsg{{{"bad", SparkSparseVector(32, {1}, {1.0})}}});
+  CHECK(out.size() == n_before);
+  delete eng;
+}
+
+static void buffered_output_and_router() {
+  Config conf = base_conf();
+  conf["cpslab.allpair.outputIODuration"] = "50";
+  Engine* eng = make_engine(64, 0.5, 0.0, false, 0);
+  std::vector<OutMessage> out;
+  GpuIndexingWorkerActor<Engine> w(conf, *eng, [&](const OutMessage& m) { out.push_back(m); });
+  w.receive(VectorIOMsg{{{"a", V({{0, 1.0}})}}});
+  w.receive(VectorIOMsg{{{"b", V({{0, 1.0}})}}});
+  CHECK(out.empty());                                   // buffered until the IOTicket (IWA:131-132)
+  w.receive(IOTicket{});
+  CHECK(out.size() == 1);
+  const auto& o = std::get<SimilarityOutput>(out[0]).output;
+  CHECK(o.size() == 1 && o.at("b").at("a") == 1.0);     // only non-empty results are buffered (IWA:115-119)
+  w.receive(IOTicket{});
+  CHECK(out.size() == 1);                               // cleared after the send (IWA:141)
+  delete eng;
+
+  // client -> router -> worker, timer-driven batching (WWA:164-183)
+  Config c2 = base_conf();
+  c2["cpslab.allpair.ioTriggerPeriod"] = "10";
+  Engine* e2 = make_engine(64, 0.5, 0.0, false, 0);
+  std::vector<OutMessage> out2;
+  GpuIndexingWorkerActor<Engine> w2(c2, *e2, [&](const OutMessage& m) { out2.push_back(m); });
+  RegionRouter<Engine> router(c2, w2);
+  LocalActorSystem<Engine> sys;
+  sys.registerRouter("127.0.0.1:2551", router);
+  ClientConnection<Engine> client({"127.0.0.1:2551"}, sys);
+  client.insertNewVector(std::vector<IdVector>{{"a", V({{0, 1.0}})}});
+  client.insertNewVector(std::vector<IdVector>{{"b", V({{0, 1.0}})}});
+  CHECK(out2.empty());
+  router.tell(IOTrigger{});
+  CHECK(out2.size() == 1);
+  const auto& ob = std::get<SimilarityOutput>(out2[0]).output;
+  CHECK(ob.at("a").at("b") == 1.0 && ob.at("b").at("a") == 1.0);     // one batch: both orders
+  // README form: vectors without ids
+  client.insertNewVector(std::vector<SparkSparseVector>{V({{0, 1.0}})});
+  router.tell(IOTrigger{});
+  CHECK(out2.size() == 2 && std::get<SimilarityOutput>(out2[1]).output.count("auto-0") == 1);
+  delete e2;
+}
+
+static void as_built_first_list_skip() {
+  // KAT-B: batch1 a={0:.6,1:.8}, batch2 b={1:.8,2:.6}: the only shared dim is b's first -> nothing as built
+  Config conf = base_conf();
+  conf["cpslab.allpair.gpu.semantics"] = "R0";
+  Engine* eng = make_engine(64, 0.5, 0.0, true, 0);
+  std::vector<OutMessage> out;
+  GpuIndexingWorkerActor<Engine> w(conf, *eng, [&](const OutMessage& m) { out.push_back(m); });
+  w.receive(VectorIOMsg{{{"a", V({{0, .6}, {1, .8}})}}});
+  w.receive(VectorIOMsg{{{"b", V({{1, .8}, {2, .6}})}}});
+  CHECK(std::get<SimilarityOutput>(out[1]).output.at("b").empty());
+  delete eng;
+  Engine* e2 = make_engine(64, 0.5, 0.0, true, 0);
+  std::vector<OutMessage> o2;
+  GpuIndexingWorkerActor<Engine> w2(conf, *e2, [&](const OutMessage& m) { o2.push_back(m); });
+  w2.receive(VectorIOMsg{{{"b", V({{1, .8}, {2, .6}})}}});
+  w2.receive(VectorIOMsg{{{"a", V({{0, .6}, {1, .8}})}}});      // reversed arrival: dim 1 is not a's first
+  CHECK(std::get<SimilarityOutput>(o2[1]).output.at("a").at("b") == .8 * .8);
+  delete e2;
+}
+
+static void formats() {
+  CHECK(java_double_to_string(1.0) == "1.0" && java_double_to_string(0.64) == "0.64" && java_double_to_string(1.25e-5) == "1.25E-5");
+  CHECK(java_double_to_string(1e7) == "1.0E7" && java_double_to_string(123456.789) == "123456.789" && java_double_to_string(0.001) == "0.001");
+  CHECK(V({{17, 0.25}, {3, 0.5}}, 1 << 20).toString() == "(1048576,[3,17],[0.5,0.25])");
+  bool threw = false;
+  try { SparkSparseVector(8, {3, 3}, {1.0, 1.0}); } catch (const std::invalid_argument&) { threw = true; }
+  CHECK(threw);
+  CHECK(scala_set_first({3, 17, 100, 1000, 65537, 200000}) == 200000 && scala_set_first({5, 10, 15, 20, 25, 30, 35}) == 5);   // SURVEY 8(a) examples
+  threw = false;
+  try { Config c; conf_required(c, "cpslab.allpair.vectorDim"); } catch (const std::out_of_range&) { threw = true; }
+  CHECK(threw);
+}
+
+int main(int argc, char** argv) {
+  const int pruning = argc > 1 ? std::atoi(argv[1]) : 0;
+  formats();
+  scenario(pruning);
+  buffered_output_and_router();
+  as_built_first_list_skip();
+  if (failures) { std::fprintf(stderr, "%d check(s) failed\n", failures); return 1; }
+  std::printf("actor scenario ok (pruning=%d)\n", pruning);
+  return 0;
+}
