@@ -114,3 +114,18 @@ if True:
         best[cs_] = 0.0; best[qi_] = 0.0
     print("---- position-based admission (alpha 0.8): touched %.0f per query, admitted by the remaining-score bound %.0f per query (%.1f%%)" % (
         touched_n / len(qs), admitted_n / len(qs), 100.0 * admitted_n / max(touched_n, 1)))
+
+# ---- the reference's own plan: per-dimension max weights (EPA:51-57, HBaseUpLoader.scala:113-129).  How much could
+# stay out of the index under  sum_{d in U} c[d] * maxw[d] < t  compared with the Cauchy-Schwarz bound (alpha -> 1)?
+if True:
+    maxw = np.zeros(D); np.maximum.at(maxw, ix, v)
+    mw_s = v_s * maxw[ix_s]
+    cmw = np.cumsum(mw_s)
+    start_mw = cmw[ip[:-1]] - mw_s[ip[:-1]]
+    run_mw = cmw - np.repeat(start_mw, np.diff(ip))
+    un_mw = run_mw < t
+    un_l2 = run <= (t * t) * (1 - 2.0 ** -20)
+    either = un_mw | un_l2
+    for name, m in (("max-weight bound", un_mw), ("Cauchy-Schwarz bound (alpha = 1)", un_l2), ("either", either)):
+        dfi = np.bincount(ix_s[~m], minlength=D)
+        print("---- %-34s un-indexed %.1f%% of components, postings visited %.3e" % (name, 100 * m.mean(), float(np.sum(df.astype(np.float64) * dfi))))
