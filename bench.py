@@ -14,6 +14,10 @@ stream, max over ranks.  `e2e`: the same call with pinned HOST buffers (H2D + pa
 the timed region).  `roofline`: 8 B x postings_visited / CUDA-event time of the scoring kernel against
 the measured HBM copy peak.  `cpu_baseline`: the oracle's restatement of the reference algorithm on
 a bounded sample, on this box's host cores.  --impl reference times that CPU path as its own arm.
+`roofline.onchip`: accumulator updates/s against the measured shared-memory atomic peak (what binds the
+kernel).  `pruned`: the same batches of the value phase through a second engine with exact index reduction
+(include/apss.h `pruning` = 2) -- identical pairs, counters of the reduced work, reported beside
+the parity-mode headline; --prune N makes it the main arm instead, --no-pruned-leg skips it.
 """
 from __future__ import annotations
 
