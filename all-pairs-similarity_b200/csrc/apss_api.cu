@@ -2,6 +2,7 @@
 // One handle = one index worker on one GPU (replaces IndexingWorkerActor, IWA:21-149).
 #include "apss.h"
 #include "apss_kernels.cuh"
+#include "apss_qmajor.cuh"
 
 #include <cub/cub.cuh>
 #include <cuda.h>   // driver types only; entry points are resolved at run time (no libcuda link)
@@ -178,6 +179,15 @@ struct apss_handle {
   DevBuf<uint8_t> q_skip; DevBuf<float> q_cu, q_nrm;
   DevBuf<unsigned long long> pr_keys_in, pr_keys_out, pr_vals_in, pr_vals_out;
   int64_t tot_skipped = 0;
+  // query-major scoring on the reduced index (prune_mode 3): LSM posting segments, oldest first
+  struct Seg { uint2* post = nullptr; int32_t* dir = nullptr; int64_t n_post = -1; int64_t cap_post = 0; int64_t row_lo = 0, row_hi = 0; };
+  std::vector<Seg> segs;
+  cudaMemPool_t pool = nullptr;
+  DevBuf<unsigned> sg_keys_in, sg_keys_out; DevBuf<unsigned long long> sg_vals_in;
+  DevBuf<int32_t> qm_cnt, qm_off; DevBuf<QmItem> qm_items;
+  int64_t merges = 0, merged_postings = 0;
+  int qm_cap = QM_CAP; size_t qm_items_cap0 = 0;     // test hooks: APSS_QM_CAP, APSS_QM_ITEMS_CAP
+  bool broken = false;       // a failure after the index was touched that could not be rolled back: every later call fails
   // query-block transposition (v2 kernel)
   DevBuf<unsigned long long> bt_keys_in, bt_keys_out, bt_vals_in, bt_vals_out, ud_key; DevBuf<int32_t> bt_flags, bt_pos, ud_dim, ud_start, bd_ptr;
   // outputs
@@ -210,6 +220,7 @@ struct apss_handle {
                                           "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+static constexpr int U16_MAX_NNZ = 60000;   // longest vector the packed-u16 tile kernel accepts (see transpose_query_blocks)
 static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
 template <int WARPS, int UNROLL>
@@ -403,8 +414,18 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
     if (cudaMemcpyAsync(h->maxw.p, cfg->max_weight, sizeof(double) * cfg->dim, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return bail(APSS_E_CUDA);
   }
   if (cfg->pruning) {
-    if ((cfg->pruning != 1 && cfg->pruning != 2) || algo != 3) return bail(APSS_E_INVALID);   // only the default scoring kernel applies the bound
+    if (cfg->pruning < 1 || cfg->pruning > 3 || algo != 3) return bail(APSS_E_INVALID);   // only the default scoring kernel applies the bound
     h->prune_mode = cfg->pruning;
+    if (cfg->pruning == 3) {     // posting segments come from a private stream-ordered pool (merges allocate and free)
+      cudaMemPoolProps pp{};
+      pp.allocType = cudaMemAllocationTypePinned; pp.handleTypes = cudaMemHandleTypeNone;
+      pp.location.type = cudaMemLocationTypeDevice; pp.location.id = h->device;
+      if (cudaMemPoolCreate(&h->pool, &pp) != cudaSuccess) { cudaGetLastError(); return bail(APSS_E_CUDA); }
+      unsigned long long keep = ~0ULL;
+      cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      { const char* e = getenv("APSS_QM_CAP"); if (e && atoi(e) >= 8 && atoi(e) <= QM_CAP) h->qm_cap = atoi(e); }
+      { const char* e = getenv("APSS_QM_ITEMS_CAP"); if (e && atoll(e) >= 1) h->qm_items_cap0 = (size_t)atoll(e); }
+    }
     if (cfg->pruning == 1 && (QB != 16 || warps != 16 || h->COLS != 4)) return bail(APSS_E_INVALID);   // tile kernel: default shape only
     { const char* cw = getenv("APSS_CAND_WARPS"); if (cw && (atoi(cw) == 16 || atoi(cw) == 24 || atoi(cw) == 32)) h->cand_warps = atoi(cw); }
     { const char* cs = getenv("APSS_CAND_SLICES"); if (cs && atoi(cs) >= 1 && atoi(cs) <= 256) h->cand_slices_env = atoi(cs); }
@@ -458,6 +479,11 @@ extern "C" void apss_destroy(apss_handle* h) {
   h->qdir.release(); h->heavy.release(); h->ifw_ptr.release(); h->ifw.release(); h->q_icnt.release(); h->q_iptr.release();
   h->df.release(); h->fwd_skip.release(); h->row_ub.release(); h->q_skip.release(); h->q_cu.release(); h->q_nrm.release();
   h->pr_keys_in.release(); h->pr_keys_out.release(); h->pr_vals_in.release(); h->pr_vals_out.release();
+  for (auto& sg : h->segs) { if (sg.post) cudaFreeAsync(sg.post, h->stream); if (sg.dir) cudaFreeAsync(sg.dir, h->stream); }
+  h->segs.clear();
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->pool) cudaMemPoolDestroy(h->pool);
+  h->sg_keys_in.release(); h->sg_keys_out.release(); h->sg_vals_in.release(); h->qm_cnt.release(); h->qm_off.release(); h->qm_items.release();
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->h_total) cudaFreeHost(h->h_total);
@@ -480,7 +506,7 @@ static int32_t prune_select(apss_handle* h, int32_t n, int32_t batch_nnz) {
   CK(h->pr_keys_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_keys_out.reserve(std::max(batch_nnz, 1), 0, s));
   CK(h->pr_vals_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_vals_out.reserve(std::max(batch_nnz, 1), 0, s));
   if (batch_nnz) {
-    k_df_update<<<cdiv(batch_nnz, 256), 256, 0, s>>>(batch_nnz, h->q_dim.p, h->df.p);
+    k_df_update<<<cdiv(batch_nnz, 256), 256, 0, s>>>(batch_nnz, h->q_dim.p, h->df.p, 1);
     CK(cudaGetLastError());
     k_rank_keys<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->df.p, h->pr_keys_in.p, h->pr_vals_in.p);
     CK(cudaGetLastError());
@@ -522,6 +548,29 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
     CK(h->fwd_skip.reserve(std::max<int64_t>(nnz_new, 1), nnz_old, s)); CK(h->row_ub.reserve(n_new, n_old, s));
     if (batch_nnz) CK(cudaMemcpyAsync(h->fwd_skip.p + nnz_old, h->q_skip.p, (size_t)batch_nnz, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(h->row_ub.p + n_old, h->q_cu.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+  }
+  if (h->prune_mode == 3) {     // query-major scoring: the batch becomes one new posting segment (merged after the call)
+    if (batch_nnz) {
+      if ((int)h->segs.size() >= QM_MAXSEG) return h->fail(APSS_E_STATE, "too many posting segments");
+      apss_handle::Seg sg; sg.cap_post = (int64_t)batch_nnz + 2; sg.row_lo = n_old; sg.row_hi = n_new;
+      CK(h->sg_keys_in.reserve(batch_nnz, 0, s)); CK(h->sg_keys_out.reserve(batch_nnz, 0, s)); CK(h->sg_vals_in.reserve(batch_nnz, 0, s));
+      CK(cudaMallocFromPoolAsync((void**)&sg.post, sizeof(uint2) * (size_t)sg.cap_post, h->pool, s));
+      { cudaError_t e_ = cudaMallocFromPoolAsync((void**)&sg.dir, sizeof(int32_t) * ((size_t)D + 1), h->pool, s);
+        if (e_ != cudaSuccess) { cudaFreeAsync(sg.post, s); return h->fail(APSS_E_NOMEM, "segment directory: %s", cudaGetErrorString(e_)); } }
+      h->segs.push_back(sg);       // from here on a failure is undone by drop_last_segment()
+      int dimbits = 1; while ((1LL << dimbits) < (int64_t)D + 1) ++dimbits;
+      k_seg_emit<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, n_old, h->q_ptr.p, h->q_dim.p, h->q_w.p, h->q_skip.p, D, h->sg_keys_in.p, h->sg_vals_in.p);
+      CK(cudaGetLastError());
+      size_t tb = 0;
+      unsigned long long* vout = reinterpret_cast<unsigned long long*>(sg.post);
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->sg_keys_in.p, h->sg_keys_out.p, h->sg_vals_in.p, vout, batch_nnz, 0, dimbits, s));
+      CK(h->cub_tmp.reserve(tb, 0, s));
+      CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->sg_keys_in.p, h->sg_keys_out.p, h->sg_vals_in.p, vout, batch_nnz, 0, dimbits, s));
+      k_seg_dir<<<cdiv((int64_t)D + 1, 256), 256, 0, s>>>(h->sg_keys_out.p, batch_nnz, D, sg.dir);
+      CK(cudaGetLastError()); h->kernel_launches += 5;
+    }
+    h->n_local = n_new; h->nnz = nnz_new; h->ntiles = 0;
+    return APSS_OK;
   }
   if (h->prune_mode == 2) {     // candidate-major scoring streams the forward store: there is no tile index to maintain
     CK(h->heavy.reserve(n_new, 0, s));
@@ -607,7 +656,11 @@ static int32_t transpose_query_blocks(apss_handle* h, int32_t n, int32_t batch_n
   // fixed-point scale: every dot product is <= max squared norm (Cauchy-Schwarz); keep 2x headroom
   const double bound = std::max(h->max_sq, 1e-300) * (1.0 + 1e-6);
   // (dense-head kernel: u16 accumulators, sums stay below 2^15 + one quantum per shared dim)
-  F = (int)std::floor(std::log2((h->algo == 3 ? 32768.0 : 2147483648.0) / bound));
+  // (every shared dimension adds an over-shoot of up to one quantum: max_sq * 2^F + max_nnz must stay below 2^16;
+  //  up to ~32 K components per vector this is the 2^15 headroom rule, beyond that the scale drops -- estimates only
+  //  ever err upwards, so a coarser scale costs verify work, never a pair)
+  F = h->algo == 3 ? (int)std::floor(std::log2(std::min(32768.0, 65535.0 - (double)h->max_nnz_seen - 1.0) / bound))
+                   : (int)std::floor(std::log2(2147483648.0 / bound));
   F = std::max(-100, std::min(100, F));
   const double ts = t * std::ldexp(1.0, F) * (1.0 - std::ldexp(1.0, h->algo == 3 ? -16 : -20));
   const double tmax = h->algo == 3 ? 65535.0 : 4294967295.0;
@@ -688,6 +741,89 @@ static int32_t score_candidate_major(apss_handle* h, int32_t n, int32_t batch_nn
   return APSS_OK;
 }
 
+// One scoring attempt of the query-major path on the reduced index: cut the batch's lists into pieces
+// (k_qm_count + scan + k_qm_emit), then k_score_qm.  h_total[1] receives the number of pieces needed.
+static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, int64_t q_local_base, const int64_t* d_qkey) {
+  cudaStream_t s = h->stream;
+  const double t = h->cfg.similarity_threshold;
+  h->h_total[1] = 0;
+  if (!h->n_local || !batch_nnz || h->segs.empty()) return APSS_OK;
+  SegList sl{}; sl.n = (int32_t)h->segs.size();
+  for (int k = 0; k < sl.n; ++k) { sl.post[k] = h->segs[k].post; sl.dir[k] = h->segs[k].dir; }
+  CK(h->qm_cnt.reserve((size_t)batch_nnz + 1, 0, s)); CK(h->qm_off.reserve((size_t)batch_nnz + 1, 0, s));
+  if (!h->qm_items.cap) CK(h->qm_items.reserve(h->qm_items_cap0 ? h->qm_items_cap0 : std::max<size_t>((size_t)batch_nnz * 2, (size_t)1 << 16), 0, s));
+  k_qm_count<<<cdiv((int64_t)batch_nnz + 1, 256), 256, 0, s>>>(batch_nnz, h->q_dim.p, sl, h->qm_cnt.p);
+  CK(cudaGetLastError());
+  size_t tb = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, h->qm_cnt.p, h->qm_off.p, batch_nnz + 1, s));
+  CK(h->cub_tmp.reserve(tb, 0, s));
+  CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tb, h->qm_cnt.p, h->qm_off.p, batch_nnz + 1, s));
+  QmArgs a{};
+  {   // u32 fixed point: every dot product is <= the largest squared norm (Cauchy-Schwarz)
+    const int Fc = std::max(-100, std::min(100, (int)std::floor(std::log2(2147483648.0 / (std::max(h->max_sq, 1e-300) * (1.0 + 1e-6))))));
+    a.scale = (float)std::ldexp(1.0, Fc); a.inv_scale = (float)std::ldexp(1.0, -Fc);
+  }
+  k_qm_emit<<<cdiv(batch_nnz, 256), 256, 0, s>>>(batch_nnz, h->q_dim.p, h->q_w.p, a.scale, sl, h->qm_off.p, h->qm_items.p, (long long)h->qm_items.cap);
+  CK(cudaGetLastError());
+  a.q_ptr = h->q_ptr.p; a.item_off = h->qm_off.p; a.items = h->qm_items.p; a.item_cap = (long long)h->qm_items.cap;
+  a.q_nrm = h->q_nrm.p; a.q_key = h->custom_keys ? d_qkey : nullptr; a.row_ub = h->row_ub.p; a.c_key = h->key.p;
+  a.n_rows = h->n_local; a.q_local_base = q_local_base; a.nq = n;
+  a.thr = (float)t; if ((double)a.thr > t) a.thr = std::nextafterf(a.thr, -INFINITY);
+  a.band1 = (float)(1.0 + (double)(h->max_nnz_seen + 8) * std::ldexp(1.0, -22));
+  {
+    const double cm = std::sqrt(std::max(h->prune_lim, 0.0)) * (1.0 + 1e-9);
+    a.cu_max = (float)cm; if ((double)a.cu_max < cm) a.cu_max = std::nextafterf(a.cu_max, INFINITY);
+  }
+  a.cap = h->qm_cap;
+  a.out_q = h->pf_q.p; a.out_c = h->pf_c.p; a.out_est = h->pf_est.p; a.out_cap = h->pf_q.cap;
+  a.counters = h->d_counters;
+  const size_t smem = (size_t)(2 * QM_TBL + QM_HOT) * sizeof(unsigned);
+  auto kern = h->custom_keys ? k_score_qm<1024, true> : k_score_qm<1024, false>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, h->smem_optin - 1024)));
+  kern<<<h->sm_count, 1024, smem, s>>>(a);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_total + 1, h->qm_off.p + batch_nnz, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  h->kernel_launches += 4; h->score_launches++;
+  return APSS_OK;
+}
+
+// LSM policy: after a committed append, the youngest segments are merged while the next older one is at most
+// twice their sum (every posting is copied ~3 times over the life of the index; a query term meets
+// O(log #batches) lists).  Stream-ordered: the caller does not wait for it.
+static int32_t merge_segments(apss_handle* h) {
+  cudaStream_t s = h->stream;
+  const int D = h->cfg.dim;
+  const int size = (int)h->segs.size();
+  if (size < 2) return APSS_OK;
+  int j = 1; int64_t sum = h->segs.back().n_post;
+  while (j < size) {
+    const int64_t prev = h->segs[size - 1 - j].n_post;
+    if (sum + prev > 0x7fff0000LL) break;                                  // directories are int32 per segment
+    if (prev > 2 * sum && size - j <= QM_MAXSEG - 8) break;
+    sum += prev; ++j;
+  }
+  if (j < 2) return APSS_OK;
+  apss_handle::Seg out; out.n_post = sum; out.cap_post = sum + 2;
+  out.row_lo = h->segs[size - j].row_lo; out.row_hi = h->segs.back().row_hi;
+  CK(cudaMallocFromPoolAsync((void**)&out.post, sizeof(uint2) * (size_t)out.cap_post, h->pool, s));
+  { cudaError_t e_ = cudaMallocFromPoolAsync((void**)&out.dir, sizeof(int32_t) * ((size_t)D + 1), h->pool, s);
+    if (e_ != cudaSuccess) { cudaFreeAsync(out.post, s); return h->fail(APSS_E_NOMEM, "merged segment directory: %s", cudaGetErrorString(e_)); } }
+  MergeSrc m{}; m.n = j;
+  for (int k = 0; k < j; ++k) { m.post[k] = h->segs[size - j + k].post; m.dir[k] = h->segs[size - j + k].dir; }
+  k_merge_dir<<<cdiv((int64_t)D + 1, 256), 256, 0, s>>>(D, m, out.dir);
+  for (int k = 0; k < j; ++k) {
+    const int64_t np = h->segs[size - j + k].n_post;
+    if (np > 0) k_merge_copy<<<cdiv(np, 256), 256, 0, s>>>(k, (int)np, D, m, out.dir, out.post);
+  }
+  { cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) { cudaFreeAsync(out.post, s); cudaFreeAsync(out.dir, s); return h->fail(APSS_E_CUDA, "segment merge: %s", cudaGetErrorString(e_)); } }
+  for (int k = 0; k < j; ++k) { cudaFreeAsync(h->segs[size - j + k].post, s); cudaFreeAsync(h->segs[size - j + k].dir, s); }
+  h->segs.resize(size - j);
+  h->segs.push_back(out);
+  h->kernel_launches += 1 + j; h->merges++; h->merged_postings += sum;
+  return APSS_OK;
+}
+
 // One scoring attempt of the tile kernels (K2/K3): the row kernel, the query-block kernel or the dense-head kernel.
 static int32_t score_tiles(apss_handle* h, int32_t n, int32_t batch_nnz, BlockArgs blk, int F, unsigned thr_int, int64_t q_local_base,
                            const int64_t* d_qkey) {
@@ -720,12 +856,57 @@ static int32_t score_tiles(apss_handle* h, int32_t n, int32_t batch_nnz, BlockAr
   return APSS_OK;
 }
 
+// What a batch may change on the host side of the handle; restored when the call fails after the index was touched.
+struct BatchTxn {
+  int64_t n_local, nnz, n_post, ntiles, next_id; size_t n_segs; int max_nnz_seen; double max_sq; bool custom_keys;
+  bool touched = false;      // index_append ran (forward store / tiles / segments may hold the batch)
+  bool df_updated = false;   // document frequencies include the batch
+  int32_t batch_nnz = 0;
+};
+
+static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const int64_t* indptr, const int32_t* indices, const double* values,
+                                 const int64_t* ext_keys, const int32_t* first_dim, uint32_t flags, apss_batch_result* out);
+
+// Undo a failed batch: the append-only stores (forward store, compact store, posting segments) are simply cut
+// back; the tile index rewrites its open tile in place, so there the handle is retired instead.
+static void rollback_batch(apss_handle* h, const BatchTxn& txn) {
+  const std::string why = h->err;
+  bool ok = cudaSetDevice(h->device) == cudaSuccess;
+  if (h->prune_mode != 2 && h->prune_mode != 3) ok = false;
+  if (ok && txn.df_updated && txn.batch_nnz) {
+    k_df_update<<<cdiv(txn.batch_nnz, 256), 256, 0, h->stream>>>(txn.batch_nnz, h->q_dim.p, h->df.p, -1);
+    ok = cudaGetLastError() == cudaSuccess;
+  }
+  while (h->segs.size() > txn.n_segs) {
+    if (h->segs.back().post) cudaFreeAsync(h->segs.back().post, h->stream);
+    if (h->segs.back().dir) cudaFreeAsync(h->segs.back().dir, h->stream);
+    h->segs.pop_back();
+  }
+  if (ok) ok = cudaStreamSynchronize(h->stream) == cudaSuccess;
+  h->n_local = txn.n_local; h->nnz = txn.nnz; h->n_post = txn.n_post; h->ntiles = txn.ntiles; h->next_id = txn.next_id;
+  h->custom_keys = txn.custom_keys;
+  h->last_n = -1; h->last_pairs = 0;
+  if (!ok) { h->broken = true; cudaGetLastError(); }
+  h->err = why + (ok ? " (batch rolled back: the index is unchanged)" : " (the index could not be rolled back: this handle is retired, destroy it)");
+}
+
 extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* indptr, const int32_t* indices, const double* values,
                                      const int64_t* ext_keys, const int32_t* first_dim, uint32_t flags, apss_batch_result* out) {
   if (!h) return APSS_E_INVALID;
+  if (h->broken) return h->fail(APSS_E_STATE, "handle retired after a failed batch that could not be rolled back; destroy it");
+  BatchTxn txn{h->n_local, h->nnz, h->n_post, h->ntiles, h->next_id, h->segs.size(), h->max_nnz_seen, h->max_sq, h->custom_keys};
+  const int32_t rc = insert_batch_impl(h, txn, n, indptr, indices, values, ext_keys, first_dim, flags, out);
+  if (rc != APSS_OK && txn.touched) rollback_batch(h, txn);
+  return rc;
+}
+
+static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const int64_t* indptr, const int32_t* indices, const double* values,
+                                 const int64_t* ext_keys, const int32_t* first_dim, uint32_t flags, apss_batch_result* out) {
   if (n < 0 || (n > 0 && (!indptr || (!indices && !values)))) return h->fail(APSS_E_INVALID, "null batch arrays");
   if (n > (1 << 24)) return h->fail(APSS_E_INVALID, "batch too large: at most 2^24 vectors per call");
   if (h->n_local + n > 0x7fffff00LL) return h->fail(APSS_E_INVALID, "shard full: internal ids are int32");
+  if (!((flags & APSS_BATCH_QUERY_ONLY) || h->frozen) && h->next_id + (int64_t)n > 0x7fffffffLL)
+    return h->fail(APSS_E_INVALID, "id space exhausted: internal ids are int32 (next_id %lld + %d vectors)", (long long)h->next_id, n);
   CK(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const bool dev_ptrs = flags & APSS_BATCH_DEVICE_PTRS;
@@ -780,7 +961,15 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     return h->fail(APSS_E_INPUT, h->h_counters[C_ERR] == 2 ? "indptr is not monotone / does not start at 0"
                                                            : "indices must be strictly increasing and < dim (SparseVector.scala:96-108)");
   }
+  if (h->h_counters[C_TOTNNZ] > 0x7fffff00ULL)     // q_cnt / q_ptr are int32 (the device-pointer entry has no host-side bound)
+    return h->fail(APSS_E_INVALID, "batch too large: at most 2^31 components per call");
   const int32_t batch_nnz = h->h_total[0];
+  // dense-head tile kernel: two u16 accumulators per word; a sum is < max_sq * 2^F + one quantum per shared
+  // dimension, so the longest vector bounds what the scale can absorb (see transpose_query_blocks)
+  if (h->algo == 3 && h->prune_mode < 2 && std::max(h->max_nnz_seen, (int)h->h_counters[C_MAXNNZ]) > U16_MAX_NNZ)
+    return h->fail(APSS_E_INPUT, "a vector keeps %d components after the value prune; the u16 tile kernel takes at most %d "
+                                 "(use kernel_variant 2 << 16, u32 accumulators, or pruning = 3)", (int)h->h_counters[C_MAXNNZ], U16_MAX_NNZ);
+  txn.batch_nnz = batch_nnz;
   res.n_rejected = (int32_t)h->h_counters[C_NREJ]; res.n_empty = (int32_t)h->h_counters[C_NEMPTY]; res.n_active = (int32_t)h->h_counters[C_NACTIVE];
   h->max_nnz_seen = std::max(h->max_nnz_seen, (int)h->h_counters[C_MAXNNZ]);
   {
@@ -799,17 +988,33 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   int64_t q_local_base = -1;
   if (!query_only) {
     q_local_base = h->n_local;
-    if (h->prune) { const int32_t rcp = prune_select(h, n, batch_nnz); if (rcp != APSS_OK) return rcp; }
+    if (h->prune) { txn.df_updated = batch_nnz > 0; txn.touched = true; const int32_t rcp = prune_select(h, n, batch_nnz); if (rcp != APSS_OK) return rcp; }
+    txn.touched = true;
     int32_t rc = index_append(h, n, batch_nnz, d_keys);
     if (rc != APSS_OK) return rc;
     h->next_id += n;
+    if (getenv("APSS_TEST_FAIL_AFTER_APPEND")) return h->fail(APSS_E_NOMEM, "injected failure after the index append (APSS_TEST_FAIL_AFTER_APPEND)");
   }
+  // commit of a successful indexing call (after the final synchronisation): skipped-component tally, size of the new
+  // posting segment, then the stream-ordered segment merges
+  auto commit_index = [&]() {
+    if (!h->prune || query_only) return;
+    const int64_t skipped = (int64_t)h->h_counters[C_SKIPPED];
+    h->tot_skipped += skipped; h->n_post = h->nnz - h->tot_skipped;
+    if (h->prune_mode == 3 && h->segs.size() > txn.n_segs) {
+      apss_handle::Seg& sg = h->segs.back();
+      sg.n_post = (int64_t)batch_nnz - skipped;
+      if (sg.n_post <= 0) { cudaFreeAsync(sg.post, s); cudaFreeAsync(sg.dir, s); h->segs.pop_back(); }
+      const std::string keep = h->err;
+      if (merge_segments(h) != APSS_OK) { cudaGetLastError(); h->err = keep; }     // left unmerged: the index stays valid
+    }
+  };
 
   if ((flags & APSS_BATCH_INDEX_ONLY) && !query_only) {
     CK(cudaEventRecord(h->ev_b1, s));
     if (h->prune) CK(cudaMemcpyAsync(h->h_counters + C_SKIPPED, h->d_counters + C_SKIPPED, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (h->prune) { h->tot_skipped += (int64_t)h->h_counters[C_SKIPPED]; h->n_post = h->nnz - h->tot_skipped; }
+    commit_index();
     float ms0 = 0.f; CK(cudaEventElapsedTime(&ms0, h->ev_b0, h->ev_b1)); res.device_ms = ms0;
     h->last_n = n; h->last_pairs = 0;
     if (out) *out = res;
@@ -835,15 +1040,18 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     plan_query_slices(h, n, &slices, &qsub);
     const int32_t rc = build_query_index(h, n, batch_nnz, slices, qsub);
     if (rc != APSS_OK) return rc;
+  } else if (h->prune_mode == 3) {
+    // the pieces are cut inside score_query_major (they depend on the segments only)
   } else if (h->algo != 1 && batch_nnz) {
     const int32_t rc = transpose_query_blocks(h, n, batch_nnz, &blk, &F, &thr_int);
     if (rc != APSS_OK) return rc;
   }
-  for (int attempt = 0; attempt < 3; ++attempt) {
+  for (int attempt = 0; attempt < 4; ++attempt) {
     CK(cudaMemsetAsync(h->d_counters, 0, 7 * sizeof(unsigned long long), s));   // keep the prefilter tallies
     CK(cudaMemsetAsync(h->d_counters + C_PHASE, 0, 8 * sizeof(unsigned long long), s));
     CK(cudaEventRecord(h->ev_s0, s));
-    const int32_t rcs = h->prune_mode == 2 ? score_candidate_major(h, n, batch_nnz, slices, qsub, q_local_base, d_qkey)
+    const int32_t rcs = h->prune_mode == 3 ? score_query_major(h, n, batch_nnz, q_local_base, d_qkey)
+                      : h->prune_mode == 2 ? score_candidate_major(h, n, batch_nnz, slices, qsub, q_local_base, d_qkey)
                                            : score_tiles(h, n, batch_nnz, blk, F, thr_int, q_local_base, d_qkey);
     if (rcs != APSS_OK) return rcs;
     CK(cudaEventRecord(h->ev_s1, s));
@@ -859,10 +1067,14 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
     CK(cudaMemcpyAsync(h->h_counters + C_PHASE, h->d_counters + C_PHASE, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     if (h->prune) CK(cudaMemcpyAsync(h->h_counters + C_SKIPPED, h->d_counters + C_SKIPPED, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (h->h_counters[C_PF] <= h->pf_q.cap) break;
-    if (attempt == 2) return h->fail(APSS_E_NOMEM, "pair buffer overflow persisted");
-    const size_t need = (size_t)h->h_counters[C_PF] + 1024;     // grow and replay
-    CK(h->pf_q.reserve(need, 0, s)); CK(h->pf_c.reserve(need, 0, s)); CK(h->pf_est.reserve(need, 0, s));
+    const bool items_short = h->prune_mode == 3 && (size_t)h->h_total[1] > h->qm_items.cap;
+    if (h->h_counters[C_PF] <= h->pf_q.cap && !items_short) break;
+    if (attempt == 3) return h->fail(APSS_E_NOMEM, "pair / piece buffer overflow persisted");
+    if (items_short) CK(h->qm_items.reserve((size_t)h->h_total[1] + (size_t)h->h_total[1] / 4 + 1024, 0, s));     // grow and replay
+    if (h->h_counters[C_PF] > h->pf_q.cap) {
+      const size_t need = (size_t)h->h_counters[C_PF] + 1024;
+      CK(h->pf_q.reserve(need, 0, s)); CK(h->pf_c.reserve(need, 0, s)); CK(h->pf_est.reserve(need, 0, s));
+    }
   }
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->ev_s0, h->ev_s1)); res.score_ms = ms;
@@ -873,7 +1085,7 @@ extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* i
   res.n_pairs = (int64_t)h->h_counters[C_FINAL];
   res.n_pairs_r1 = (int64_t)h->h_counters[C_R1];
   for (int k = 0; k < 8; ++k) h->phase_cycles[k] = (int64_t)h->h_counters[C_PHASE + k];
-  if (h->prune && !query_only) { h->tot_skipped += (int64_t)h->h_counters[C_SKIPPED]; h->n_post = h->nnz - h->tot_skipped; }
+  commit_index();
   res.work_items = (int64_t)((unsigned long long)h->ntiles * (unsigned long long)(h->algo == 1 ? n : (n + h->QB - 1) / h->QB));
   if (h->prune_mode == 2) {
     res.work_items = (int64_t)h->h_counters[C_HEAVY_TOT];      // (stored vector, query slice) pairs that took the heavy pass
@@ -931,8 +1143,8 @@ extern "C" int32_t apss_set_next_id(apss_handle* h, int64_t next_id) {
 extern "C" int32_t apss_get_stats(apss_handle* h, apss_stats* out) {
   if (!h || !out) return APSS_E_INVALID;
   apss_stats s{};
-  s.n_vectors = h->n_local; s.n_postings = h->n_post; s.n_tiles = h->ntiles;
-  s.bytes_postings = h->n_post * 8; s.bytes_directory = h->ntiles * ((int64_t)h->cfg.dim + 1) * 4;
+  s.n_vectors = h->n_local; s.n_postings = h->n_post; s.n_tiles = h->prune_mode == 3 ? (int64_t)h->segs.size() : h->ntiles;   // pruning = 3: posting segments
+  s.bytes_postings = h->n_post * 8; s.bytes_directory = s.n_tiles * ((int64_t)h->cfg.dim + 1) * 4;
   s.bytes_forward = h->nnz * 12 + (h->n_local + 1) * 8;
   s.tot_postings_visited = h->tot_postings; s.tot_candidates_unique = h->tot_cands; s.tot_pairs = h->tot_pairs; s.tot_prefilter = h->tot_pf;
   s.score_launches = h->score_launches; s.kernel_launches = h->kernel_launches; s.tot_score_ms = h->tot_score_ms;

@@ -42,6 +42,7 @@ enum Counter : int {
   C_SKIPPED = 12,  // components of this batch left out of the index by exact index reduction
   C_HEAVY = 13,    // candidate-major kernel: stored vectors deferred to the heavy pass (this launch)
   C_HEAVY_TOT = 14, // same, summed over the query slices of the batch
+  C_TOTNNZ = 15,   // components kept by the value prune, whole batch (64-bit: the per-vector counts are int32)
   C_PHASE = 16,    // 8 per-phase cycle totals of the dense kernel (thread 0 of every CTA)
   C_COUNT = 24
 };
@@ -103,6 +104,7 @@ __global__ void k_prefilter_count(int n, const int64_t* __restrict__ ptr, const 
   else if (kept == 0) { st = 1; atomicAdd(&counters[C_NEMPTY], 1ULL); }
   else {
     st = 2; atomicAdd(&counters[C_NACTIVE], 1ULL); atomicMax(&counters[C_MAXNNZ], (unsigned long long)kept);
+    atomicAdd(&counters[C_TOTNNZ], (unsigned long long)kept);
     atomicMax(&counters[C_MAXSQ], (unsigned long long)__double_as_longlong(sq));
   }
   status[v] = st; cnt[v] = kept;
@@ -144,9 +146,9 @@ __global__ void k_default_keys(int n, int64_t id_base, int64_t* __restrict__ key
 // dot(q, c restricted to U) <= |q| |c_U| <= sqrt(alpha) t < t, so a pair with dot >= t always shares an
 // indexed component, and the candidate test becomes  indexed part + |q| |c_U| >= t  (checked in the
 // scoring kernel's epilogue; the fp64 verify kernel then computes the full dot product as before).
-__global__ void k_df_update(int nnz, const int32_t* __restrict__ q_dim, int32_t* __restrict__ df) {
+__global__ void k_df_update(int nnz, const int32_t* __restrict__ q_dim, int32_t* __restrict__ df, int delta) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < nnz) atomicAdd(df + q_dim[p], 1);
+  if (p < nnz) atomicAdd(df + q_dim[p], delta);
 }
 
 // sort key (row, max_df - df): a stable sort keeps ascending dims among equal frequencies

@@ -65,6 +65,7 @@ def parse_args():
                     help="main arm with exact index reduction on (1 tile kernel, 2 candidate-major kernel); counters then count the reduced work")
     ap.add_argument("--prune-alpha", type=float, default=0.0)
     ap.add_argument("--no-pruned-leg", action="store_true", help="skip the extra 'pruned' measurement of the default run")
+    ap.add_argument("--pruned-mode", type=int, default=3, help="pruning mode of the 'pruned' leg (3 query-major posting-list kernel, 2 candidate-major)")
     ap.add_argument("--shard-gen", action="store_true", help="generate per-rank shards (default for heavy-tail configs)")
     ap.add_argument("--verbose", action="store_true", help="per-step timings on stderr")
     ap.add_argument("--profile-range", action="store_true",
@@ -430,7 +431,7 @@ def main():
     if not args.prune and not args.no_pruned_leg and not shard_gen:
         eng.close()
         del disp
-        eng2 = native.Index(D, t, device=local_rank, pruning=2, prune_alpha=args.prune_alpha,
+        eng2 = native.Index(D, t, device=local_rank, pruning=args.pruned_mode, prune_alpha=args.prune_alpha,
                             reserve_vectors=int((N + n_fresh * B) / world * 1.1) + 2 * B, reserve_nnz=int(total_nnz / world * 1.15) + (1 << 20))
         disp2 = ShardDispatcher(eng2, device=dev)
         for lo in range(0, N, B):
@@ -472,7 +473,7 @@ def main():
             w7 = time.time()
             pe = {"ms_per_step": ev6.elapsed_time(ev7) / K, "wall_ms_per_step": (w7 - w6) * 1e3 / K,
                   "pairs_per_sec": pe_pairs / (ev6.elapsed_time(ev7) * 1e-3), "pairs_identical_to_parity_run": pe_pairs == e_p}
-        pruned = {"kernel": "apss::k_score_cand (candidate-major, reduced index)", "ms_per_step": dt_pr / K * 1e3,
+        pruned = {"kernel": "apss::k_score_qm (query-major posting-list traversal, reduced index)" if args.pruned_mode == 3 else "apss::k_score_cand (candidate-major, reduced index)", "ms_per_step": dt_pr / K * 1e3,
                   "pairs_per_sec": p_tot["pairs"] / dt_pr, "pairs_identical_to_parity_run": p_tot["pairs"] == tot["pairs"],
                   "speedup_vs_parity_run": dt_value / dt_pr,
                   "equivalent_candidates_per_sec": tot["cands"] / dt_pr,

@@ -233,7 +233,7 @@ def test_pair_buffer_overflow_grows_and_replays(algo):
     assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_pruned_pair_buffer_overflow_and_zero_threshold(mode):
     """a low threshold with a tiny pair buffer: the reduced-index kernels replay after growing it; t = 0 keeps
     everything indexed (nothing may be left out when any shared dim makes a pair)"""
@@ -433,7 +433,7 @@ def test_keys_only_on_some_batches():
 
 # ---------------------------------------------------------------- exact index reduction
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("tile,batch,t,alpha", [(0, 2500, 0.6, 0.0), (256, 333, 0.6, 0.5), (1024, 4096, 0.4, 0.95),
                                                 (128, 7, 0.7, 0.0), (512, 1000, 0.9, 0.3)])
 def test_pruned_index_same_pairs_fewer_postings(tile, batch, t, alpha, mode):
@@ -460,7 +460,7 @@ def test_pruned_index_same_pairs_fewer_postings(tile, batch, t, alpha, mode):
     assert tot_pr * 2 < tot_full
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_pruned_index_query_only_keys_and_r0(mode):
     """frozen / query-only batches, duplicate external ids and the R0 post-filter on top of the reduced index"""
     N, D, t = 3000, 1 << 10, 0.5
@@ -487,7 +487,7 @@ def test_pruned_index_query_only_keys_and_r0(mode):
         assert_pairs_equal(gpu_pairs(g0, rg), ro.pair_set())
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_pruned_index_refuses_vectors_over_the_norm_promise(mode):
     n = native()
     g = n.Index(64, 0.5, pruning=mode)                       # max_query_norm defaults to 1
@@ -504,12 +504,12 @@ def test_pruned_index_refuses_vectors_over_the_norm_promise(mode):
     assert gpu_pairs(g5, rg) == {(1, 0): 25.0}
     for kv in (1 << 16, 2 << 16):                            # only the default scoring kernel applies the bound
         with pytest.raises(n.ApssError):
-            n.Index(64, 0.5, pruning=True, kernel_variant=kv)
+            n.Index(64, 0.5, pruning=mode, kernel_variant=kv)
     with pytest.raises(n.ApssError):
         n.Index(64, 0.5, pruning=True, prune_alpha=1.0)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_pruned_c2_shape(mode):
     """C2's shape (100 K x 2^16, t = 0.8) on a 30 K prefix: full pair-set parity, large work reduction"""
     import apss_b200
@@ -525,6 +525,43 @@ def test_pruned_c2_shape(mode):
         assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
         tf += ro.postings_visited; tp += rg.postings_visited
     assert o.totals()["pairs"] > 0 and tp * 20 < tf
+
+
+@pytest.mark.parametrize("cap,items_cap", [(0, 0), (64, 0), (700, 50), (8, 1)])
+def test_query_major_ranged_passes_merges_and_piece_replay(cap, items_cap, monkeypatch):
+    """pruning = 3: a dimension shared by every vector (too heavy to stay out of the index) gives every query a list as
+    long as the index: with the per-pass capacity lowered (APSS_QM_CAP) the query is scored in candidate-id ranges sized
+    by the counting walk (halved until they fit); a tiny piece buffer (APSS_QM_ITEMS_CAP) forces the grow-and-replay
+    path; small batches force segment merges; duplicate ids and in-batch pairs included"""
+    rng = np.random.default_rng(5)
+    N, D, t = 4000, 512, 0.5
+    rows = []
+    for i in range(N):
+        dims = rng.choice(np.arange(1, D), size=6, replace=False)
+        v = {int(d): float(x) for d, x in zip(dims, rng.uniform(0.05, 0.3, size=6))}
+        v[0] = 0.9
+        nrm = np.sqrt(sum(x * x for x in v.values()))
+        rows.append({d: x / nrm for d, x in v.items()})
+    keys = np.arange(N, dtype=np.int64); keys[5::11] = keys[4:-1:11]
+    if cap:
+        monkeypatch.setenv("APSS_QM_CAP", str(cap))
+    if items_cap:
+        monkeypatch.setenv("APSS_QM_ITEMS_CAP", str(items_cap))
+    n = native()
+    for use_keys in (False, True):
+        o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8, pruning=True)
+        g = n.Index(D, t, pruning=3)
+        for lo, hi in [(0, 1500), (1500, 1507), (1507, 1600), (1600, 3100), (3100, 3101), (3101, 4000)]:
+            csr = csr_from_dicts(rows[lo:hi])
+            kw_o = dict(keys=keys[lo:hi]) if use_keys else {}
+            kw_g = dict(ext_keys=keys[lo:hi]) if use_keys else {}
+            ro = o.insert_batch(*csr, **kw_o); rg = g.insert_batch(*csr, **kw_g)
+            assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+            assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+        st = g.stats()
+        assert st["n_postings"] == sum(len(r) for r in rows) - st["n_unindexed"] and 1 <= st["n_tiles"] <= 6
+        assert o.totals()["pairs"] > 1000
+        g.close()
 
 
 @pytest.mark.parametrize("slices", [0, 3, 16])
