@@ -184,9 +184,9 @@ struct apss_handle {
   std::vector<Seg> segs;
   cudaMemPool_t pool = nullptr;
   DevBuf<unsigned> sg_keys_in, sg_keys_out; DevBuf<unsigned long long> sg_vals_in;
-  DevBuf<int32_t> qm_cnt, qm_off; DevBuf<QmItem> qm_items;
+  DevBuf<unsigned long long> qm_cnt, qm_off; DevBuf<QmItem> qm_items;
   int64_t merges = 0, merged_postings = 0;
-  int qm_cap = QM_CAP; size_t qm_items_cap0 = 0;     // test hooks: APSS_QM_CAP, APSS_QM_ITEMS_CAP
+  int qm_cap = QM_CAP, qm_nt = 1024; size_t qm_items_cap0 = 0; bool qm_pipe = true; DevBuf<int32_t> qm_deferred;     // test hooks: APSS_QM_CAP, APSS_QM_ITEMS_CAP
   bool broken = false;       // a failure after the index was touched that could not be rolled back: every later call fails
   // query-block transposition (v2 kernel)
   DevBuf<unsigned long long> bt_keys_in, bt_keys_out, bt_vals_in, bt_vals_out, ud_key; DevBuf<int32_t> bt_flags, bt_pos, ud_dim, ud_start, bd_ptr;
@@ -406,7 +406,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   h->ctas_per_sm = ctas; h->seg_cap = seg_cap;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(APSS_E_CUDA);
   if (cudaMalloc(&h->d_counters, C_COUNT * sizeof(unsigned long long)) != cudaSuccess) return bail(APSS_E_NOMEM);
-  if (cudaMallocHost(&h->h_counters, C_COUNT * sizeof(unsigned long long)) != cudaSuccess) return bail(APSS_E_NOMEM);
+  if (cudaMallocHost(&h->h_counters, (C_COUNT + 2) * sizeof(unsigned long long)) != cudaSuccess) return bail(APSS_E_NOMEM);
   if (cudaMallocHost(&h->h_total, sizeof(int32_t) * 4) != cudaSuccess) return bail(APSS_E_NOMEM);
   cudaEventCreate(&h->ev_b0); cudaEventCreate(&h->ev_b1); cudaEventCreate(&h->ev_s0); cudaEventCreate(&h->ev_s1);
   if (cfg->max_weight) {
@@ -424,6 +424,8 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
       unsigned long long keep = ~0ULL;
       cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
       { const char* e = getenv("APSS_QM_CAP"); if (e && atoi(e) >= 8 && atoi(e) <= QM_CAP) h->qm_cap = atoi(e); }
+      { const char* e = getenv("APSS_QM_NT"); if (e && atoi(e) == 512) h->qm_nt = 512; }
+      { const char* e = getenv("APSS_QM_PIPE"); if (e && atoi(e) == 0) h->qm_pipe = false; }      // measurement / tests: ranged kernel only
       { const char* e = getenv("APSS_QM_ITEMS_CAP"); if (e && atoll(e) >= 1) h->qm_items_cap0 = (size_t)atoll(e); }
     }
     if (cfg->pruning == 1 && (QB != 16 || warps != 16 || h->COLS != 4)) return bail(APSS_E_INVALID);   // tile kernel: default shape only
@@ -483,7 +485,7 @@ extern "C" void apss_destroy(apss_handle* h) {
   h->segs.clear();
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->pool) cudaMemPoolDestroy(h->pool);
-  h->sg_keys_in.release(); h->sg_keys_out.release(); h->sg_vals_in.release(); h->qm_cnt.release(); h->qm_off.release(); h->qm_items.release();
+  h->sg_keys_in.release(); h->sg_keys_out.release(); h->sg_vals_in.release(); h->qm_cnt.release(); h->qm_off.release(); h->qm_items.release(); h->qm_deferred.release();
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->h_total) cudaFreeHost(h->h_total);
@@ -552,7 +554,7 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
   if (h->prune_mode == 3) {     // query-major scoring: the batch becomes one new posting segment (merged after the call)
     if (batch_nnz) {
       if ((int)h->segs.size() >= QM_MAXSEG) return h->fail(APSS_E_STATE, "too many posting segments");
-      apss_handle::Seg sg; sg.cap_post = (int64_t)batch_nnz + 2; sg.row_lo = n_old; sg.row_hi = n_new;
+      apss_handle::Seg sg; sg.cap_post = (int64_t)batch_nnz + 64;      // a lane may read up to one 1 KB window past a list sg.row_lo = n_old; sg.row_hi = n_new;
       CK(h->sg_keys_in.reserve(batch_nnz, 0, s)); CK(h->sg_keys_out.reserve(batch_nnz, 0, s)); CK(h->sg_vals_in.reserve(batch_nnz, 0, s));
       CK(cudaMallocFromPoolAsync((void**)&sg.post, sizeof(uint2) * (size_t)sg.cap_post, h->pool, s));
       { cudaError_t e_ = cudaMallocFromPoolAsync((void**)&sg.dir, sizeof(int32_t) * ((size_t)D + 1), h->pool, s);
@@ -746,7 +748,7 @@ static int32_t score_candidate_major(apss_handle* h, int32_t n, int32_t batch_nn
 static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, int64_t q_local_base, const int64_t* d_qkey) {
   cudaStream_t s = h->stream;
   const double t = h->cfg.similarity_threshold;
-  h->h_total[1] = 0;
+  h->h_counters[C_ITEMS] = 0;
   if (!h->n_local || !batch_nnz || h->segs.empty()) return APSS_OK;
   SegList sl{}; sl.n = (int32_t)h->segs.size();
   for (int k = 0; k < sl.n; ++k) { sl.post[k] = h->segs[k].post; sl.dir[k] = h->segs[k].dir; }
@@ -777,12 +779,32 @@ static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, i
   a.cap = h->qm_cap;
   a.out_q = h->pf_q.p; a.out_c = h->pf_c.p; a.out_est = h->pf_est.p; a.out_cap = h->pf_q.cap;
   a.counters = h->d_counters;
-  const size_t smem = (size_t)(2 * QM_TBL + QM_HOT) * sizeof(unsigned);
-  auto kern = h->custom_keys ? k_score_qm<1024, true> : k_score_qm<1024, false>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, h->smem_optin - 1024)));
-  kern<<<h->sm_count, 1024, smem, s>>>(a);
+  CK(h->qm_deferred.reserve((size_t)n, 0, s));
+  a.deferred = h->qm_deferred.p; a.deferred_cap = n;
+  CK(cudaMemsetAsync(h->d_counters + C_HEAVY, 0, 2 * sizeof(unsigned long long), s));      // deferred count, ranged-kernel cursor
+  if (h->qm_pipe) {
+    // producer / consumer kernel for the queries that fit one table pass; the others land on the deferred list
+    QmArgs ap = a; ap.cap = std::min(a.cap, QP_CAP);
+    auto kern = h->custom_keys ? k_score_qm_pipe<true> : k_score_qm_pipe<false>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QP_SMEM));
+    kern<<<h->sm_count, 1024, QP_SMEM, s>>>(ap);
+    CK(cudaGetLastError());
+    a.from_list = 1; h->kernel_launches++;
+  }
+  if (h->qm_nt == 512) {          // two CTAs per SM, half the table each
+    a.cap = std::min(a.cap, QM_CAP2);
+    const size_t smem = (size_t)(2 * QM_TBL2 + QM_HOT) * sizeof(unsigned);
+    auto kern = h->custom_keys ? k_score_qm<512, QM_TBL2, true> : k_score_qm<512, QM_TBL2, false>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<h->sm_count * 2, 512, smem, s>>>(a);
+  } else {
+    const size_t smem = (size_t)(2 * QM_TBL + QM_HOT) * sizeof(unsigned);
+    auto kern = h->custom_keys ? k_score_qm<1024, QM_TBL, true> : k_score_qm<1024, QM_TBL, false>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, h->smem_optin - 1024)));
+    kern<<<h->sm_count, 1024, smem, s>>>(a);
+  }
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(h->h_total + 1, h->qm_off.p + batch_nnz, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_counters + C_ITEMS, h->qm_off.p + batch_nnz, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   h->kernel_launches += 4; h->score_launches++;
   return APSS_OK;
 }
@@ -803,7 +825,7 @@ static int32_t merge_segments(apss_handle* h) {
     sum += prev; ++j;
   }
   if (j < 2) return APSS_OK;
-  apss_handle::Seg out; out.n_post = sum; out.cap_post = sum + 2;
+  apss_handle::Seg out; out.n_post = sum; out.cap_post = sum + 64;
   out.row_lo = h->segs[size - j].row_lo; out.row_hi = h->segs.back().row_hi;
   CK(cudaMallocFromPoolAsync((void**)&out.post, sizeof(uint2) * (size_t)out.cap_post, h->pool, s));
   { cudaError_t e_ = cudaMallocFromPoolAsync((void**)&out.dir, sizeof(int32_t) * ((size_t)D + 1), h->pool, s);
@@ -1067,10 +1089,11 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
     CK(cudaMemcpyAsync(h->h_counters + C_PHASE, h->d_counters + C_PHASE, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     if (h->prune) CK(cudaMemcpyAsync(h->h_counters + C_SKIPPED, h->d_counters + C_SKIPPED, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    const bool items_short = h->prune_mode == 3 && (size_t)h->h_total[1] > h->qm_items.cap;
+    const size_t items_need = h->prune_mode == 3 ? (size_t)(h->h_counters[C_ITEMS] >> 36) : 0;
+    const bool items_short = items_need > h->qm_items.cap;
     if (h->h_counters[C_PF] <= h->pf_q.cap && !items_short) break;
     if (attempt == 3) return h->fail(APSS_E_NOMEM, "pair / piece buffer overflow persisted");
-    if (items_short) CK(h->qm_items.reserve((size_t)h->h_total[1] + (size_t)h->h_total[1] / 4 + 1024, 0, s));     // grow and replay
+    if (items_short) CK(h->qm_items.reserve(items_need + items_need / 4 + 1024, 0, s));     // grow and replay
     if (h->h_counters[C_PF] > h->pf_q.cap) {
       const size_t need = (size_t)h->h_counters[C_PF] + 1024;
       CK(h->pf_q.reserve(need, 0, s)); CK(h->pf_c.reserve(need, 0, s)); CK(h->pf_est.reserve(need, 0, s));
@@ -1150,7 +1173,7 @@ extern "C" int32_t apss_get_stats(apss_handle* h, apss_stats* out) {
   s.score_launches = h->score_launches; s.kernel_launches = h->kernel_launches; s.tot_score_ms = h->tot_score_ms;
   for (int k = 0; k < 8; ++k) s.phase_cycles[k] = h->phase_cycles[k];
   s.frozen = h->frozen; s.tile_vectors = h->CR; s.warps_per_cta = h->WARPS; s.sm_count = h->sm_count;
-  s.n_unindexed = h->tot_skipped;
+  s.n_unindexed = h->tot_skipped; s.segment_merges = h->merges; s.merged_postings = h->merged_postings; s.n_devices = 1;
   *out = s;
   return APSS_OK;
 }

@@ -43,8 +43,9 @@ enum Counter : int {
   C_HEAVY = 13,    // candidate-major kernel: stored vectors deferred to the heavy pass (this launch)
   C_HEAVY_TOT = 14, // same, summed over the query slices of the batch
   C_TOTNNZ = 15,   // components kept by the value prune, whole batch (64-bit: the per-vector counts are int32)
+  C_ITEMS = 25,    // host mirror only: (pieces << 36 | postings) of the batch, query-major kernel
   C_PHASE = 16,    // 8 per-phase cycle totals of the dense kernel (thread 0 of every CTA)
-  C_COUNT = 24
+  C_COUNT = 24     // device counters; the pinned host mirror has C_COUNT + 2 words
 };
 
 static constexpr unsigned FULL = 0xffffffffu;

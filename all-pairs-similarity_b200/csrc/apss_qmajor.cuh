@@ -11,8 +11,8 @@
 //              merged by per-dimension concatenation (k_merge_dir / k_merge_copy: a streaming copy, no sort),
 //              so a query term meets O(log(#batches)) lists.  "Appended in place on insert": nothing older
 //              than the merged suffix is ever rewritten.
-//   per batch  k_qm_count / scan / k_qm_emit cut every (query term, segment) list into PIECES of <= QM_PIECE
-//              postings: (pointer, length, query weight * 2^F), contiguous per query.
+//   per batch  k_qm_count / scan / k_qm_emit cut every (query term, segment) list into PIECES of <= 64
+//              postings (one 128-bit load per lane): (pointer, length, query weight * 2^F), contiguous per query.
 //   scoring    k_score_qm: persistent, ONE CTA PER QUERY at a time.  The warps take the query's pieces
 //              round-robin and stream them with 128-bit loads (two postings per lane, 512 B..1 KB per warp
 //              instruction, coalesced); every posting is accumulated into a shared-memory open-addressing
@@ -33,11 +33,12 @@
 
 namespace apss {
 
-static constexpr int QM_PIECE = 128;      // postings per piece
 static constexpr int QM_MAXSEG = 40;      // segments a handle may hold (LSM: ~log2(#batches) in practice)
 static constexpr int QM_HOT = 2048;       // hot-list capacity per pass (slots); more => full scan of the table
-static constexpr int QM_TBL = 26624;      // table slots (keys + values = 208 KB of shared memory)
+static constexpr int QM_TBL = 26624;      // table slots, one 1024-thread CTA per SM (keys + values = 208 KB of shared memory)
 static constexpr int QM_CAP = 14336;      // list entries scored per pass (load factor <= 0.54)
+static constexpr int QM_TBL2 = 13056;     // two 512-thread CTAs per SM: half the table each
+static constexpr int QM_CAP2 = 7040;
 
 struct QmItem { unsigned long long post; int32_t len; float wqs; };      // 16 B
 static_assert(sizeof(QmItem) == 16, "QmItem is read with one 128-bit load");
@@ -102,30 +103,47 @@ __global__ void k_merge_copy(int src, int n_post, int D, const MergeSrc m, const
 
 // ------------------------------------------------------------------ per batch: the pieces of every query
 
-// thread per query term: pieces of its lists over all segments
-__global__ void k_qm_count(int nnz, const int32_t* __restrict__ q_dim, const SegList sl, int32_t* __restrict__ cnt) {
+// A piece is at most one 128-bit load per lane: it never crosses a 1 KB-aligned window of 64 postings counted from the
+// 16-byte pair its list starts in.  A list [a, b) that starts on the upper half of a pair (a odd; segment buffers are
+// 256-byte aligned) gets a first piece of <= 63 postings, every other piece starts on a pair boundary and has <= 64.
+__device__ __forceinline__ int qm_pieces(int a, int b) {
+  const int len = b - a;
+  if (len <= 0) return 0;
+  const int first = min(len, 64 - (a & 1));
+  return 1 + (len - first + 63) / 64;
+}
+
+// thread per query term: (pieces << 36 | postings) of its lists over all segments; ONE 64-bit scan then yields both
+// the piece offsets and the per-query posting totals
+__global__ void k_qm_count(int nnz, const int32_t* __restrict__ q_dim, const SegList sl, unsigned long long* __restrict__ cnt) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > nnz) return;
-  int c = 0;
+  unsigned long long c = 0;
   if (t < nnz) {
     const int d = q_dim[t];
-    for (int s = 0; s < sl.n; ++s) { const int len = __ldg(sl.dir[s] + d + 1) - __ldg(sl.dir[s] + d); c += (len + QM_PIECE - 1) / QM_PIECE; }
+    for (int s = 0; s < sl.n; ++s) {
+      const int a = __ldg(sl.dir[s] + d), b = __ldg(sl.dir[s] + d + 1);
+      c += ((unsigned long long)qm_pieces(a, b) << 36) + (unsigned long long)(b - a);
+    }
   }
   cnt[t] = c;
 }
 
 __global__ void k_qm_emit(int nnz, const int32_t* __restrict__ q_dim, const float* __restrict__ q_w, float scale, const SegList sl,
-                          const int32_t* __restrict__ off, QmItem* __restrict__ items, long long cap) {
+                          const unsigned long long* __restrict__ off, QmItem* __restrict__ items, long long cap) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nnz) return;
-  long long o = off[t];
-  if (o == off[t + 1]) return;
+  long long o = (long long)(off[t] >> 36);
+  if (o == (long long)(off[t + 1] >> 36)) return;
   const int d = q_dim[t];
   const float wqs = q_w[t] * scale;
   for (int s = 0; s < sl.n; ++s) {
     const int a = __ldg(sl.dir[s] + d), b = __ldg(sl.dir[s] + d + 1);
-    for (int p = a; p < b; p += QM_PIECE, ++o)
-      if (o < cap) { QmItem it; it.post = (unsigned long long)(sl.post[s] + p); it.len = min(QM_PIECE, b - p); it.wqs = wqs; items[o] = it; }
+    for (int p = a; p < b; ++o) {
+      const int len = min(b - p, 64 - (p & 1));
+      if (o < cap) { QmItem it; it.post = (unsigned long long)(sl.post[s] + p); it.len = len; it.wqs = wqs; items[o] = it; }
+      p += len;
+    }
   }
 }
 
@@ -133,7 +151,7 @@ __global__ void k_qm_emit(int nnz, const int32_t* __restrict__ q_dim, const floa
 
 struct QmArgs {
   const int32_t* q_ptr;          // pruned batch CSR
-  const int32_t* item_off;       // [batch_nnz + 1] piece offsets per query term
+  const unsigned long long* item_off;   // [batch_nnz + 1] per query term: (piece offset << 36 | posting offset)
   const QmItem* items; long long item_cap;
   const float* q_nrm; const int64_t* q_key;
   const float* row_ub; const int64_t* c_key;
@@ -146,6 +164,8 @@ struct QmArgs {
   int32_t cap;                   // list entries scored per pass (QM_CAP; tests lower it to reach the ranged passes)
   int32_t* out_q; int32_t* out_c; float* out_est; unsigned long long out_cap;
   unsigned long long* counters;
+  int32_t* deferred; int32_t deferred_cap;   // queries the pipelined kernel left to the ranged kernel (count in C_HEAVY)
+  int32_t from_list;             // k_score_qm: 0 = take every query from the cursor, 1 = take the deferred list
 };
 
 template <int NT>
@@ -161,33 +181,39 @@ __device__ __forceinline__ long long qm_block_sum(long long v, long long* red, i
   return s;
 }
 
-template <int NT, bool DUPKEYS>
-__global__ void __launch_bounds__(NT, 1) k_score_qm(const QmArgs a) {
+static constexpr int QM_G = 4;            // pieces a warp keeps in flight (independent 128-bit loads per lane)
+
+template <int NT, int TBL, bool DUPKEYS>
+__global__ void __launch_bounds__(NT, 2048 / NT / 2 * 1) k_score_qm(const QmArgs a) {
   extern __shared__ __align__(16) unsigned qm_smem[];
   unsigned* keys = qm_smem;
-  unsigned* vals = qm_smem + QM_TBL;
-  int* hot = reinterpret_cast<int*>(qm_smem + 2 * QM_TBL);
+  unsigned* vals = qm_smem + TBL;
+  int* hot = reinterpret_cast<int*>(qm_smem + 2 * TBL);
   __shared__ long long red[NT / 32];
   __shared__ int s_q;
   __shared__ unsigned s_hot_n;
   constexpr int NW = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid * 4; i < 2 * QM_TBL; i += NT * 4) *reinterpret_cast<uint4*>(qm_smem + i) = make_uint4(0, 0, 0, 0);
+  for (int i = tid * 4; i < 2 * TBL; i += NT * 4) *reinterpret_cast<uint4*>(qm_smem + i) = make_uint4(0, 0, 0, 0);
   unsigned long long n_post = 0; unsigned n_cand = 0;
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_q = (int)atomicAdd(&a.counters[C_WORK], 1ULL);
+    if (tid == 0) {
+      if (a.from_list) {
+        const unsigned long long k = atomicAdd(&a.counters[C_HEAVY_TOT], 1ULL);
+        s_q = k < min(a.counters[C_HEAVY], (unsigned long long)a.deferred_cap) ? a.deferred[k] : a.nq;
+      } else s_q = (int)atomicAdd(&a.counters[C_WORK], 1ULL);
+    }
     __syncthreads();
     const int q = s_q;
     if (q >= a.nq) break;
     const int t0 = __ldg(a.q_ptr + q), t1 = __ldg(a.q_ptr + q + 1);
     if (t0 == t1) continue;
-    const long long i0 = __ldg(a.item_off + t0), i1 = min((long long)__ldg(a.item_off + t1), a.item_cap);
+    const unsigned long long o0 = __ldg(a.item_off + t0), o1 = __ldg(a.item_off + t1);
+    const long long i0 = (long long)(o0 >> 36), i1 = min((long long)(o1 >> 36), a.item_cap);
     if (i0 >= i1) continue;
-    long long mine = 0;
-    for (long long i = i0 + tid; i < i1; i += NT) mine += __ldg(&a.items[i].len);
-    const long long total = qm_block_sum<NT>(mine, red, tid);
+    const long long total = (long long)((o1 & 0xfffffffffULL) - (o0 & 0xfffffffffULL));
     if (tid == 0) n_post += (unsigned long long)total;
     const float qn = __ldg(a.q_nrm + q);
     const unsigned self = a.q_local_base >= 0 ? (unsigned)(a.q_local_base + q) : 0xffffffffu;
@@ -196,47 +222,77 @@ __global__ void __launch_bounds__(NT, 1) k_score_qm(const QmArgs a) {
     // smallest fixed-point sum a candidate of this query needs before the exact test can pass (0: test them all)
     unsigned thr_fix = 0;
     {
-      const double em = ((double)a.thr - (double)a.cu_max * (double)qn * (1.0 + 1e-6)) / (double)a.band1;
-      if (em > 0.0) thr_fix = (unsigned)fmin(floor(em * (double)a.scale * (1.0 - 1e-6)), 4294967295.0);
+      const float em = (a.thr - a.cu_max * qn * 1.000001f) / a.band1;
+      if (em > 0.f) thr_fix = (unsigned)fminf(floorf(em * a.scale * 0.99999f), 4294967040.f);
     }
     const bool scan_all = DUPKEYS || thr_fix == 0;
+    // the query's pieces, a contiguous share per warp
+    const int per = (int)((i1 - i0 + NW - 1) / NW);
+    const long long w_lo = i0 + (long long)warp * per, w_hi = min(i1, w_lo + per);
 
-    // one pass: candidates with lo <= id < hi (ranged) or all of them
+    // one pass: candidates with lo <= id < hi (ranged) or all of them; count_only: how many entries the range holds
     auto walk = [&](const bool ranged, const bool count_only, const unsigned lo, const unsigned hi, const unsigned size) -> long long {
       long long cnt = 0;
-      for (long long i = i0 + warp; i < i1; i += NW) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(a.items + i));          // same address on every lane
-        const unsigned long long pp = ((unsigned long long)raw.y << 32) | raw.x;
-        const int len = (int)raw.z; const float wqs = __uint_as_float(raw.w);
-        if (ranged) {       // ids ascend inside a list: skip a piece that lies outside the range
-          const uint2* p2 = reinterpret_cast<const uint2*>(pp);
-          if (__ldg(&p2[len - 1].x) < lo || __ldg(&p2[0].x) >= hi) continue;
-        }
-        const int odd = (int)((pp >> 3) & 1ULL);                                       // list starts on the upper half of a 16-byte pair
-        const uint4* p4 = reinterpret_cast<const uint4*>(pp - 8ULL * odd);
-        for (int j0 = -odd; j0 < len; j0 += 64) {
-          const int j = j0 + 2 * lane;
-          if (j + 1 < 0 || j >= len) continue;
-          const uint4 v = ld_stream4(p4 + ((j + odd) >> 1));
+      for (long long base = w_lo; base < w_hi; base += 32) {
+        const int nd = (int)min(32LL, w_hi - base);
+        uint4 desc = make_uint4(0, 0, 0, 0);
+        if (lane < nd) desc = __ldg(reinterpret_cast<const uint4*>(a.items + base + lane));      // one descriptor per lane
+        for (int g = 0; g < nd; g += QM_G) {
+          uint4 v[QM_G]; int jj[QM_G]; int ln[QM_G]; float ws[QM_G];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const unsigned c = u ? v.z : v.x; const float w = __uint_as_float(u ? v.w : v.y);
-            if (j + u < 0 || j + u >= len || c == self) continue;
-            if (ranged && (c < lo || c >= hi)) continue;
-            if (count_only) { ++cnt; continue; }
-            const unsigned contrib = __float2uint_ru(__fmul_ru(w, wqs));
-            const unsigned k = c + 1u;
-            unsigned slot = __umulhi(c * 0x9E3779B1u, size);
-            for (;;) {
-              const unsigned old = atomicCAS(keys + slot, 0u, k);
-              if (old == 0u) { ++n_cand; break; }
-              if (old == k) break;
-              if (++slot == size) slot = 0;
+          for (int k = 0; k < QM_G; ++k) {                     // QM_G independent loads in flight
+            const int src = min(g + k, 31);
+            const unsigned plo = __shfl_sync(FULL, desc.x, src), phi = __shfl_sync(FULL, desc.y, src);
+            ln[k] = (g + k < nd) ? (int)__shfl_sync(FULL, desc.z, src) : 0;
+            ws[k] = __uint_as_float(__shfl_sync(FULL, desc.w, src));
+            const unsigned long long pp = ((unsigned long long)phi << 32) | plo;
+            const int odd = (int)((pp >> 3) & 1ULL);           // the list starts on the upper half of a 16-byte pair
+            jj[k] = 2 * lane - odd;
+            v[k] = make_uint4(0, 0, 0, 0);
+            if (jj[k] + 1 >= 0 && jj[k] < ln[k]) v[k] = ld_stream4(reinterpret_cast<const uint4*>(pp - 8ULL * odd) + lane);
+          }
+          unsigned cc[2 * QM_G], slot[2 * QM_G], contrib[2 * QM_G], old[2 * QM_G]; bool on[2 * QM_G];
+#pragma unroll
+          for (int k = 0; k < QM_G; ++k)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int e = 2 * k + u;
+              cc[e] = u ? v[k].z : v[k].x;
+              const float w = __uint_as_float(u ? v[k].w : v[k].y);
+              on[e] = jj[k] + u >= 0 && jj[k] + u < ln[k] && cc[e] != self;
+              if (ranged) on[e] = on[e] && cc[e] >= lo && cc[e] < hi;
+              contrib[e] = __float2uint_ru(__fmul_ru(w, ws[k]));
+              slot[e] = __umulhi(cc[e] * 0x9E3779B1u, size);
             }
-            const unsigned prev = atomicAdd(vals + slot, contrib);
-            if (!scan_all && prev < thr_fix && prev + contrib >= thr_fix) {
-              const unsigned e = atomicAdd(&s_hot_n, 1u);
-              if (e < (unsigned)QM_HOT) hot[e] = (int)slot;
+          if (count_only) {
+#pragma unroll
+            for (int e = 0; e < 2 * QM_G; ++e) cnt += on[e];
+            continue;
+          }
+#pragma unroll
+          for (int e = 0; e < 2 * QM_G; ++e) { old[e] = 0u; if (on[e]) old[e] = atomicCAS(keys + slot[e], 0u, cc[e] + 1u); }
+#pragma unroll
+          for (int e = 0; e < 2 * QM_G; ++e) {
+            if (!on[e]) continue;
+            const unsigned k1 = cc[e] + 1u;
+            if (old[e] != 0u && old[e] != k1) {               // occupied by another candidate: linear probing
+              unsigned sl_ = slot[e];
+              for (;;) {
+                if (++sl_ == size) sl_ = 0;
+                const unsigned o = atomicCAS(keys + sl_, 0u, k1);
+                if (o == 0u || o == k1) { old[e] = o; break; }
+              }
+              slot[e] = sl_;
+            }
+            n_cand += old[e] == 0u;
+          }
+#pragma unroll
+          for (int e = 0; e < 2 * QM_G; ++e) {
+            if (!on[e]) continue;
+            const unsigned prev = atomicAdd(vals + slot[e], contrib[e]);
+            if (!scan_all && prev < thr_fix && prev + contrib[e] >= thr_fix) {
+              const unsigned h = atomicAdd(&s_hot_n, 1u);
+              if (h < (unsigned)QM_HOT) hot[h] = (int)slot[e];
             }
           }
         }
@@ -254,7 +310,7 @@ __global__ void __launch_bounds__(NT, 1) k_score_qm(const QmArgs a) {
       }
     };
     auto pass = [&](const bool ranged, const unsigned lo, const unsigned hi, const long long entries) {
-      unsigned size = (unsigned)min((long long)QM_TBL, max(256LL, (2 * entries + 31) & ~31LL));
+      const unsigned size = (unsigned)min((long long)TBL, max(256LL, (3 * entries + 31) & ~31LL));
       if (tid == 0) s_hot_n = 0u;
       __syncthreads();
       const unsigned cand0 = n_cand;
@@ -279,10 +335,10 @@ __global__ void __launch_bounds__(NT, 1) k_score_qm(const QmArgs a) {
       while (lo < a.n_rows) {
         long long width = (long long)((double)a.cap * 0.7 * (double)a.n_rows / (double)total);
         long long hi = min((long long)a.n_rows, lo + max(1LL, width));
-        long long cnt = qm_block_sum<NT>(walk(true, true, (unsigned)lo, (unsigned)hi, 0u), red, tid);
+        long long cnt = qm_block_sum<NT>(walk(true, true, (unsigned)lo, (unsigned)hi, 1u), red, tid);
         while (cnt > a.cap && hi - lo > a.cap) {
           hi = lo + (hi - lo) / 2;
-          cnt = qm_block_sum<NT>(walk(true, true, (unsigned)lo, (unsigned)hi, 0u), red, tid);
+          cnt = qm_block_sum<NT>(walk(true, true, (unsigned)lo, (unsigned)hi, 1u), red, tid);
         }
         if (cnt) pass(true, (unsigned)lo, (unsigned)hi, min(cnt, hi - lo));
         lo = hi;
@@ -294,6 +350,255 @@ __global__ void __launch_bounds__(NT, 1) k_score_qm(const QmArgs a) {
   for (int o = 16; o > 0; o >>= 1) nc += __shfl_down_sync(FULL, nc, o);
   if (lane == 0 && nc) atomicAdd(&a.counters[C_CANDS], nc);
   if (tid == 0 && n_post) atomicAdd(&a.counters[C_POSTINGS], n_post);
+}
+
+// ------------------------------------------------------------------ the pipelined kernel (bulk-async producer / consumers)
+
+// k_score_qm above pays a chain of dependent global round trips per query (cursor -> q_ptr -> offsets -> piece
+// descriptors -> postings) with the whole CTA in lock step.  Here one PRODUCER warp runs ahead of the 31 CONSUMER
+// warps: it walks the queries, and for every stage of the ring it (a) loads up to QP_SP piece descriptors, (b) posts
+// the stage's byte count on the stage's mbarrier (arrive.expect_tx) and (c) issues one cp.async.bulk per piece -- the
+// 16-byte aligned window of <= 512 B holding the piece -- straight into the stage's shared-memory slots.  Consumers
+// wait on the full barrier, read their pieces with one LDS.128 per lane, accumulate into the hash table exactly as
+// k_score_qm does, and release the stage through the empty barrier.  A query's last stage triggers the consumer-only
+// epilogue (hot list, clear) behind a named barrier while the producer is already staging the next query.  Queries
+// whose lists exceed one table pass are appended to the deferred list for k_score_qm's ranged passes.
+static constexpr int QP_NCW = 31;                 // consumer warps
+static constexpr int QP_SP = 2 * QP_NCW;          // pieces per stage (two per consumer warp)
+static constexpr int QP_STAGES = 2;
+static constexpr int QP_SLOT = 512;               // bytes per piece slot
+static constexpr int QP_STAGE_BYTES = QP_SP * QP_SLOT;
+static constexpr int QP_TBL = 19712;              // table slots: 232448 - ring - hot list - metadata, in 8-byte slots
+static constexpr int QP_CAP = 10752;              // entries per query handled here (load factor <= 0.55)
+static constexpr int QP_F_FIRST = 1, QP_F_LAST = 2, QP_F_END = 4;
+
+struct QpHdr { int q, np, flags, total; float qn; int pad; long long qkey; };      // 32 B per stage
+static constexpr size_t QP_SMEM = (size_t)2 * QP_TBL * 4 + (size_t)QM_HOT * 4 + (size_t)QP_STAGES * QP_STAGE_BYTES +
+                                  (size_t)QP_STAGES * QP_SP * 8 + (size_t)QP_STAGES * sizeof(QpHdr) + (size_t)QP_STAGES * 16;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "QP_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra QP_DONE_%=;\n\t"
+      "bra QP_WAIT_%=;\n\t"
+      "QP_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(QP_NCW * 32) : "memory"); }
+
+template <bool DUPKEYS>
+__global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
+  extern __shared__ __align__(128) unsigned char qp_smem[];
+  unsigned* keys = reinterpret_cast<unsigned*>(qp_smem);
+  unsigned* vals = keys + QP_TBL;
+  int* hot = reinterpret_cast<int*>(vals + QP_TBL);
+  unsigned char* ring = reinterpret_cast<unsigned char*>(hot + QM_HOT);                  // QP_STAGES x QP_STAGE_BYTES, 128-byte aligned
+  uint2* meta = reinterpret_cast<uint2*>(ring + (size_t)QP_STAGES * QP_STAGE_BYTES);     // per piece: (len | odd << 16, weight bits)
+  QpHdr* hdr = reinterpret_cast<QpHdr*>(meta + QP_STAGES * QP_SP);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(hdr + QP_STAGES);    // full[QP_STAGES], empty[QP_STAGES]
+  __shared__ unsigned s_hot_n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid * 4; i < 2 * QP_TBL; i += 1024 * 4) *reinterpret_cast<uint4*>(keys + i) = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    s_hot_n = 0u;
+    for (int s = 0; s < QP_STAGES; ++s) { mbar_init(smem_u32(bars + s), 1u); mbar_init(smem_u32(bars + QP_STAGES + s), (unsigned)QP_NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ------------------------------------------------ producer
+    int stage = 0; unsigned phase = 0; unsigned long long n_post = 0;
+    auto next_stage = [&]() { if (++stage == QP_STAGES) { stage = 0; phase ^= 1u; } };
+    for (;;) {
+      int q = 0;
+      if (lane == 0) q = (int)atomicAdd(&a.counters[C_WORK], 1ULL);
+      q = __shfl_sync(FULL, q, 0);
+      if (q >= a.nq) break;
+      const int t0 = __ldg(a.q_ptr + q), t1 = __ldg(a.q_ptr + q + 1);
+      if (t0 == t1) continue;
+      const unsigned long long o0 = __ldg(a.item_off + t0), o1 = __ldg(a.item_off + t1);
+      const long long i0 = (long long)(o0 >> 36), i1 = min((long long)(o1 >> 36), a.item_cap);
+      if (i0 >= i1) continue;
+      const long long total = (long long)((o1 & 0xfffffffffULL) - (o0 & 0xfffffffffULL));
+      if (total > a.cap) {                                     // too long for one table pass: the ranged kernel takes it
+        if (lane == 0) { const unsigned long long k = atomicAdd(&a.counters[C_HEAVY], 1ULL); if (k < (unsigned long long)a.deferred_cap) a.deferred[k] = q; }
+        continue;
+      }
+      n_post += (unsigned long long)total;
+      const float qn = __ldg(a.q_nrm + q);
+      long long qkey = 0;
+      if (DUPKEYS) qkey = __ldg(a.q_key + q);
+      for (long long base = i0; base < i1; base += QP_SP) {
+        const int np = (int)min((long long)QP_SP, i1 - base);
+        uint4 d[2]; unsigned bytes[2] = {0u, 0u}; unsigned sum = 0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {                          // descriptors first: they do not depend on the ring
+          const int k = lane + 32 * r;
+          d[r] = make_uint4(0, 0, 0, 0);
+          if (k < np) {
+            d[r] = __ldg(reinterpret_cast<const uint4*>(a.items + base + k));
+            bytes[r] = ((((d[r].x >> 3) & 1u) + d[r].z) * 8u + 15u) & ~15u;
+            sum += bytes[r];
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        mbar_wait(smem_u32(bars + QP_STAGES + stage), phase ^ 1u);          // the consumers have released this stage
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int k = lane + 32 * r;
+          if (k < np) meta[stage * QP_SP + k] = make_uint2(d[r].z | (((d[r].x >> 3) & 1u) << 16), d[r].w);
+        }
+        if (lane == 0) {
+          QpHdr hh; hh.q = q; hh.np = np; hh.total = (int)total; hh.qn = qn; hh.pad = 0; hh.qkey = qkey;
+          hh.flags = (base == i0 ? QP_F_FIRST : 0) | (base + QP_SP >= i1 ? QP_F_LAST : 0);
+          hdr[stage] = hh;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(smem_u32(bars + stage), sum);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int k = lane + 32 * r;
+          if (k < np) {
+            const unsigned long long pp = ((unsigned long long)d[r].y << 32) | d[r].x;
+            bulk_g2s(smem_u32(ring + (size_t)stage * QP_STAGE_BYTES + (size_t)k * QP_SLOT), reinterpret_cast<const void*>(pp & ~15ULL), bytes[r], smem_u32(bars + stage));
+          }
+        }
+        next_stage();
+      }
+    }
+    // no more queries: one empty END stage
+    mbar_wait(smem_u32(bars + QP_STAGES + stage), phase ^ 1u);
+    if (lane == 0) {
+      QpHdr hh; hh.q = a.nq; hh.np = 0; hh.total = 0; hh.qn = 0.f; hh.pad = 0; hh.qkey = 0; hh.flags = QP_F_END;
+      hdr[stage] = hh;
+      mbar_arrive(smem_u32(bars + stage));
+      if (n_post) atomicAdd(&a.counters[C_POSTINGS], n_post);
+    }
+    return;
+  }
+
+  // -------------------------------------------------- consumers
+  const int cw = warp - 1, ctid = tid - 32;
+  constexpr int CT = QP_NCW * 32;
+  int stage = 0; unsigned phase = 0; unsigned n_cand = 0;
+  unsigned size = 256u, thr_fix = 0u, self = 0xffffffffu; bool scan_all = true; float qn = 0.f; long long qkey = 0; int q = 0;
+  for (;;) {
+    mbar_wait(smem_u32(bars + stage), phase);
+    const QpHdr hh = hdr[stage];
+    if (hh.flags & QP_F_END) break;
+    if (hh.flags & QP_F_FIRST) {
+      q = hh.q; qn = hh.qn; qkey = hh.qkey;
+      size = (unsigned)min((long long)QP_TBL, max(256LL, (3LL * hh.total + 31) & ~31LL));
+      self = a.q_local_base >= 0 ? (unsigned)(a.q_local_base + q) : 0xffffffffu;
+      const float em = (a.thr - a.cu_max * qn * 1.000001f) / a.band1;
+      thr_fix = em > 0.f ? (unsigned)fminf(floorf(em * a.scale * 0.99999f), 4294967040.f) : 0u;
+      scan_all = DUPKEYS || thr_fix == 0u;
+    }
+    {
+      uint4 v[2]; int jj[2], ln[2]; float ws[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int k = cw + QP_NCW * r;
+        v[r] = make_uint4(0, 0, 0, 0); jj[r] = 0; ln[r] = 0; ws[r] = 0.f;
+        if (k < hh.np) {
+          const uint2 m = meta[stage * QP_SP + k];
+          const int odd = (int)(m.x >> 16);
+          ln[r] = (int)(m.x & 0xffffu); ws[r] = __uint_as_float(m.y);
+          jj[r] = 2 * lane - odd;
+          if (jj[r] + 1 >= 0 && jj[r] < ln[r])
+            v[r] = *reinterpret_cast<const uint4*>(ring + (size_t)stage * QP_STAGE_BYTES + (size_t)k * QP_SLOT + (size_t)lane * 16);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bars + QP_STAGES + stage));      // the postings are in registers: release the stage
+      unsigned cc[4], slot[4], contrib[4], old[4]; bool on[4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int e = 2 * r + u;
+          cc[e] = u ? v[r].z : v[r].x;
+          const float w = __uint_as_float(u ? v[r].w : v[r].y);
+          on[e] = jj[r] + u >= 0 && jj[r] + u < ln[r] && cc[e] != self;
+          contrib[e] = __float2uint_ru(__fmul_ru(w, ws[r]));
+          slot[e] = __umulhi(cc[e] * 0x9E3779B1u, size);
+        }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { old[e] = 0u; if (on[e]) old[e] = atomicCAS(keys + slot[e], 0u, cc[e] + 1u); }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (!on[e]) continue;
+        const unsigned k1 = cc[e] + 1u;
+        if (old[e] != 0u && old[e] != k1) {                   // occupied by another candidate: linear probing
+          unsigned sl_ = slot[e];
+          for (;;) {
+            if (++sl_ == size) sl_ = 0;
+            const unsigned o = atomicCAS(keys + sl_, 0u, k1);
+            if (o == 0u || o == k1) { old[e] = o; break; }
+          }
+          slot[e] = sl_;
+        }
+        if (!DUPKEYS) n_cand += old[e] == 0u;                 // (with caller keys: counted in the scan, same-key candidates do not count)
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (!on[e]) continue;
+        const unsigned prev = atomicAdd(vals + slot[e], contrib[e]);
+        if (!scan_all && prev < thr_fix && prev + contrib[e] >= thr_fix) {
+          const unsigned h = atomicAdd(&s_hot_n, 1u);
+          if (h < (unsigned)QM_HOT) hot[h] = (int)slot[e];
+        }
+      }
+    }
+    if (hh.flags & QP_F_LAST) {                                  // consumer-only epilogue of the query
+      auto test_emit = [&](const unsigned k, const unsigned vv) {
+        const long long c = (long long)k - 1;
+        if (DUPKEYS) { if (__ldg(a.c_key + c) == qkey) return; ++n_cand; }
+        const float est = __uint2float_ru(vv) * a.inv_scale;
+        const float ub = __fmul_ru(__ldg(a.row_ub + c), qn);
+        if (__fmaf_ru(est, a.band1, ub) >= a.thr) {
+          const unsigned long long o = atomicAdd(&a.counters[C_PF], 1ULL);
+          if (o < a.out_cap) { a.out_q[o] = q; a.out_c[o] = (int32_t)c; a.out_est[o] = est; }
+        }
+      };
+      consumer_bar();
+      const unsigned nh = s_hot_n;
+      if (scan_all || nh > (unsigned)QM_HOT) {
+        for (unsigned i = ctid; i < size; i += CT) { const unsigned k = keys[i]; if (k) test_emit(k, vals[i]); }
+      } else {
+        for (unsigned e = ctid; e < nh; e += CT) { const int s = hot[e]; test_emit(keys[s], vals[s]); }
+      }
+      consumer_bar();
+      for (unsigned i = ctid * 4; i < size; i += CT * 4) {
+        *reinterpret_cast<uint4*>(keys + i) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(vals + i) = make_uint4(0, 0, 0, 0);
+      }
+      if (ctid == 0) s_hot_n = 0u;
+      consumer_bar();
+    }
+    if (++stage == QP_STAGES) { stage = 0; phase ^= 1u; }
+  }
+  unsigned long long nc = n_cand;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nc += __shfl_down_sync(FULL, nc, o);
+  if (lane == 0 && nc) atomicAdd(&a.counters[C_CANDS], nc);
 }
 
 }  // namespace apss

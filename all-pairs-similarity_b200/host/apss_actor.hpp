@@ -103,6 +103,7 @@ using IdVector = std::pair<std::string, SparkSparseVector>;     // (String id, v
 
 struct VectorIOMsg { std::vector<IdVector> vectors; };                                  // MSG:13
 struct SparseVectorWrapper { std::set<int32_t> indices; IdVector sparseVector; };       // SparseVectorWrapper.scala:9
+struct DataPacket { int32_t shardId; std::vector<SparseVectorWrapper> vectors; };      // MSG:16
 struct IndexData { std::vector<SparseVectorWrapper> vectors; };                         // MSG:18
 struct IOTicket {};                                                                     // MSG:39
 struct IOTrigger {};
@@ -164,11 +165,17 @@ inline int32_t scala_set_first(const std::vector<int32_t>& dims) {
 // One apss_handle.  Throws std::runtime_error with the library's text on any non-zero status: there is no fallback.
 class CApiEngine {
  public:
-  CApiEngine(int dim, double similarity_threshold, double index_threshold, int device, int semantics, int pruning = 0) {
+  CApiEngine(int dim, double similarity_threshold, double index_threshold, int device, int semantics, int pruning = 0,
+             const std::vector<int>& devices = {}) {
     apss_config cfg{};
     cfg.struct_size = (int32_t)sizeof cfg;
     cfg.dim = dim; cfg.similarity_threshold = similarity_threshold; cfg.index_threshold = index_threshold;
     cfg.device = device; cfg.semantics = semantics; cfg.pruning = pruning;
+    if (!devices.empty()) {                       // the GPUs that share the index: id-range shards below the C ABI
+      if (devices.size() > APSS_MAX_DEVICES) throw std::invalid_argument("too many devices");
+      cfg.n_devices = (int32_t)devices.size(); cfg.device = devices[0];
+      for (size_t i = 0; i < devices.size(); ++i) cfg.device_ids[i] = devices[i];
+    }
     const int32_t rc = apss_create(&cfg, &h_);
     if (rc != APSS_OK) throw std::runtime_error("apss_create failed: status " + std::to_string(rc));
   }
@@ -219,9 +226,13 @@ class GpuIndexingWorkerActor {
 
   // ---- IWA:122-148
   void receive(const IndexData& m) {            // wrappers carry admitted, pruned vectors (EPA:97, WWA:192-194)
-    std::vector<IdVector> vs;
-    for (const auto& w : m.vectors) vs.push_back(w.sparseVector);
-    handle_batch(vs, /*skip_admit=*/true);
+    std::vector<IdVector> vs; std::vector<int32_t> firsts;
+    for (const auto& w : m.vectors) {
+      vs.push_back(w.sparseVector);
+      // as built, the skipped first posting list (IWA:89 + IWA:106-107) is the first element of the WRAPPER's Set (IWA:102)
+      if (as_built) { std::vector<int32_t> d(w.indices.begin(), w.indices.end()); std::sort(d.begin(), d.end()); firsts.push_back(scala_set_first(d)); }
+    }
+    handle_batch(vs, /*skip_admit=*/true, as_built ? &firsts : nullptr);
   }
   void receive(const VectorIOMsg& m) { handle_batch(m.vectors, /*skip_admit=*/false); }
   void receive(IOTicket) {                                                   // IWA:138-142
@@ -234,7 +245,8 @@ class GpuIndexingWorkerActor {
   void receive(const Test& t) { reply(t); }                                  // IWA:145-147
 
   // buildInvertedIndex + querySimilarItems (IWA:61-111) for one batch; returns outputSimSet
-  std::map<std::string, std::map<std::string, double>> query_and_index(const std::vector<IdVector>& vectors, bool skip_admit) {
+  std::map<std::string, std::map<std::string, double>> query_and_index(const std::vector<IdVector>& vectors, bool skip_admit,
+                                                                       const std::vector<int32_t>* firsts = nullptr) {
     std::map<std::string, std::map<std::string, double>> out;
     if (vectors.empty()) return out;
     const int32_t n = (int32_t)vectors.size();
@@ -249,13 +261,19 @@ class GpuIndexingWorkerActor {
     }
     const int64_t base = (int64_t)ids_.size();
     std::vector<int64_t> keys((size_t)n);
-    for (int32_t i = 0; i < n; ++i) {           // String ids never cross the ABI: key = internal id of the first occurrence
+    // String ids never cross the ABI: key = internal id of the first occurrence.  Nothing is recorded in first_of_ / ids_
+    // until the engine has accepted the batch (a refused batch leaves no trace).
+    std::map<std::string, int64_t> fresh; bool dups = dups_;
+    for (int32_t i = 0; i < n; ++i) {
       auto it = first_of_.find(vectors[i].first);
-      if (it != first_of_.end()) { dups_ = true; keys[i] = it->second; }
-      else { keys[i] = base + i; if (!stopUpdateIndex) first_of_.emplace(vectors[i].first, base + i); }
+      if (it != first_of_.end()) { dups = true; keys[i] = it->second; continue; }
+      auto ins = fresh.emplace(vectors[i].first, base + i);
+      if (!ins.second) dups = true;
+      keys[i] = ins.first->second;
     }
     std::vector<int32_t> first_dim;
-    if (as_built) {
+    if (as_built && firsts) first_dim = *firsts;
+    else if (as_built) {
       first_dim.resize((size_t)n);
       for (int32_t i = 0; i < n; ++i) {
         std::vector<int32_t> kept;
@@ -264,8 +282,10 @@ class GpuIndexingWorkerActor {
       }
     }
     const uint32_t flags = (stopUpdateIndex ? APSS_BATCH_QUERY_ONLY : 0u) | (skip_admit ? APSS_BATCH_SKIP_ADMIT : 0u);
-    const apss_batch_result res = engine_.insert_batch(n, indptr.data(), indices.data(), values.data(), dups_ ? keys.data() : nullptr,
-                                                       as_built ? first_dim.data() : nullptr, flags);
+    const apss_batch_result res = engine_.insert_batch(n, indptr.data(), indices.data(), values.data(), dups ? keys.data() : nullptr,
+                                                       as_built ? first_dim.data() : nullptr, flags);      // throws: batch dropped, nothing recorded
+    dups_ = dups;
+    if (!stopUpdateIndex) first_of_.insert(fresh.begin(), fresh.end());
     std::vector<uint8_t> status; engine_.fetch_status(status, n);
     std::vector<int32_t> q, c; std::vector<double> sim; engine_.fetch_pairs(q, c, sim, res.n_pairs);
     if (!stopUpdateIndex) for (const auto& v : vectors) ids_.push_back(v.first);
@@ -289,9 +309,9 @@ class GpuIndexingWorkerActor {
     return (int64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
   }
   void reply(const OutMessage& m) { if (replyTo_) replyTo_(m); }
-  void handle_batch(const std::vector<IdVector>& vectors, bool skip_admit) {
+  void handle_batch(const std::vector<IdVector>& vectors, bool skip_admit, const std::vector<int32_t>* firsts = nullptr) {
     try {                                                                    // IWA:124
-      auto out = query_and_index(vectors, skip_admit);
+      auto out = query_and_index(vectors, skip_admit, firsts);
       if (replyTo_) {                                                        // IWA:128
         if (outputWritingDuration <= 0) reply(SimilarityOutput{std::move(out), now_ms()});     // IWA:129-130
         else for (const auto& [qid, sims] : out) for (const auto& [cid, s] : sims) writeBuffer[qid][cid] = s;   // IWA:113-120
@@ -324,6 +344,9 @@ class RegionRouter {
   void tell(IOTrigger) {
     if (!buffer_.empty()) { VectorIOMsg m{std::move(buffer_)}; buffer_.clear(); worker_.receive(m); }
   }
+  // EPA:113-122 handleDataPacket: the reference splits the packet by dimension over its index workers (EPA:37-49); an
+  // id-range shard holds all dimensions of its vectors, so the whole packet becomes ONE IndexData
+  void tell(const DataPacket& m) { worker_.receive(IndexData{m.vectors}); }
   template <class M> void tell(const M& m) { worker_.receive(m); }
   const long long ioTriggerPeriod;
 

@@ -105,7 +105,7 @@ class SimilarityOutput:                                      # Message.scala:20-
             sb.append("---------------------------------")
             sb.append(qid + ":")
             for cid, sim in sims.items():
-                sb.append(cid + "," + repr(float(sim)) + ";")
+                sb.append(cid + "," + java_double_to_string(float(sim)) + ";")     # Scala string concatenation = Double.toString
             sb.append("\n")
         return "".join(sb)
 
@@ -136,6 +136,12 @@ class StartTest:                                             # Message.scala:42
 class StartTime:                                             # Message.scala:43
     vectorId: str
     moment: int
+
+
+def java_double_to_string(x: float) -> str:
+    """java.lang.Double.toString (what `cid + "," + sim` produces at Message.scala:29): see etl.java_double_to_string."""
+    from .etl import java_double_to_string as f
+    return f(x)
 
 
 def to_csr(vectors: Sequence[Tuple[str, SparkSparseVector]], dim: int):

@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get("APSS_LIB_NAME") or ("libapss_b200_dbg.so" if os.environ.get("APSS_DEBUG_LIB") else
                         ("libapss_b200_prof.so" if os.environ.get("APSS_PROF_LIB") else "libapss_b200.so")))
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+MAX_DEVICES = 16
 SEM_R1, SEM_R0 = 0, 1
 BATCH_QUERY_ONLY, BATCH_DEVICE_PTRS, BATCH_SKIP_ADMIT, BATCH_INDEX_ONLY = 1, 2, 4, 8
 ST_REJECTED, ST_EMPTY, ST_ACTIVE = 0, 1, 2
@@ -40,7 +41,8 @@ class Config(C.Structure):
                 ("index_threshold", C.c_double), ("max_weight", C.c_void_p), ("device", C.c_int32),
                 ("semantics", C.c_int32), ("tile_vectors", C.c_int32), ("kernel_variant", C.c_int32),
                 ("reserve_vectors", C.c_int64), ("reserve_nnz", C.c_int64), ("reserve_pairs", C.c_int64),
-                ("pruning", C.c_int32), ("reserved0", C.c_int32), ("prune_alpha", C.c_double), ("max_query_norm", C.c_double)]
+                ("pruning", C.c_int32), ("reserved0", C.c_int32), ("prune_alpha", C.c_double), ("max_query_norm", C.c_double),
+                ("n_devices", C.c_int32), ("device_ids", C.c_int32 * MAX_DEVICES), ("reserved1", C.c_int32)]
 
 
 class BatchResultC(C.Structure):
@@ -57,7 +59,8 @@ class StatsC(C.Structure):
                 ("score_launches", C.c_int64), ("kernel_launches", C.c_int64), ("tot_score_ms", C.c_double),
                 ("phase_cycles", C.c_int64 * 8),
                 ("frozen", C.c_int32), ("tile_vectors", C.c_int32), ("warps_per_cta", C.c_int32), ("sm_count", C.c_int32),
-                ("n_unindexed", C.c_int64)]
+                ("n_unindexed", C.c_int64), ("segment_merges", C.c_int64), ("merged_postings", C.c_int64),
+                ("n_devices", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -139,7 +142,8 @@ class Index:
 
     def __init__(self, dim, similarity_threshold, index_threshold=0.0, max_weight=None, device=0, semantics=SEM_R1,
                  tile_vectors=0, kernel_variant=0, reserve_vectors=0, reserve_nnz=0, reserve_pairs=0,
-                 pruning=False, prune_alpha=0.0, max_query_norm=0.0):
+                 pruning=False, prune_alpha=0.0, max_query_norm=0.0, devices=None):
+        """devices: list of CUDA ordinals that share the index (id-range shards below the C ABI); None = `device` alone."""
         self._L = load_library()
         self._mw = None if max_weight is None else np.ascontiguousarray(max_weight, dtype=np.float64)
         if self._mw is not None and len(self._mw) != dim:
@@ -148,6 +152,13 @@ class Index:
                      None if self._mw is None else self._mw.ctypes.data, int(device), int(semantics), int(tile_vectors),
                      int(kernel_variant), int(reserve_vectors), int(reserve_nnz), int(reserve_pairs),
                      int(pruning), 0, float(prune_alpha), float(max_query_norm))
+        if devices is not None:
+            if not 1 <= len(devices) <= MAX_DEVICES:
+                raise ValueError("1..%d devices" % MAX_DEVICES)
+            cfg.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                cfg.device_ids[i] = int(d)
+            cfg.device = int(devices[0])
         h = C.c_void_p()
         rc = self._L.apss_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -224,6 +235,7 @@ class Index:
         self._check(self._L.apss_get_stats(self._h, C.byref(s)))
         d = {f: getattr(s, f) for f, _ in StatsC._fields_}
         d["phase_cycles"] = list(d["phase_cycles"])
+        d.pop("reserved", None)
         return d
 
     @property

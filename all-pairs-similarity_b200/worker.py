@@ -21,7 +21,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import native
-from .messages import (IndexData, IOTicket, IOTrigger, ReceiveTimeout, SimilarityOutput, SparkSparseVector, Test,
+from .messages import (DataPacket, IndexData, IOTicket, IOTrigger, ReceiveTimeout, SimilarityOutput, SparkSparseVector, Test,
                        VectorIOMsg, to_csr)
 
 _M32 = 0xFFFFFFFF
@@ -88,14 +88,18 @@ class GpuIndexingWorkerActor:
         if engine is None:                        # the product path: CUDA or nothing
             engine = native.Index(self.vectorDim, self.similarityThreshold, self.indexThreshold, device=device,
                                   semantics=native.SEM_R0 if self.as_built else native.SEM_R1,
-                                  pruning=int(conf_get(conf, "cpslab.allpair.gpu.pruning", 0)))   # 0 parity counters, 2 exact index reduction
+                                  pruning=int(conf_get(conf, "cpslab.allpair.gpu.pruning", 0)),    # 0 parity counters, 3 exact index reduction
+                                  devices=conf_get(conf, "cpslab.allpair.gpu.devices", None))     # GPUs sharing the index (shards below the C ABI)
         self.engine = engine
 
     # -- IWA:122-148
     def receive(self, msg):
         if isinstance(msg, IndexData):
-            # wrappers carry admitted, pruned vectors (EPA:97, WWA:192-194): do not re-admit
-            self._handle_batch([w.sparseVector for w in msg.vectors], skip_admit=True)
+            # wrappers carry admitted, pruned vectors (EPA:97, WWA:192-194): do not re-admit.  As built, the first
+            # posting list skipped (IWA:89 + IWA:106-107) is the first element of the WRAPPER's Set (IWA:102)
+            ws = list(msg.vectors)
+            firsts = [scala_set_first(sorted(w.indices)) for w in ws] if self.as_built else None
+            self._handle_batch([w.sparseVector for w in ws], skip_admit=True, firsts=firsts)
         elif isinstance(msg, VectorIOMsg):
             self._handle_batch(list(msg.vectors), skip_admit=False)
         elif isinstance(msg, IOTicket) or msg is IOTicket:
@@ -112,9 +116,9 @@ class GpuIndexingWorkerActor:
         if self.replyTo is not None:
             self.replyTo(m)
 
-    def _handle_batch(self, vectors: List[Tuple[str, SparkSparseVector]], skip_admit: bool):
+    def _handle_batch(self, vectors: List[Tuple[str, SparkSparseVector]], skip_admit: bool, firsts=None):
         try:                                                                   # IWA:124
-            out = self.query_and_index(vectors, skip_admit)
+            out = self.query_and_index(vectors, skip_admit, firsts)
             if self.replyTo is not None:                                       # IWA:128
                 if self.outputWritingDuration <= 0:                            # IWA:129-130
                     self._reply(SimilarityOutput(out, int(time.time() * 1000)))
@@ -125,24 +129,33 @@ class GpuIndexingWorkerActor:
         except Exception:                                                      # IWA:135-137
             traceback.print_exc(file=sys.stderr)
 
-    def query_and_index(self, vectors, skip_admit=False) -> Dict[str, Dict[str, float]]:
+    def query_and_index(self, vectors, skip_admit=False, firsts=None) -> Dict[str, Dict[str, float]]:
         """buildInvertedIndex + querySimilarItems (IWA:61-111) for one batch; returns outputSimSet."""
         if not vectors:
             return {}
         indptr, indices, values = to_csr(vectors, self.vectorDim)
         n = len(vectors)
         base = len(self._ids)
+        # keys of this batch: a String id seen before keeps the key of its first occurrence (IWA:91 compares Strings).
+        # Nothing is recorded in _first_of / _ids until the engine has accepted the batch (a refused batch leaves no trace).
         keys = np.empty(n, np.int64)
+        fresh: Dict[str, int] = {}
+        dups = self._dups
         for i, (vid, _) in enumerate(vectors):
-            if vid in self._first_of:
-                self._dups = True
-            keys[i] = self._first_of.setdefault(vid, base + i) if not self.stopUpdateIndex else self._first_of.get(vid, base + i)
+            if vid in self._first_of or vid in fresh:
+                dups = True
+            keys[i] = self._first_of[vid] if vid in self._first_of else fresh.setdefault(vid, base + i)
         first_dim = None
         if self.as_built:
-            first_dim = np.array([scala_set_first(indices[indptr[i]:indptr[i + 1]][values[indptr[i]:indptr[i + 1]] > self.indexThreshold])
-                                  for i in range(n)], np.int32)
-        res = self.engine.insert_batch(indptr, indices, values, ext_keys=keys if self._dups else None, first_dim=first_dim,
+            if firsts is None:
+                firsts = [scala_set_first(indices[indptr[i]:indptr[i + 1]][values[indptr[i]:indptr[i + 1]] > self.indexThreshold])
+                          for i in range(n)]
+            first_dim = np.asarray(firsts, np.int32)
+        res = self.engine.insert_batch(indptr, indices, values, ext_keys=keys if dups else None, first_dim=first_dim,
                                        query_only=self.stopUpdateIndex, skip_admit=skip_admit)
+        self._dups = dups
+        if not self.stopUpdateIndex:
+            self._first_of.update(fresh)
         status = self.engine.fetch_status(n)
         q, c, s = self.engine.fetch_pairs()
         if not self.stopUpdateIndex:
@@ -174,6 +187,10 @@ class RegionRouter:
                 self.worker.receive(msg)
             else:
                 self._buffer.extend(msg.vectors)
+        elif isinstance(msg, DataPacket):
+            # EPA:113-122 handleDataPacket: the reference splits the packet by dimension over its index workers
+            # (spawnToIndexActor, EPA:37-49); an id-range shard holds all dimensions, so the whole packet is ONE IndexData
+            self.worker.receive(IndexData(msg.vectors))
         elif isinstance(msg, IOTrigger) or msg is IOTrigger:
             if self._buffer:
                 buf, self._buffer = self._buffer, []

@@ -18,8 +18,12 @@
  * itself.  Distinct handles may be used concurrently.
  *
  * Errors: every function returns APSS_OK (0) or a negative apss_status; nothing aborts or throws
- * across the boundary (the reference swallows exceptions per batch, IWA:124-137).  A batch that
- * fails validation leaves the index untouched (all-or-nothing).
+ * across the boundary (the reference swallows exceptions per batch, IWA:124-137).  A batch is
+ * all-or-nothing: one that fails validation never touches the index, and one that fails later (out of
+ * memory, CUDA error) is rolled back before the call returns -- the index, the id counter and the
+ * document frequencies are what they were.  Where a roll-back is impossible (the tile index rewrites
+ * its open tile in place; a sticky CUDA error) the handle is retired: every later call returns
+ * APSS_E_STATE and the only valid operation is apss_destroy.
  */
 #ifndef APSS_H_
 #define APSS_H_
@@ -30,7 +34,8 @@
 extern "C" {
 #endif
 
-#define APSS_ABI_VERSION 2
+#define APSS_ABI_VERSION 3
+#define APSS_MAX_DEVICES 16
 
 typedef enum apss_status {
   APSS_OK = 0,
@@ -83,13 +88,24 @@ typedef struct apss_config {
   /* postings_visited / candidates_unique count only what the reduced index makes the kernel touch.         */
   int32_t pruning;             /* 0 = off (parity counters); 1 = on, tile kernel on the reduced index;     */
                                /* 2 = on, candidate-major kernel (the batch is inverted instead and the    */
-                               /* stored vectors are streamed; same results and counters as 1, much faster) */
+                               /* stored vectors are streamed); 3 = on, query-major posting-list traversal */
+                               /* of dimension-sorted CSR posting segments with shared-memory hash         */
+                               /* accumulators (the fastest; the reference's own loop order, IWA:101-104). */
+                               /* 1, 2 and 3 give the same pairs, similarities and counters.               */
   int32_t reserved0;
   double prune_alpha;          /* share of (t / max_query_norm)^2 a vector may keep out of the index;      */
                                /* 0 = default 0.8; must be < 1                                             */
   double max_query_norm;       /* promise: every vector of every batch has L2 norm <= this after the value */
                                /* prune; 0 = default 1.0 (LoadGenerator.scala:35-37 normalises).  A batch  */
                                /* that breaks the promise is refused (APSS_E_INPUT), never mis-scored.      */
+  /* Shard dispatch below the ABI (replaces the remote router EPA:37-49,113-122): with       */
+  /* n_devices > 1 the ONE handle an actor holds owns all the listed GPUs.  The index is partitioned by          */
+  /* internal-id range, block-cyclic (block = one insert batch, owner = batch number mod n_devices); every      */
+  /* batch is copied to device_ids[0] once and fanned out over NVLink peer copies, each GPU scores it against   */
+  /* its own shard (the owner also indexes it), and the per-shard pair lists are gathered into one result.      */
+  int32_t n_devices;           /* 0 or 1: one GPU, `device`.  N > 1: device_ids[0..N-1] (then `device` is ignored) */
+  int32_t device_ids[APSS_MAX_DEVICES];
+  int32_t reserved1;
 } apss_config;
 
 typedef struct apss_batch_result {
@@ -112,7 +128,7 @@ typedef struct apss_batch_result {
 typedef struct apss_stats {
   int64_t n_vectors;         /* vectors stored in this shard (all statuses)                          */
   int64_t n_postings;        /* postings resident in HBM                                             */
-  int64_t n_tiles;
+  int64_t n_tiles;           /* index tiles; pruning = 3: posting segments                           */
   int64_t bytes_postings;    /* 8 B each                                                             */
   int64_t bytes_directory;
   int64_t bytes_forward;     /* fp64 forward store used by the verify kernel                         */
@@ -132,6 +148,10 @@ typedef struct apss_stats {
   int32_t warps_per_cta;
   int32_t sm_count;
   int64_t n_unindexed;       /* stored components kept out of the index by exact index reduction     */
+  int64_t segment_merges;    /* pruning = 3: posting-segment merges so far and the postings they copied     */
+  int64_t merged_postings;
+  int32_t n_devices;         /* GPUs behind this handle; the other fields are sums over the shards           */
+  int32_t reserved;
 } apss_stats;
 
 int32_t apss_abi_version(void);

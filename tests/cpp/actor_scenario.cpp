@@ -133,6 +133,37 @@ static void as_built_first_list_skip() {
   delete e2;
 }
 
+// IndexData / DataPacket (Message.scala:16-18): wrappers carry admitted, pruned vectors -- no second admission filter --
+// and, as built, the skipped first posting list is the first element of the WRAPPER's Set (IWA:102)
+static void index_data_and_data_packet(int pruning) {
+  Config conf = base_conf();
+  Engine* eng = make_engine(64, 0.5, 0.0, false, pruning);
+  std::vector<OutMessage> out;
+  GpuIndexingWorkerActor<Engine> w(conf, *eng, [&](const OutMessage& m) { out.push_back(m); });
+  RegionRouter<Engine> router(conf, w);
+  auto wrap = [](const char* id, SparkSparseVector v) { std::set<int32_t> d(v.indices.begin(), v.indices.end()); return SparseVectorWrapper{d, IdVector{id, v}}; };
+  w.receive(IndexData{{wrap("p", V({{3, .3}}))}});                          // sum 0.3 < t: a VectorIOMsg would reject it (EPA:81-93)
+  CHECK(out.size() == 1 && std::get<SimilarityOutput>(out[0]).output.count("p") == 1);
+  router.tell(DataPacket{0, {wrap("q", V({{3, .9}, {4, .1}})), wrap("r", V({{3, 1.0}}))}});   // EPA:113-122 -> ONE IndexData
+  CHECK(out.size() == 2);
+  const auto& o = std::get<SimilarityOutput>(out[1]).output;
+  CHECK(o.size() == 2 && o.at("r").count("q") == 1 && o.at("q").at("r") == .9 && o.at("q").count("p") == 0);   // .9 * .3 < t
+  // a refused batch leaves no trace in the id tables: "dup" is new again afterwards and pairs with nothing of its own name
+  w.receive(VectorIOMsg{{{"dup", SparkSparseVector(32, {1}, {1.0})}}});     // wrong size: dropped whole (IWA:135-137)
+  w.receive(VectorIOMsg{{{"dup", V({{3, 1.0}})}}});
+  CHECK(out.size() == 3 && std::get<SimilarityOutput>(out[2]).output.at("dup").count("r") == 1);
+  delete eng;
+  // as built: first(q) comes from the wrapper's Set
+  Config c0 = base_conf(); c0["cpslab.allpair.gpu.semantics"] = "R0";
+  Engine* e0 = make_engine(64, 0.5, 0.0, true, pruning);
+  std::vector<OutMessage> o0;
+  GpuIndexingWorkerActor<Engine> w0(c0, *e0, [&](const OutMessage& m) { o0.push_back(m); });
+  w0.receive(IndexData{{wrap("a", V({{0, .6}, {1, .8}}))}});
+  w0.receive(IndexData{{wrap("b", V({{1, .8}, {2, .6}}))}});               // only shared dim is b's first: dropped as built
+  CHECK(std::get<SimilarityOutput>(o0[1]).output.at("b").empty());
+  delete e0;
+}
+
 static void formats() {
   CHECK(java_double_to_string(1.0) == "1.0" && java_double_to_string(0.64) == "0.64" && java_double_to_string(1.25e-5) == "1.25E-5");
   CHECK(java_double_to_string(1e7) == "1.0E7" && java_double_to_string(123456.789) == "123456.789" && java_double_to_string(0.001) == "0.001");
@@ -152,6 +183,7 @@ int main(int argc, char** argv) {
   scenario(pruning);
   buffered_output_and_router();
   as_built_first_list_skip();
+  index_data_and_data_packet(pruning);
   if (failures) { std::fprintf(stderr, "%d check(s) failed\n", failures); return 1; }
   std::printf("actor scenario ok (pruning=%d)\n", pruning);
   return 0;

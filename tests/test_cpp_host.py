@@ -60,7 +60,7 @@ def test_cpp_actor_against_the_oracle_double(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("pruning", [0, 2])
+@pytest.mark.parametrize("pruning", [0, 2, 3])
 def test_cpp_actor_through_the_c_abi(tmp_path, pruning):
     import apss_b200
     lib = apss_b200.native.LIB_PATH

@@ -589,3 +589,14 @@ def test_candidate_major_heavy_vectors_and_many_queries(slices, monkeypatch):
         assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
         assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
     assert o.totals()["pairs"] > 1000
+
+
+def test_generator_gives_the_same_bits_on_cpu_and_cuda():
+    """generator g2: the oracle box and the GPU box regenerate the same data from the seed"""
+    import torch
+    from apss_b200 import synth
+    for kw in (dict(N=6000, D=1 << 14, nnz_mean=40, seed=20260103), dict(N=1500, D=1 << 16, nnz_mean=200, seed=5, heavy_tail=True)):
+        a = synth.generate(device="cpu", **kw)
+        b = synth.generate(device="cuda", **kw)
+        assert torch.equal(a.indptr, b.indptr.cpu()) and torch.equal(a.indices, b.indices.cpu())
+        assert torch.equal(a.values, b.values.cpu())          # bit for bit, fp64

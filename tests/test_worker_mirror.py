@@ -51,6 +51,34 @@ def test_worker_messages_cpu():
     scenario(gpu=False)
 
 
+def index_data_scenario(gpu, **over):
+    """IndexData / DataPacket (Message.scala:16-18) through the worker and the router: no second admission filter
+    (EPA:97 ran upstream), first(q) from the wrapper's own Set as built, and a refused batch leaves no trace."""
+    w, out, pkg = mk(gpu=gpu, **over)
+    M = pkg.messages
+    from apss_b200.worker import RegionRouter
+    V = lambda d: M.SparkSparseVector.sparse(64, list(d.items()))
+    wrap = lambda vid, v: M.SparseVectorWrapper(frozenset(int(i) for i in v.indices), (vid, v))
+    w.receive(M.IndexData({wrap("p", V({3: .3}))}))                     # sum 0.3 < t: would be rejected as VectorIOMsg
+    assert out[0].output == {"p": {}}
+    RegionRouter(CONF, w).tell(M.DataPacket(0, [wrap("q", V({3: .9, 4: .1})), wrap("r", V({3: 1.0}))]))   # EPA:113-122
+    assert out[1].output == {"q": {"r": .9}, "r": {"q": .9}}           # q.p = .27 and r.p = .3 stay below t
+    n = len(out)
+    w.receive(M.VectorIOMsg([("dup", M.SparkSparseVector(32, [1], [1.0]))]))     # refused whole (IWA:135-137)
+    assert len(out) == n
+    w.receive(M.VectorIOMsg([("dup", V({3: 1.0}))]))
+    assert "r" in out[n].output["dup"] and "dup" not in out[n].output["dup"]
+    assert "1.0E-5" in str(M.SimilarityOutput({"x": {"y": 1e-5}}, 0))   # Double.toString, not Python's repr
+    w0, out0, _ = mk(gpu=gpu, **dict(over, **{"cpslab.allpair.gpu.semantics": "R0"}))
+    w0.receive(M.IndexData({wrap("a", V({0: .6, 1: .8}))}))
+    w0.receive(M.IndexData({wrap("b", V({1: .8, 2: .6}))}))             # only shared dim is b's first: dropped as built
+    assert out0[1].output == {"b": {}}
+
+
+def test_index_data_and_data_packet_cpu():
+    index_data_scenario(gpu=False)
+
+
 def test_index_data_skips_admission():
     w, out, pkg = mk()
     M = pkg.messages
@@ -120,7 +148,13 @@ def test_vector_text_format_roundtrip():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("pruning", [0, 2])
+@pytest.mark.parametrize("pruning", [0, 3])
+def test_index_data_and_data_packet_gpu(pruning):
+    index_data_scenario(gpu=True, **{"cpslab.allpair.gpu.pruning": pruning})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pruning", [0, 2, 3])
 def test_worker_messages_gpu(pruning):
     # same messages, same SimilarityOutput with exact index reduction switched on through the config
     scenario(gpu=True, **{"cpslab.allpair.gpu.pruning": pruning})
