@@ -591,9 +591,9 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
   // first stored component of row_lo: the open tile's postings are rewritten in place
   int64_t nnz_lo = nnz_old;
   if (row_lo < n_old) {
-    CK(cudaMemcpyAsync(h->h_counters + C_COUNT - 1, h->fwd_ptr.p + row_lo, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_counters + C_SCRATCH, h->fwd_ptr.p + row_lo, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    nnz_lo = (int64_t)h->h_counters[C_COUNT - 1];
+    nnz_lo = (int64_t)h->h_counters[C_SCRATCH];
   }
   const int64_t m = nnz_new - nnz_lo;
   const int64_t post_base = nnz_lo;   // postings are stored in the same order of tiles as the forward store
@@ -1070,7 +1070,7 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
   }
   for (int attempt = 0; attempt < 4; ++attempt) {
     CK(cudaMemsetAsync(h->d_counters, 0, 7 * sizeof(unsigned long long), s));   // keep the prefilter tallies
-    CK(cudaMemsetAsync(h->d_counters + C_PHASE, 0, 8 * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(h->d_counters + C_PHASE, 0, 10 * sizeof(unsigned long long), s));      // phase timers + dense-phase tallies
     CK(cudaEventRecord(h->ev_s0, s));
     const int32_t rcs = h->prune_mode == 3 ? score_query_major(h, n, batch_nnz, q_local_base, d_qkey)
                       : h->prune_mode == 2 ? score_candidate_major(h, n, batch_nnz, slices, qsub, q_local_base, d_qkey)
@@ -1086,7 +1086,7 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
     }
     CK(cudaEventRecord(h->ev_b1, s));
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->h_counters + C_PHASE, h->d_counters + C_PHASE, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_counters + C_PHASE, h->d_counters + C_PHASE, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     if (h->prune) CK(cudaMemcpyAsync(h->h_counters + C_SKIPPED, h->d_counters + C_SKIPPED, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const size_t items_need = h->prune_mode == 3 ? (size_t)(h->h_counters[C_ITEMS] >> 36) : 0;
@@ -1107,6 +1107,7 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
   res.candidates_unique = (int64_t)h->h_counters[C_CANDS];
   res.n_pairs = (int64_t)h->h_counters[C_FINAL];
   res.n_pairs_r1 = (int64_t)h->h_counters[C_R1];
+  res.dense_postings = (int64_t)h->h_counters[C_DENSE_POST]; res.dense_fma = (int64_t)h->h_counters[C_DENSE_FMA];
   for (int k = 0; k < 8; ++k) h->phase_cycles[k] = (int64_t)h->h_counters[C_PHASE + k];
   commit_index();
   res.work_items = (int64_t)((unsigned long long)h->ntiles * (unsigned long long)(h->algo == 1 ? n : (n + h->QB - 1) / h->QB));
@@ -1195,7 +1196,7 @@ extern "C" int32_t apss_microbench_accumulators(int32_t device, int32_t mode, in
     switch (mode) {
 #define MB(M) case M: cudaFuncSetAttribute(k_microbench<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
                       k_microbench<M><<<prop.multiProcessorCount, warps * 32, smem>>>(CR, it, sink); break;
-      MB(0) MB(1) MB(2) MB(3) MB(4) MB(5)
+      MB(0) MB(1) MB(2) MB(3) MB(4) MB(5) MB(6)
 #undef MB
       default: break;
     }
@@ -1206,6 +1207,6 @@ extern "C" int32_t apss_microbench_accumulators(int32_t device, int32_t mode, in
   cudaError_t e = cudaGetLastError();
   cudaFree(sink); cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (e != cudaSuccess) return APSS_E_CUDA;
-  *updates_per_sec = (double)prop.multiProcessorCount * warps * 32.0 * 4.0 * iters / (ms * 1e-3);
+  *updates_per_sec = (double)prop.multiProcessorCount * warps * 32.0 * (mode == 6 ? 32.0 : 4.0) * iters / (ms * 1e-3);
   return APSS_OK;
 }

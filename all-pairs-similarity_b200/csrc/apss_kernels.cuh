@@ -43,9 +43,12 @@ enum Counter : int {
   C_HEAVY = 13,    // candidate-major kernel: stored vectors deferred to the heavy pass (this launch)
   C_HEAVY_TOT = 14, // same, summed over the query slices of the batch
   C_TOTNNZ = 15,   // components kept by the value prune, whole batch (64-bit: the per-vector counts are int32)
-  C_ITEMS = 25,    // host mirror only: (pieces << 36 | postings) of the batch, query-major kernel
   C_PHASE = 16,    // 8 per-phase cycle totals of the dense kernel (thread 0 of every CTA)
-  C_COUNT = 24     // device counters; the pinned host mirror has C_COUNT + 2 words
+  C_DENSE_POST = 24, // dense-head kernel: postings scored through the dense FFMA rows (the rest went through shared-memory atomics)
+  C_DENSE_FMA = 25,  // dense-head kernel: FMAs the dense phase executed (zeros and padding included)
+  C_COUNT = 26,      // device counters; the pinned host mirror has C_COUNT + 2 words:
+  C_ITEMS = 26,      //   host only: (pieces << 36 | postings) of the batch, query-major kernel
+  C_SCRATCH = 27     //   host only: one-word read-backs
 };
 
 static constexpr unsigned FULL = 0xffffffffu;
@@ -921,7 +924,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
   constexpr int NT = WARPS * 32;
   const int nwords = QB * RW;
   for (int i = tid * 4; i < nwords; i += NT * 4) *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
-  unsigned long long n_post = 0, n_cand = 0;
+  unsigned long long n_post = 0, n_cand = 0, n_dpost = 0, n_dfma = 0;
 #ifdef APSS_PHASE_TIMERS
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tc = clock64();
 #define PHASE_MARK(k) do { if (tid == 0) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; } } while (0)
@@ -965,7 +968,8 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
           const int k = atomicAdd(&s_ndense, 1);
           DBG_ASSERT(k < KD && slot < ndt && nr >= 1 && nr <= QB);
           dl[k] = make_int4(slot, rs, nr, 0);
-          n_post += (unsigned long long)(unsigned)__ldg(dt.len + (size_t)tile * KD + slot) * (unsigned)nr;
+          const unsigned long long dp = (unsigned long long)(unsigned)__ldg(dt.len + (size_t)tile * KD + slot) * (unsigned)nr;
+          n_post += dp; n_dpost += dp;
         } else {
           s = __ldg(dirt + d); e = __ldg(dirt + d + 1);
           DBG_ASSERT(d >= 0 && d < a.D && s >= 0 && e >= s && e <= tcnt && nr >= 1 && nr <= QB);
@@ -1038,6 +1042,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
     __syncthreads();
     // ---- phase D: dense dims by FFMA, thread = COLS adjacent candidates x QB rows
     if (nd) {
+      if (tid == 0) n_dfma += (unsigned long long)((nd + 3) & ~3) * (unsigned long long)QB * (unsigned long long)CR;
       const float* __restrict__ wbase = dt.w + (size_t)tile * KD * CR;
       for (int cb = tid * COLS; cb < CR; cb += NT * COLS) {
         float av[COLS][QB];
@@ -1205,8 +1210,10 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
   for (int o = 16; o > 0; o >>= 1) {
     n_post += __shfl_down_sync(FULL, n_post, o);
     n_cand += __shfl_down_sync(FULL, n_cand, o);
+    n_dpost += __shfl_down_sync(FULL, n_dpost, o);
   }
-  if (lane == 0) { atomicAdd(&a.counters[C_POSTINGS], n_post); atomicAdd(&a.counters[C_CANDS], n_cand); }
+  if (lane == 0) { atomicAdd(&a.counters[C_POSTINGS], n_post); atomicAdd(&a.counters[C_CANDS], n_cand); if (n_dpost) atomicAdd(&a.counters[C_DENSE_POST], n_dpost); }
+  if (tid == 0 && n_dfma) atomicAdd(&a.counters[C_DENSE_FMA], n_dfma);
 #ifdef APSS_PHASE_TIMERS
   if (tid == 0) { for (int k = 0; k < 8; ++k) atomicAdd(&a.counters[C_PHASE + k], (unsigned long long)ph[k]); }
 #endif
@@ -1536,6 +1543,7 @@ __global__ void k_verify(const unsigned long long* counters, unsigned long long 
 
 // ------------------------------------------------------------------ accumulator micro-benchmark
 
+// mode 6: register FFMA, 8 independent chains per thread (FP32 FMA peak)
 // mode 0: LDS/FFMA/STS random   1: same, consecutive addresses   2: ATOMS.ADD u32 random
 // 3: ATOMS.ADD u32 consecutive  4: float atomicAdd (CAS loop) random   5: FFMA+F2I+ATOMS.ADD random
 template <int MODE>
@@ -1548,6 +1556,23 @@ __global__ void k_microbench(int CR, int iters, unsigned* sink) {
   __syncwarp();
   unsigned x = (blockIdx.x * 1315423911u) ^ (threadIdx.x * 2654435761u) ^ 12345u;
   const float w = 1.0f + lane * 1e-3f;
+  if (MODE == 6) {
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = w + k;
+    const float m = 1.0f + 1e-7f * lane, c = 1e-9f * warp;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], m, c);          // 32 FMAs per iteration (reported as 4 "updates" x 8)
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += f[k];
+    if (sum == 0.12345f) sink[0] = 1u;
+    return;
+  }
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {

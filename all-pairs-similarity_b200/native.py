@@ -49,7 +49,7 @@ class BatchResultC(C.Structure):
     _fields_ = [("id_base", C.c_int64), ("n_vectors", C.c_int32), ("n_rejected", C.c_int32), ("n_empty", C.c_int32),
                 ("n_active", C.c_int32), ("n_pairs", C.c_int64), ("n_pairs_r1", C.c_int64), ("n_prefilter", C.c_int64),
                 ("postings_visited", C.c_int64), ("candidates_unique", C.c_int64), ("work_items", C.c_int64),
-                ("score_ms", C.c_double), ("device_ms", C.c_double)]
+                ("score_ms", C.c_double), ("device_ms", C.c_double), ("dense_postings", C.c_int64), ("dense_fma", C.c_int64)]
 
 
 class StatsC(C.Structure):
@@ -122,6 +122,8 @@ class BatchResult:
     work_items: int
     score_ms: float
     device_ms: float
+    dense_postings: int = 0
+    dense_fma: int = 0
 
 
 def _ptr(a):

@@ -123,6 +123,9 @@ typedef struct apss_batch_result {
                              /* vectors that took the heavy pass                                             */
   double score_ms;           /* CUDA-event time of the scoring kernel(s), on the handle's stream     */
   double device_ms;          /* CUDA-event time first kernel -> last kernel of the call              */
+  int64_t dense_postings;    /* default kernel: postings scored through the dense FFMA rows; the other    */
+                             /* postings_visited - dense_postings went through shared-memory atomics      */
+  int64_t dense_fma;         /* default kernel: FMAs the dense phase executed (zeros and padding included) */
 } apss_batch_result;
 
 typedef struct apss_stats {
@@ -201,7 +204,8 @@ const char *apss_last_error(apss_handle *h);
 void *apss_stream(apss_handle *h);
 
 /* Micro-benchmark of shared-memory accumulator update primitives (plain RMW, fixed-point atomics,
- * float CAS atomics), used to choose the accumulator design; reports updates per second. */
+ * float CAS atomics; mode 6: register FP32 FMA), used to choose the accumulator design and as the measured on-chip
+ * peaks of bench.py's roofline; reports updates (mode 6: FMAs) per second. */
 int32_t apss_microbench_accumulators(int32_t device, int32_t mode, int32_t warps, int32_t iters, double *updates_per_sec);
 
 #ifdef __cplusplus

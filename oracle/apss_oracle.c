@@ -347,18 +347,23 @@ static void worker_build_index(oworker_t *wk, const owrap_t *ws, int32_t n) {
 
 /* IWA:74-111 for one query wrapper.  `sims` is this query's outputSimSet entry (ckey -> pair
  * slot) and *has_entry says whether outputSimSet.contains(q.id). */
+/* `stripe` of `nstripes`: the threads of the parallel driver may share ONE query by candidate key (key % nstripes); a
+ * candidate's visits all fall into the same stripe in the same order, so pairs, dot calls and the first-list skip are
+ * what the serial loop gives (the posting count is taken by stripe 0).  Pure parallelisation of the restatement. */
 static void worker_query_one(const oracle_t *o, const oworker_t *wk, const owrap_t *q, map64_t *sims, int *has_entry,
-                             opair_t **out, int64_t *n_out, int64_t *cap_out, int64_t *postings, int64_t *dot_calls) {
+                             opair_t **out, int64_t *n_out, int64_t *cap_out, int64_t *postings, int64_t *dot_calls,
+                             int32_t stripe, int32_t nstripes) {
   const ovec_t *qv = &o->vecs[q->ord];
   for (int32_t j = 0; j < q->n_dims; j++) {                       /* IWA:102 (Set iteration order) */
     int64_t slot = map64_find(&wk->dim2list, q->dims[j]);         /* IWA:104; Q15: missing dim -> empty list */
     int64_t list_start = *n_out;
     if (slot >= 0) {
       const ivec_t *list = &wk->lists[wk->dim2list.val[slot]];
-      *postings += list->n;
+      if (stripe == 0) *postings += list->n;
       for (int32_t p = 0; p < list->n; p++) {                     /* IWA:86 */
         int32_t c_ord = wk->store_vec.v[list->v[p]];              /* IWA:87 */
         const ovec_t *cv = &o->vecs[c_ord];
+        if (nstripes > 1 && (int32_t)((uint64_t)cv->key % (uint64_t)nstripes) != stripe) continue;
         if (*has_entry && map64_find(sims, cv->key) < 0 && qv->key != cv->key) {   /* IWA:89-91 */
           double sim = calc_similarity_hashjoin(cv, qv);          /* IWA:92 */
           (*dot_calls)++;
@@ -515,7 +520,7 @@ int32_t oracle_insert_batch(oracle_t *o, int32_t n, const int64_t *indptr, const
           if (s < 0) { e = n_ent++; map64_put(&key2slot, qkey, e); has[e] = (o->semantics == ORC_R1); } else e = (int32_t)key2slot.val[s];
           /* pair slots index into o->pairs: keep per-entry map consistent by rebuilding offsets */
           int64_t before = o->n_pairs;
-          worker_query_one(o, wk, &wr[w][i], &sims[e], &has[e], &o->pairs, &o->n_pairs, &o->cap_pairs, &postings, &dots);
+          worker_query_one(o, wk, &wr[w][i], &sims[e], &has[e], &o->pairs, &o->n_pairs, &o->cap_pairs, &postings, &dots, 0, 1);
           (void)before;
         }
         for (int32_t e = 0; e < n_ent; e++) map64_free(&sims[e]);
@@ -527,16 +532,17 @@ int32_t oracle_insert_batch(oracle_t *o, int32_t n, const int64_t *indptr, const
         {
           opair_t *lp = NULL; int64_t ln = 0, lc = 0, lpost = 0, ldots = 0;
           map64_t sims; memset(&sims, 0, sizeof sims);
+          /* few queries, many threads (bench samples against a large index): share each query by candidate key */
+          const int32_t nstripes = nq >= 2 * nthreads ? 1 : (2 * nthreads + nq - 1) / nq;
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 1) nowait
 #endif
-          for (int32_t i = 0; i < nq; i++) {
+          for (int64_t task = 0; task < (int64_t)nq * nstripes; task++) {
+            const int32_t i = (int32_t)(task / nstripes), stripe = (int32_t)(task % nstripes);
             int has = (o->semantics == ORC_R1);
-            int64_t start = ln;
             map64_clear(&sims);
             /* sims maps ckey -> slot in lp; slots are relative to this query only for lookups */
-            worker_query_one(o, wk, &wr[w][i], &sims, &has, &lp, &ln, &lc, &lpost, &ldots);
-            (void)start;
+            worker_query_one(o, wk, &wr[w][i], &sims, &has, &lp, &ln, &lc, &lpost, &ldots, stripe, nstripes);
           }
           map64_free(&sims);
 #ifdef _OPENMP

@@ -600,3 +600,98 @@ def test_generator_gives_the_same_bits_on_cpu_and_cuda():
         b = synth.generate(device="cuda", **kw)
         assert torch.equal(a.indptr, b.indptr.cpu()) and torch.equal(a.indices, b.indices.cpu())
         assert torch.equal(a.values, b.values.cpu())          # bit for bit, fp64
+
+
+# ---------------------------------------------------------------- engine assumptions made explicit (VERDICT r1 "weak 8")
+
+def test_very_long_vectors_u16_scale_and_limit():
+    """The packed-u16 tile kernel bounds a sum by max_sq * 2^F + one quantum per shared dimension: the scale follows the
+    longest vector seen (pairs sharing > 32 K dimensions used to wrap a half-word), and a vector beyond the limit is
+    refused up front instead of being mis-scored."""
+    rng = np.random.default_rng(1)
+    D, t = 1 << 16, 0.5
+    n = native()
+    rows = []
+    base = rng.choice(D, size=40000, replace=False)
+    for i in range(6):                                   # six near-identical vectors sharing ~40 K dimensions
+        w = rng.uniform(0.5, 1.0, size=base.size) if i == 0 else w0 * rng.uniform(0.98, 1.02, size=base.size)
+        if i == 0:
+            w0 = w
+        v = dict(zip(base.tolist(), (w / np.sqrt((w * w).sum())).tolist()))
+        rows.append(v)
+    for i in range(300):                                 # and ordinary short ones
+        dims = rng.choice(D, size=20, replace=False)
+        w = rng.uniform(0.1, 1.0, size=20)
+        rows.append(dict(zip(dims.tolist(), (w / np.sqrt((w * w).sum())).tolist())))
+    csr = csr_from_dicts(rows)
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8)
+    ro = o.insert_batch(*csr)
+    for kw in (dict(), dict(pruning=3), dict(kernel_variant=2 << 16)):
+        g = n.Index(D, t, **kw)
+        rg = g.insert_batch(*csr)
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+        assert len(ro.sim) >= 30
+        if not kw.get("pruning"):
+            assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+        g.close()
+    big = np.arange(61000, dtype=np.int32)
+    csr_big = (np.array([0, big.size], np.int64), big, np.full(big.size, 1.0 / np.sqrt(big.size)))
+    g = n.Index(D, t)
+    g.insert_batch(*csr_from_dicts([A]))
+    with pytest.raises(n.ApssError) as e:
+        g.insert_batch(*csr_big)
+    assert e.value.code == -4 and "u16" in str(e.value) and g.stats()["n_vectors"] == 1
+    g3 = n.Index(D, t, pruning=3)                        # the hash-table kernel has no such limit
+    g3.insert_batch(*csr_big)
+    assert g3.stats()["n_vectors"] == 1
+
+
+@pytest.mark.parametrize("mode", [0, 2, 3])
+def test_failure_after_the_index_append_is_rolled_back_or_retires_the_handle(mode, monkeypatch):
+    """A batch that fails AFTER the index was touched must not leave the shard advanced behind the caller's back:
+    append-only layouts (pruning 2 / 3) are cut back -- ids, document frequencies and posting segments as before, later
+    batches give the oracle's pairs -- and the tile index, which rewrites its open tile in place, retires the handle."""
+    N, D, t = 3000, 1 << 10, 0.5
+    data = _synth(N, D, 12, seed=9)
+    n = native()
+    o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8, pruning=bool(mode))
+    g = n.Index(D, t, tile_vectors=256, pruning=mode)
+    b = [csr_slice(data, lo, lo + 500) for lo in range(0, N, 500)]
+    for k in (0, 1):
+        ro = o.insert_batch(*b[k]); rg = g.insert_batch(*b[k])
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+    st0 = g.stats()
+    monkeypatch.setenv("APSS_TEST_FAIL_AFTER_APPEND", "1")
+    with pytest.raises(n.ApssError) as e:
+        g.insert_batch(*b[2])
+    monkeypatch.delenv("APSS_TEST_FAIL_AFTER_APPEND")
+    assert e.value.code == -3
+    if mode == 0:
+        assert "retired" in str(e.value)
+        with pytest.raises(n.ApssError) as e2:
+            g.insert_batch(*b[2])
+        assert e2.value.code == -5                        # APSS_E_STATE: only apss_destroy is valid now
+        return
+    assert "rolled back" in str(e.value)
+    st1 = g.stats()
+    assert (st1["n_vectors"], st1["n_postings"], st1["n_unindexed"]) == (st0["n_vectors"], st0["n_postings"], st0["n_unindexed"])
+    with pytest.raises(n.ApssError):
+        g.fetch_pairs()                                   # no completed batch to fetch from
+    for k in (2, 3, 4, 5):                                # the same batch again, then the rest: counters prove df was restored
+        ro = o.insert_batch(*b[k]); rg = g.insert_batch(*b[k])
+        assert rg.id_base == ro.id_base
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+        assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+    assert g.stats()["n_unindexed"] == o.n_unindexed
+
+
+def test_int32_bounds_of_ids_and_component_counts():
+    """internal ids are int32: a batch that would run the id space over is refused before anything is touched"""
+    n = native()
+    g = n.Index(64, 0.5)
+    g.set_next_id((1 << 31) - 3)
+    with pytest.raises(n.ApssError) as e:
+        g.insert_batch(*csr_from_dicts([A, dict(A), dict(A), dict(A)]))
+    assert e.value.code == -1 and "id space" in str(e.value)
+    rg = g.insert_batch(*csr_from_dicts([A, dict(A)]))     # two still fit
+    assert rg.id_base == (1 << 31) - 3 and g.stats()["n_vectors"] == 2
