@@ -8,6 +8,7 @@
 #include <cuda.h>   // driver types only; entry points are resolved at run time (no libcuda link)
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -151,6 +152,7 @@ struct apss_handle {
   int64_t next_id = 0;
   int max_nnz_seen = 0;
   int64_t phase_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // last batch, profiling build only (see apss_stats)
+  double host_us[6] = {0, 0, 0, 0, 0, 0};               // APSS_HOST_TIMING: host wall clock of the last batch by phase
 
   // shard
   int64_t n_local = 0, nnz = 0, n_post = 0;
@@ -180,13 +182,19 @@ struct apss_handle {
   DevBuf<unsigned long long> pr_keys_in, pr_keys_out, pr_vals_in, pr_vals_out;
   int64_t tot_skipped = 0;
   // query-major scoring on the reduced index (prune_mode 3): LSM posting segments, oldest first
-  struct Seg { uint2* post = nullptr; int32_t* dir = nullptr; int64_t n_post = -1; int64_t cap_post = 0; int64_t row_lo = 0, row_hi = 0; };
+  // Segments are stacked by age in ONE growable arena (VMM: the pointer never moves, growth maps pages behind it and
+  // copies nothing); a merge writes to the scratch arena and is copied back over its sources -- or, when it took
+  // every segment, the two arenas simply swap.  Directories come from a fixed pool of (D + 1)-entry slots.
+  struct Seg { int64_t off = 0; int32_t dir_slot = -1; int64_t n_post = -1; int64_t cap_post = 0; int64_t row_lo = 0, row_hi = 0; };
   std::vector<Seg> segs;
-  cudaMemPool_t pool = nullptr;
+  VmBuf<uint2> seg_arena[2];
+  DevBuf<int32_t> dir_pool; std::vector<int32_t> dir_free;
+  uint2* seg_post(const Seg& g) const { return seg_arena[0].p + g.off; }
+  int32_t* seg_dir(const Seg& g) const { return dir_pool.p + (size_t)g.dir_slot * ((size_t)cfg.dim + 1); }
   DevBuf<unsigned> sg_keys_in, sg_keys_out; DevBuf<unsigned long long> sg_vals_in;
   DevBuf<unsigned long long> qm_cnt, qm_off; DevBuf<QmItem> qm_items;
   int64_t merges = 0, merged_postings = 0;
-  int qm_cap = QM_CAP, qm_nt = 1024; size_t qm_items_cap0 = 0; bool qm_pipe = true; DevBuf<int32_t> qm_deferred;     // test hooks: APSS_QM_CAP, APSS_QM_ITEMS_CAP
+  int qm_cap = QM_CAP, qm_nt = 1024; size_t qm_items_cap0 = 0; bool qm_pipe = true; DevBuf<int32_t> qm_deferred, hot_q, hot_c; DevBuf<float> hot_est;     // test hooks: APSS_QM_CAP, APSS_QM_ITEMS_CAP
   bool broken = false;       // a failure after the index was touched that could not be rolled back: every later call fails
   // query-block transposition (v2 kernel)
   DevBuf<unsigned long long> bt_keys_in, bt_keys_out, bt_vals_in, bt_vals_out, ud_key; DevBuf<int32_t> bt_flags, bt_pos, ud_dim, ud_start, bd_ptr;
@@ -416,13 +424,10 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (cfg->pruning) {
     if (cfg->pruning < 1 || cfg->pruning > 3 || algo != 3) return bail(APSS_E_INVALID);   // only the default scoring kernel applies the bound
     h->prune_mode = cfg->pruning;
-    if (cfg->pruning == 3) {     // posting segments come from a private stream-ordered pool (merges allocate and free)
-      cudaMemPoolProps pp{};
-      pp.allocType = cudaMemAllocationTypePinned; pp.handleTypes = cudaMemHandleTypeNone;
-      pp.location.type = cudaMemLocationTypeDevice; pp.location.id = h->device;
-      if (cudaMemPoolCreate(&h->pool, &pp) != cudaSuccess) { cudaGetLastError(); return bail(APSS_E_CUDA); }
-      unsigned long long keep = ~0ULL;
-      cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (cfg->pruning == 3) {
+      h->seg_arena[0].device = h->seg_arena[1].device = cfg->device;
+      if (h->dir_pool.reserve((size_t)(QM_MAXSEG + 2) * ((size_t)cfg->dim + 1), 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+      for (int k = QM_MAXSEG + 1; k >= 0; --k) h->dir_free.push_back(k);
       { const char* e = getenv("APSS_QM_CAP"); if (e && atoi(e) >= 8 && atoi(e) <= QM_CAP) h->qm_cap = atoi(e); }
       { const char* e = getenv("APSS_QM_NT"); if (e && atoi(e) == 512) h->qm_nt = 512; }
       { const char* e = getenv("APSS_QM_PIPE"); if (e && atoi(e) == 0) h->qm_pipe = false; }      // measurement / tests: ranged kernel only
@@ -443,17 +448,22 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (cfg->reserve_vectors > 0) {
     int64_t nv = cfg->reserve_vectors, nt = (nv + CR - 1) / CR;
     if (h->fwd_ptr.reserve(nv + 1, 0, h->stream) != cudaSuccess || h->gid.reserve(nv, 0, h->stream) != cudaSuccess ||
-        h->key.reserve(nv, 0, h->stream) != cudaSuccess || h->dir.reserve((size_t)nt * ((size_t)cfg->dim + 1), 0, h->stream) != cudaSuccess ||
-        h->tile_base.reserve(nt + 1, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
-    if (algo == 3 && (h->dn_cnt.reserve(nt, 0, h->stream) != cudaSuccess || h->tile_cnt.reserve(nt, 0, h->stream) != cudaSuccess ||
+        h->key.reserve(nv, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+    if (h->prune_mode < 2 && (h->dir.reserve((size_t)nt * ((size_t)cfg->dim + 1), 0, h->stream) != cudaSuccess ||      // (no tiles in modes 2 / 3)
+                              h->tile_base.reserve(nt + 1, 0, h->stream) != cudaSuccess)) return bail(APSS_E_NOMEM);
+    if (algo == 3 && h->prune_mode < 2 && (h->dn_cnt.reserve(nt, 0, h->stream) != cudaSuccess || h->tile_cnt.reserve(nt, 0, h->stream) != cudaSuccess ||
                       h->dn_dim.reserve((size_t)nt * KD, 0, h->stream) != cudaSuccess || h->dn_len.reserve((size_t)nt * KD, 0, h->stream) != cudaSuccess ||
                       h->dn_hash.reserve((size_t)nt * HS, 0, h->stream) != cudaSuccess || h->dn_w.reserve((size_t)nt * KD * CR, 0, h->stream) != cudaSuccess))
       return bail(APSS_E_NOMEM);
   }
   if (cfg->reserve_nnz > 0) {
-    if (h->fwd_idx.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess || h->fwd_val.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess ||
-        h->post.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+    if (h->fwd_idx.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess || h->fwd_val.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+    if (h->prune_mode < 2 && h->post.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+    if (h->prune && h->fwd_skip.reserve(cfg->reserve_nnz, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+    if (h->prune_mode == 3 && (h->seg_arena[0].reserve((size_t)cfg->reserve_nnz / 2, 0, h->stream) != cudaSuccess ||
+                               h->seg_arena[1].reserve((size_t)cfg->reserve_nnz / 2, 0, h->stream) != cudaSuccess)) return bail(APSS_E_NOMEM);
   }
+  if (cfg->reserve_vectors > 0 && h->prune && h->row_ub.reserve(cfg->reserve_vectors, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
   {
     size_t np = cfg->reserve_pairs > 0 ? (size_t)cfg->reserve_pairs : (size_t)1 << 20;
     if (h->pf_q.reserve(np, 0, h->stream) != cudaSuccess || h->pf_c.reserve(np, 0, h->stream) != cudaSuccess || h->pf_est.reserve(np, 0, h->stream) != cudaSuccess ||
@@ -481,11 +491,8 @@ extern "C" void apss_destroy(apss_handle* h) {
   h->qdir.release(); h->heavy.release(); h->ifw_ptr.release(); h->ifw.release(); h->q_icnt.release(); h->q_iptr.release();
   h->df.release(); h->fwd_skip.release(); h->row_ub.release(); h->q_skip.release(); h->q_cu.release(); h->q_nrm.release();
   h->pr_keys_in.release(); h->pr_keys_out.release(); h->pr_vals_in.release(); h->pr_vals_out.release();
-  for (auto& sg : h->segs) { if (sg.post) cudaFreeAsync(sg.post, h->stream); if (sg.dir) cudaFreeAsync(sg.dir, h->stream); }
-  h->segs.clear();
-  if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->pool) cudaMemPoolDestroy(h->pool);
-  h->sg_keys_in.release(); h->sg_keys_out.release(); h->sg_vals_in.release(); h->qm_cnt.release(); h->qm_off.release(); h->qm_items.release(); h->qm_deferred.release();
+  h->segs.clear(); h->seg_arena[0].release(); h->seg_arena[1].release(); h->dir_pool.release();
+  h->sg_keys_in.release(); h->sg_keys_out.release(); h->sg_vals_in.release(); h->qm_cnt.release(); h->qm_off.release(); h->qm_items.release(); h->qm_deferred.release(); h->hot_q.release(); h->hot_c.release(); h->hot_est.release();
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->h_total) cudaFreeHost(h->h_total);
@@ -553,22 +560,23 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
   }
   if (h->prune_mode == 3) {     // query-major scoring: the batch becomes one new posting segment (merged after the call)
     if (batch_nnz) {
-      if ((int)h->segs.size() >= QM_MAXSEG) return h->fail(APSS_E_STATE, "too many posting segments");
-      apss_handle::Seg sg; sg.cap_post = (int64_t)batch_nnz + 64;      // a lane may read up to one 1 KB window past a list sg.row_lo = n_old; sg.row_hi = n_new;
+      if ((int)h->segs.size() >= QM_MAXSEG || h->dir_free.empty()) return h->fail(APSS_E_STATE, "too many posting segments");
+      apss_handle::Seg sg; sg.row_lo = n_old; sg.row_hi = n_new;
+      sg.cap_post = (int64_t)batch_nnz + 64;      // the sort writes the un-indexed components behind the postings; + one window of read slack
+      if (!h->segs.empty()) { const apss_handle::Seg& b = h->segs.back(); sg.off = (b.off + b.n_post + 64 + 31) & ~(int64_t)31; }
+      CK(h->seg_arena[0].reserve((size_t)(sg.off + sg.cap_post), 0, s));
       CK(h->sg_keys_in.reserve(batch_nnz, 0, s)); CK(h->sg_keys_out.reserve(batch_nnz, 0, s)); CK(h->sg_vals_in.reserve(batch_nnz, 0, s));
-      CK(cudaMallocFromPoolAsync((void**)&sg.post, sizeof(uint2) * (size_t)sg.cap_post, h->pool, s));
-      { cudaError_t e_ = cudaMallocFromPoolAsync((void**)&sg.dir, sizeof(int32_t) * ((size_t)D + 1), h->pool, s);
-        if (e_ != cudaSuccess) { cudaFreeAsync(sg.post, s); return h->fail(APSS_E_NOMEM, "segment directory: %s", cudaGetErrorString(e_)); } }
-      h->segs.push_back(sg);       // from here on a failure is undone by drop_last_segment()
+      sg.dir_slot = h->dir_free.back(); h->dir_free.pop_back();
+      h->segs.push_back(sg);       // from here on a failure is undone by the roll-back
       int dimbits = 1; while ((1LL << dimbits) < (int64_t)D + 1) ++dimbits;
       k_seg_emit<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, n_old, h->q_ptr.p, h->q_dim.p, h->q_w.p, h->q_skip.p, D, h->sg_keys_in.p, h->sg_vals_in.p);
       CK(cudaGetLastError());
       size_t tb = 0;
-      unsigned long long* vout = reinterpret_cast<unsigned long long*>(sg.post);
+      unsigned long long* vout = reinterpret_cast<unsigned long long*>(h->seg_post(sg));
       CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->sg_keys_in.p, h->sg_keys_out.p, h->sg_vals_in.p, vout, batch_nnz, 0, dimbits, s));
       CK(h->cub_tmp.reserve(tb, 0, s));
       CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->sg_keys_in.p, h->sg_keys_out.p, h->sg_vals_in.p, vout, batch_nnz, 0, dimbits, s));
-      k_seg_dir<<<cdiv((int64_t)D + 1, 256), 256, 0, s>>>(h->sg_keys_out.p, batch_nnz, D, sg.dir);
+      k_seg_dir<<<cdiv((int64_t)D + 1, 256), 256, 0, s>>>(h->sg_keys_out.p, batch_nnz, D, h->seg_dir(sg));
       CK(cudaGetLastError()); h->kernel_launches += 5;
     }
     h->n_local = n_new; h->nnz = nnz_new; h->ntiles = 0;
@@ -751,7 +759,7 @@ static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, i
   h->h_counters[C_ITEMS] = 0;
   if (!h->n_local || !batch_nnz || h->segs.empty()) return APSS_OK;
   SegList sl{}; sl.n = (int32_t)h->segs.size();
-  for (int k = 0; k < sl.n; ++k) { sl.post[k] = h->segs[k].post; sl.dir[k] = h->segs[k].dir; }
+  for (int k = 0; k < sl.n; ++k) { sl.post[k] = h->seg_post(h->segs[k]); sl.dir[k] = h->seg_dir(h->segs[k]); }
   CK(h->qm_cnt.reserve((size_t)batch_nnz + 1, 0, s)); CK(h->qm_off.reserve((size_t)batch_nnz + 1, 0, s));
   if (!h->qm_items.cap) CK(h->qm_items.reserve(h->qm_items_cap0 ? h->qm_items_cap0 : std::max<size_t>((size_t)batch_nnz * 2, (size_t)1 << 16), 0, s));
   k_qm_count<<<cdiv((int64_t)batch_nnz + 1, 256), 256, 0, s>>>(batch_nnz, h->q_dim.p, sl, h->qm_cnt.p);
@@ -783,14 +791,25 @@ static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, i
   a.deferred = h->qm_deferred.p; a.deferred_cap = n;
   CK(cudaMemsetAsync(h->d_counters + C_HEAVY, 0, 2 * sizeof(unsigned long long), s));      // deferred count, ranged-kernel cursor
   if (h->qm_pipe) {
-    // producer / consumer kernel for the queries that fit one table pass; the others land on the deferred list
+    // producer / consumer kernel for the queries that fit one table pass; the others land on the deferred list.  Its hot
+    // candidates go to a chunked buffer (q = -1 marks unused entries), k_qm_filter applies the exact test afterwards.
+    if (!h->hot_q.cap) {
+      const size_t c0 = std::max<size_t>((size_t)h->sm_count * 4 * QP_CHUNK, (size_t)1 << 22);
+      CK(h->hot_q.reserve(c0, 0, s)); CK(h->hot_c.reserve(c0, 0, s)); CK(h->hot_est.reserve(c0, 0, s));
+    }
+    CK(cudaMemsetAsync(h->hot_q.p, 0xff, sizeof(int32_t) * h->hot_q.cap, s));
+    CK(cudaMemsetAsync(h->d_counters + C_HOTN, 0, sizeof(unsigned long long), s));
     QmArgs ap = a; ap.cap = std::min(a.cap, QP_CAP);
+    ap.hot_q = h->hot_q.p; ap.hot_c = h->hot_c.p; ap.hot_est = h->hot_est.p; ap.hot_cap = (unsigned)std::min<size_t>(h->hot_q.cap, 0xffff0000u);
     auto kern = h->custom_keys ? k_score_qm_pipe<true> : k_score_qm_pipe<false>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QP_SMEM));
     kern<<<h->sm_count, 1024, QP_SMEM, s>>>(ap);
     CK(cudaGetLastError());
-    a.from_list = 1; h->kernel_launches++;
-  }
+    k_qm_filter<<<h->sm_count * 8, 256, 0, s>>>(ap);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_counters + C_HOTN, h->d_counters + C_HOTN, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    a.from_list = 1; h->kernel_launches += 2;
+  } else h->h_counters[C_HOTN] = 0;
   if (h->qm_nt == 512) {          // two CTAs per SM, half the table each
     a.cap = std::min(a.cap, QM_CAP2);
     const size_t smem = (size_t)(2 * QM_TBL2 + QM_HOT) * sizeof(unsigned);
@@ -824,22 +843,26 @@ static int32_t merge_segments(apss_handle* h) {
     if (prev > 2 * sum && size - j <= QM_MAXSEG - 8) break;
     sum += prev; ++j;
   }
-  if (j < 2) return APSS_OK;
+  if (j < 2 || h->dir_free.empty()) return APSS_OK;
   apss_handle::Seg out; out.n_post = sum; out.cap_post = sum + 64;
-  out.row_lo = h->segs[size - j].row_lo; out.row_hi = h->segs.back().row_hi;
-  CK(cudaMallocFromPoolAsync((void**)&out.post, sizeof(uint2) * (size_t)out.cap_post, h->pool, s));
-  { cudaError_t e_ = cudaMallocFromPoolAsync((void**)&out.dir, sizeof(int32_t) * ((size_t)D + 1), h->pool, s);
-    if (e_ != cudaSuccess) { cudaFreeAsync(out.post, s); return h->fail(APSS_E_NOMEM, "merged segment directory: %s", cudaGetErrorString(e_)); } }
+  out.off = h->segs[size - j].off; out.row_lo = h->segs[size - j].row_lo; out.row_hi = h->segs.back().row_hi;
+  CK(h->seg_arena[1].reserve((size_t)(sum + 64), 0, s));
+  out.dir_slot = h->dir_free.back();
   MergeSrc m{}; m.n = j;
-  for (int k = 0; k < j; ++k) { m.post[k] = h->segs[size - j + k].post; m.dir[k] = h->segs[size - j + k].dir; }
-  k_merge_dir<<<cdiv((int64_t)D + 1, 256), 256, 0, s>>>(D, m, out.dir);
+  for (int k = 0; k < j; ++k) { m.post[k] = h->seg_post(h->segs[size - j + k]); m.dir[k] = h->seg_dir(h->segs[size - j + k]); }
+  k_merge_dir<<<cdiv((int64_t)D + 1, 256), 256, 0, s>>>(D, m, h->seg_dir(out));
   for (int k = 0; k < j; ++k) {
     const int64_t np = h->segs[size - j + k].n_post;
-    if (np > 0) k_merge_copy<<<cdiv(np, 256), 256, 0, s>>>(k, (int)np, D, m, out.dir, out.post);
+    if (np > 0) k_merge_copy<<<cdiv(np, 256), 256, 0, s>>>(k, (int)np, D, m, h->seg_dir(out), h->seg_arena[1].p);
   }
-  { cudaError_t e_ = cudaGetLastError();
-    if (e_ != cudaSuccess) { cudaFreeAsync(out.post, s); cudaFreeAsync(out.dir, s); return h->fail(APSS_E_CUDA, "segment merge: %s", cudaGetErrorString(e_)); } }
-  for (int k = 0; k < j; ++k) { cudaFreeAsync(h->segs[size - j + k].post, s); cudaFreeAsync(h->segs[size - j + k].dir, s); }
+  { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return h->fail(APSS_E_CUDA, "segment merge: %s", cudaGetErrorString(e_)); }
+  if (j == size) std::swap(h->seg_arena[0], h->seg_arena[1]);        // everything was merged: the scratch arena IS the index now
+  else {
+    CK(h->seg_arena[0].reserve((size_t)(out.off + out.cap_post), 0, s));
+    CK(cudaMemcpyAsync(h->seg_arena[0].p + out.off, h->seg_arena[1].p, sizeof(uint2) * (size_t)sum, cudaMemcpyDeviceToDevice, s));
+  }
+  h->dir_free.pop_back();
+  for (int k = 0; k < j; ++k) h->dir_free.push_back(h->segs[size - j + k].dir_slot);
   h->segs.resize(size - j);
   h->segs.push_back(out);
   h->kernel_launches += 1 + j; h->merges++; h->merged_postings += sum;
@@ -899,11 +922,7 @@ static void rollback_batch(apss_handle* h, const BatchTxn& txn) {
     k_df_update<<<cdiv(txn.batch_nnz, 256), 256, 0, h->stream>>>(txn.batch_nnz, h->q_dim.p, h->df.p, -1);
     ok = cudaGetLastError() == cudaSuccess;
   }
-  while (h->segs.size() > txn.n_segs) {
-    if (h->segs.back().post) cudaFreeAsync(h->segs.back().post, h->stream);
-    if (h->segs.back().dir) cudaFreeAsync(h->segs.back().dir, h->stream);
-    h->segs.pop_back();
-  }
+  while (h->segs.size() > txn.n_segs) { h->dir_free.push_back(h->segs.back().dir_slot); h->segs.pop_back(); }
   if (ok) ok = cudaStreamSynchronize(h->stream) == cudaSuccess;
   h->n_local = txn.n_local; h->nnz = txn.nnz; h->n_post = txn.n_post; h->ntiles = txn.ntiles; h->next_id = txn.next_id;
   h->custom_keys = txn.custom_keys;
@@ -939,6 +958,8 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
   res.n_vectors = n; res.id_base = h->next_id;
   if (n == 0) { h->last_n = 0; h->last_status.clear(); if (out) *out = res; return APSS_OK; }
 
+  const auto hts0 = std::chrono::steady_clock::now();
+  auto hmark = [&](int k) { h->host_us[k] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - hts0).count(); };
   CK(cudaEventRecord(h->ev_b0, s));
   // ---- stage the batch on the device
   const int64_t* d_ptr; const int32_t* d_idx; const double* d_val; const int64_t* d_keys = nullptr; const int32_t* d_first = nullptr;
@@ -978,7 +999,9 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
   CK(cudaMemcpyAsync(h->h_total, h->q_ptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   h->last_status.resize(n);
   CK(cudaMemcpyAsync(h->last_status.data(), h->q_status.p, n, cudaMemcpyDeviceToHost, s));
+  hmark(0);      // prefilter enqueued
   CK(cudaStreamSynchronize(s));
+  hmark(1);      // prefilter done
   if (h->h_counters[C_ERR]) {   // all-or-nothing (Q9): the index has not been touched yet
     return h->fail(APSS_E_INPUT, h->h_counters[C_ERR] == 2 ? "indptr is not monotone / does not start at 0"
                                                            : "indices must be strictly increasing and < dim (SparseVector.scala:96-108)");
@@ -1026,7 +1049,7 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
     if (h->prune_mode == 3 && h->segs.size() > txn.n_segs) {
       apss_handle::Seg& sg = h->segs.back();
       sg.n_post = (int64_t)batch_nnz - skipped;
-      if (sg.n_post <= 0) { cudaFreeAsync(sg.post, s); cudaFreeAsync(sg.dir, s); h->segs.pop_back(); }
+      if (sg.n_post <= 0) { h->dir_free.push_back(sg.dir_slot); h->segs.pop_back(); }
       const std::string keep = h->err;
       if (merge_segments(h) != APSS_OK) { cudaGetLastError(); h->err = keep; }     // left unmerged: the index stays valid
     }
@@ -1071,15 +1094,17 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
   for (int attempt = 0; attempt < 4; ++attempt) {
     CK(cudaMemsetAsync(h->d_counters, 0, 7 * sizeof(unsigned long long), s));   // keep the prefilter tallies
     CK(cudaMemsetAsync(h->d_counters + C_PHASE, 0, 10 * sizeof(unsigned long long), s));      // phase timers + dense-phase tallies
+    hmark(2);    // index append + per-batch query structures enqueued
     CK(cudaEventRecord(h->ev_s0, s));
     const int32_t rcs = h->prune_mode == 3 ? score_query_major(h, n, batch_nnz, q_local_base, d_qkey)
                       : h->prune_mode == 2 ? score_candidate_major(h, n, batch_nnz, slices, qsub, q_local_base, d_qkey)
                                            : score_tiles(h, n, batch_nnz, blk, F, thr_int, q_local_base, d_qkey);
     if (rcs != APSS_OK) return rcs;
     CK(cudaEventRecord(h->ev_s1, s));
+    hmark(3);    // scoring enqueued
     CK(h->out_q.reserve(h->pf_q.cap, 0, s)); CK(h->out_c.reserve(h->pf_q.cap, 0, s)); CK(h->out_sim.reserve(h->pf_q.cap, 0, s));
     if (h->n_local) {
-      k_verify<<<h->sm_count * 4, 256, 0, s>>>(h->d_counters, h->pf_q.cap, h->pf_q.p, h->pf_c.p, h->q_ptr.p, h->q_dim.p, h->q_val.p,
+      k_verify<<<h->sm_count * 8, 256, 0, s>>>(h->d_counters, h->pf_q.cap, h->pf_q.p, h->pf_c.p, h->q_ptr.p, h->q_dim.p, h->q_val.p,
                                                h->fwd_ptr.p, h->fwd_idx.p, h->fwd_val.p, h->gid.p, t, h->cfg.semantics == APSS_SEM_R0, d_first,
                                                h->out_q.p, h->out_c.p, h->out_sim.p, h->d_counters);
       CK(cudaGetLastError()); h->kernel_launches++;
@@ -1088,10 +1113,14 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->h_counters + C_PHASE, h->d_counters + C_PHASE, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     if (h->prune) CK(cudaMemcpyAsync(h->h_counters + C_SKIPPED, h->d_counters + C_SKIPPED, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    hmark(4);    // verify enqueued
     CK(cudaStreamSynchronize(s));
+    hmark(5);    // all done
     const size_t items_need = h->prune_mode == 3 ? (size_t)(h->h_counters[C_ITEMS] >> 36) : 0;
     const bool items_short = items_need > h->qm_items.cap;
-    if (h->h_counters[C_PF] <= h->pf_q.cap && !items_short) break;
+    const bool hot_short = h->prune_mode == 3 && h->qm_pipe && (size_t)h->h_counters[C_HOTN] > h->hot_q.cap;
+    if (hot_short) { const size_t need = (size_t)h->h_counters[C_HOTN] * 2; CK(h->hot_q.reserve(need, 0, s)); CK(h->hot_c.reserve(need, 0, s)); CK(h->hot_est.reserve(need, 0, s)); }
+    if (h->h_counters[C_PF] <= h->pf_q.cap && !items_short && !hot_short) break;
     if (attempt == 3) return h->fail(APSS_E_NOMEM, "pair / piece buffer overflow persisted");
     if (items_short) CK(h->qm_items.reserve(items_need + items_need / 4 + 1024, 0, s));     // grow and replay
     if (h->h_counters[C_PF] > h->pf_q.cap) {
@@ -1115,6 +1144,8 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
     res.work_items = (int64_t)h->h_counters[C_HEAVY_TOT];      // (stored vector, query slice) pairs that took the heavy pass
     if (h->n_local > 0 && res.n_active > 0) h->cand_rate = (double)res.postings_visited / ((double)h->n_local * (double)res.n_active);
   }
+  if (getenv("APSS_HOST_TIMING")) std::fprintf(stderr, "apss host us: prefilter-enq %.0f prefilter-done %.0f index-enq %.0f score-enq %.0f verify-enq %.0f done %.0f | device %.0f score %.0f\n",
+                                               h->host_us[0], h->host_us[1], h->host_us[2], h->host_us[3], h->host_us[4], h->host_us[5], res.device_ms * 1e3, res.score_ms * 1e3);
   h->last_n = n; h->last_pairs = res.n_pairs;
   h->tot_postings += res.postings_visited; h->tot_cands += res.candidates_unique; h->tot_pairs += res.n_pairs; h->tot_pf += res.n_prefilter;
   h->tot_score_ms += res.score_ms;

@@ -46,9 +46,10 @@ enum Counter : int {
   C_PHASE = 16,    // 8 per-phase cycle totals of the dense kernel (thread 0 of every CTA)
   C_DENSE_POST = 24, // dense-head kernel: postings scored through the dense FFMA rows (the rest went through shared-memory atomics)
   C_DENSE_FMA = 25,  // dense-head kernel: FMAs the dense phase executed (zeros and padding included)
-  C_COUNT = 26,      // device counters; the pinned host mirror has C_COUNT + 2 words:
-  C_ITEMS = 26,      //   host only: (pieces << 36 | postings) of the batch, query-major kernel
-  C_SCRATCH = 27     //   host only: one-word read-backs
+  C_HOTN = 26,       // query-major pipelined kernel: entries reserved in the hot-candidate buffer (chunks of QP_CHUNK)
+  C_COUNT = 27,      // device counters; the pinned host mirror has C_COUNT + 2 words:
+  C_ITEMS = 27,      //   host only: (pieces << 36 | postings) of the batch, query-major kernel
+  C_SCRATCH = 28     //   host only: one-word read-backs
 };
 
 static constexpr unsigned FULL = 0xffffffffu;
@@ -1496,16 +1497,20 @@ __global__ void __launch_bounds__(512, 1) k_score_cand_heavy(const CandArgs a, i
 // products are then added one by one in lane order = ascending dimension, the same chain on every lane.
 // Applies `sim >= similarityThreshold` (IWA:93) and, for the as-built semantics R0, drops pairs whose
 // shared dims all equal first(q) (IWA:89 + IWA:106-107).
-__global__ void k_verify(const unsigned long long* counters, unsigned long long pf_cap,
+static constexpr int VERIFY_WIN = 256;       // candidate dimensions staged per warp in shared memory
+
+__global__ void __launch_bounds__(256) k_verify(const unsigned long long* counters, unsigned long long pf_cap,
                          const int32_t* __restrict__ pf_q, const int32_t* __restrict__ pf_c,
                          const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim, const double* __restrict__ q_val,
                          const int64_t* __restrict__ fwd_ptr, const int32_t* __restrict__ fwd_idx, const double* __restrict__ fwd_val,
                          const int32_t* __restrict__ gid, double thr, int sem_r0, const int32_t* __restrict__ first_dim,
                          int32_t* __restrict__ out_q, int32_t* __restrict__ out_c, double* __restrict__ out_sim,
                          unsigned long long* wcounters) {
+  __shared__ int32_t s_win[8][VERIFY_WIN];
   unsigned long long n = counters[C_PF];
   if (n > pf_cap) n = pf_cap;
   const int lane = threadIdx.x & 31;
+  int32_t* win = s_win[threadIdx.x >> 5];
   const unsigned long long wid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
   for (unsigned long long r = wid; r < n; r += nw) {
@@ -1513,15 +1518,30 @@ __global__ void k_verify(const unsigned long long* counters, unsigned long long 
     const int i0 = q_ptr[q], ie = q_ptr[q + 1];
     const int64_t j0 = fwd_ptr[c], je = fwd_ptr[c + 1];
     const int fd = (sem_r0 && first_dim) ? first_dim[q] : -1;
+    // the candidate's dimensions go to shared memory once (coalesced) when they fit: the look-ups below then cost
+    // shared-memory latency instead of a chain of dependent global loads
+    const int nc = (int)min((int64_t)VERIFY_WIN + 1, je - j0);
+    const bool staged = nc <= VERIFY_WIN;
+    __syncwarp();
+    if (staged) for (int k = lane; k < nc; k += 32) win[k] = fwd_idx[j0 + k];
+    __syncwarp();
     double s = 0.0; int nonfirst = 0;
     for (int ib = i0; ib < ie; ib += 32) {
       const int i = ib + lane;
       double p = 0.0; bool hit = false;
       if (i < ie) {
         const int di = q_dim[i];
-        int64_t lo = j0, hi = je;                    // first j with fwd_idx[j] >= di
-        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (fwd_idx[mid] < di) lo = mid + 1; else hi = mid; }
-        if (lo < je && fwd_idx[lo] == di) { hit = true; p = __dmul_rn(fwd_val[lo], q_val[i]); nonfirst += (di != fd); }
+        int64_t pos;
+        if (staged) {
+          int lo = 0, hi = nc;                       // first k with win[k] >= di
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (win[mid] < di) lo = mid + 1; else hi = mid; }
+          hit = lo < nc && win[lo] == di; pos = j0 + lo;
+        } else {
+          int64_t lo = j0, hi = je;                  // first j with fwd_idx[j] >= di
+          while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (fwd_idx[mid] < di) lo = mid + 1; else hi = mid; }
+          hit = lo < je && fwd_idx[lo] == di; pos = lo;
+        }
+        if (hit) { p = __dmul_rn(fwd_val[pos], q_val[i]); nonfirst += (di != fd); }
       }
       unsigned m = __ballot_sync(FULL, hit);
       while (m) {                                    // ascending lane = ascending dimension

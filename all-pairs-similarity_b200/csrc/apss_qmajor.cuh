@@ -165,6 +165,8 @@ struct QmArgs {
   int32_t* out_q; int32_t* out_c; float* out_est; unsigned long long out_cap;
   unsigned long long* counters;
   int32_t* deferred; int32_t deferred_cap;   // queries the pipelined kernel left to the ranged kernel (count in C_HEAVY)
+  int32_t* hot_q; int32_t* hot_c; float* hot_est; unsigned hot_cap;     // pipelined kernel: candidates that crossed the query's
+                                 // coarse threshold, written in per-CTA chunks reserved on C_HOTN (q = -1: unused entry)
   int32_t from_list;             // k_score_qm: 0 = take every query from the cursor, 1 = take the deferred list
 };
 
@@ -366,6 +368,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT / 2 * 1) k_score_qm(const QmArgs
 static constexpr int QP_NCW = 31;                 // consumer warps
 static constexpr int QP_SP = 2 * QP_NCW;          // pieces per stage (two per consumer warp)
 static constexpr int QP_STAGES = 2;
+static constexpr int QP_QG = 8;                   // queries whose set-up chain the producer runs at once (one per lane)
 static constexpr int QP_SLOT = 512;               // bytes per piece slot
 static constexpr int QP_STAGE_BYTES = QP_SP * QP_SLOT;
 static constexpr int QP_TBL = 19712;              // table slots: 232448 - ring - hot list - metadata, in 8-byte slots
@@ -399,6 +402,19 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// predicated shared-memory atomics: no branch around the instruction (the consumer loop is issue bound)
+__device__ __forceinline__ unsigned atoms_cas_if(unsigned addr, unsigned val, bool on) {
+  unsigned old = 0;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.cas.b32 %0, [%1], 0, %2;\n\t}" : "+r"(old) : "r"(addr), "r"(val), "r"((unsigned)on) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned atoms_add_if(unsigned addr, unsigned val, bool on) {
+  unsigned old = 0;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}" : "+r"(old) : "r"(addr), "r"(val), "r"((unsigned)on) : "memory");
+  return old;
+}
+static constexpr unsigned QP_CHUNK = 32768;        // entries of the hot-candidate buffer a CTA reserves at a time (>= QP_TBL)
+
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(QP_NCW * 32) : "memory"); }
 
 template <bool DUPKEYS>
@@ -411,7 +427,7 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
   uint2* meta = reinterpret_cast<uint2*>(ring + (size_t)QP_STAGES * QP_STAGE_BYTES);     // per piece: (len | odd << 16, weight bits)
   QpHdr* hdr = reinterpret_cast<QpHdr*>(meta + QP_STAGES * QP_SP);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(hdr + QP_STAGES);    // full[QP_STAGES], empty[QP_STAGES]
-  __shared__ unsigned s_hot_n;
+  __shared__ unsigned s_hot_n, s_out_n, s_chunk_pos, s_chunk_end, s_chunk_next;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid * 4; i < 2 * QP_TBL; i += 1024 * 4) *reinterpret_cast<uint4*>(keys + i) = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
@@ -423,42 +439,76 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
 
   if (warp == 0) {
     // ------------------------------------------------ producer
+    // Two latencies are kept off the critical path: (1) the per-query chain cursor -> q_ptr -> offsets -> norm is run
+    // for QP_QG queries at once, one query per lane; (2) the piece descriptors of stage s + 1 are loaded before stage s
+    // is filled, so the only waits left are the ring's own empty barriers.
     int stage = 0; unsigned phase = 0; unsigned long long n_post = 0;
-    auto next_stage = [&]() { if (++stage == QP_STAGES) { stage = 0; phase ^= 1u; } };
-    for (;;) {
-      int q = 0;
-      if (lane == 0) q = (int)atomicAdd(&a.counters[C_WORK], 1ULL);
-      q = __shfl_sync(FULL, q, 0);
-      if (q >= a.nq) break;
-      const int t0 = __ldg(a.q_ptr + q), t1 = __ldg(a.q_ptr + q + 1);
-      if (t0 == t1) continue;
-      const unsigned long long o0 = __ldg(a.item_off + t0), o1 = __ldg(a.item_off + t1);
-      const long long i0 = (long long)(o0 >> 36), i1 = min((long long)(o1 >> 36), a.item_cap);
-      if (i0 >= i1) continue;
-      const long long total = (long long)((o1 & 0xfffffffffULL) - (o0 & 0xfffffffffULL));
-      if (total > a.cap) {                                     // too long for one table pass: the ranged kernel takes it
-        if (lane == 0) { const unsigned long long k = atomicAdd(&a.counters[C_HEAVY], 1ULL); if (k < (unsigned long long)a.deferred_cap) a.deferred[k] = q; }
-        continue;
-      }
-      n_post += (unsigned long long)total;
-      const float qn = __ldg(a.q_nrm + q);
-      long long qkey = 0;
-      if (DUPKEYS) qkey = __ldg(a.q_key + q);
-      for (long long base = i0; base < i1; base += QP_SP) {
-        const int np = (int)min((long long)QP_SP, i1 - base);
-        uint4 d[2]; unsigned bytes[2] = {0u, 0u}; unsigned sum = 0;
+    auto load_desc = [&](const long long base, const int np, uint4 (&d)[2]) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {                          // descriptors first: they do not depend on the ring
-          const int k = lane + 32 * r;
-          d[r] = make_uint4(0, 0, 0, 0);
-          if (k < np) {
-            d[r] = __ldg(reinterpret_cast<const uint4*>(a.items + base + k));
-            bytes[r] = ((((d[r].x >> 3) & 1u) + d[r].z) * 8u + 15u) & ~15u;
-            sum += bytes[r];
+      for (int r = 0; r < 2; ++r) {
+        const int k = lane + 32 * r;
+        d[r] = make_uint4(0, 0, 0, 0);
+        if (k < np) d[r] = __ldg(reinterpret_cast<const uint4*>(a.items + base + k));
+      }
+    };
+    for (;;) {
+      int qbase = 0;
+      if (lane == 0) qbase = (int)atomicAdd(&a.counters[C_WORK], (unsigned long long)QP_QG);
+      qbase = __shfl_sync(FULL, qbase, 0);
+      if (qbase >= a.nq) break;
+      // ---- one query per lane: the whole set-up chain in parallel
+      const int myq = qbase + lane;
+      long long my_i0 = 0, my_i1 = 0, my_total = 0, my_qkey = 0; float my_qn = 0.f; bool my_ok = false;
+      if (lane < QP_QG && myq < a.nq) {
+        const int t0 = __ldg(a.q_ptr + myq), t1 = __ldg(a.q_ptr + myq + 1);
+        if (t0 != t1) {
+          const unsigned long long o0 = __ldg(a.item_off + t0), o1 = __ldg(a.item_off + t1);
+          my_i0 = (long long)(o0 >> 36); my_i1 = min((long long)(o1 >> 36), a.item_cap);
+          my_total = (long long)((o1 & 0xfffffffffULL) - (o0 & 0xfffffffffULL));
+          my_ok = my_i0 < my_i1;
+          if (my_ok && my_total > a.cap) {                     // too long for one table pass: the ranged kernel takes it
+            const unsigned long long k = atomicAdd(&a.counters[C_HEAVY], 1ULL);
+            if (k < (unsigned long long)a.deferred_cap) a.deferred[k] = myq;
+            my_ok = false;
           }
+          if (my_ok) {
+            n_post += (unsigned long long)my_total;
+            my_qn = __ldg(a.q_nrm + myq);
+            if (DUPKEYS) my_qkey = __ldg(a.q_key + myq);
+          }
+        }
+      }
+      unsigned okmask = __ballot_sync(FULL, my_ok);
+      if (!okmask) continue;
+      // ---- the group's stages in order, descriptors one stage ahead
+      int g = __ffs(okmask) - 1;
+      long long base = __shfl_sync(FULL, my_i0, g), gi1 = __shfl_sync(FULL, my_i1, g);
+      uint4 d[2];
+      load_desc(base, (int)min((long long)QP_SP, gi1 - base), d);
+      while (g >= 0) {
+        const int np = (int)min((long long)QP_SP, gi1 - base);
+        const bool first = base == __shfl_sync(FULL, my_i0, g), last = base + QP_SP >= gi1;
+        // what comes next: the query's next stage, or the first stage of the group's next query
+        int ng = g; long long nbase = base + QP_SP, ngi1 = gi1;
+        if (last) {
+          okmask &= ~(1u << g);
+          ng = okmask ? __ffs(okmask) - 1 : -1;
+          const int src = ng >= 0 ? ng : 0;
+          nbase = __shfl_sync(FULL, my_i0, src); ngi1 = __shfl_sync(FULL, my_i1, src);
+        }
+        uint4 dn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (ng >= 0) load_desc(nbase, (int)min((long long)QP_SP, ngi1 - nbase), dn);
+        // ---- fill this stage
+        unsigned bytes[2], sum = 0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          bytes[r] = (lane + 32 * r < np) ? (((((d[r].x >> 3) & 1u) + d[r].z) * 8u + 15u) & ~15u) : 0u;
+          sum += bytes[r];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        const int qv = qbase + g; const long long tv = __shfl_sync(FULL, my_total, g);
+        const float qnv = __shfl_sync(FULL, my_qn, g); const long long qkv = __shfl_sync(FULL, my_qkey, g);
         mbar_wait(smem_u32(bars + QP_STAGES + stage), phase ^ 1u);          // the consumers have released this stage
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -466,8 +516,8 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
           if (k < np) meta[stage * QP_SP + k] = make_uint2(d[r].z | (((d[r].x >> 3) & 1u) << 16), d[r].w);
         }
         if (lane == 0) {
-          QpHdr hh; hh.q = q; hh.np = np; hh.total = (int)total; hh.qn = qn; hh.pad = 0; hh.qkey = qkey;
-          hh.flags = (base == i0 ? QP_F_FIRST : 0) | (base + QP_SP >= i1 ? QP_F_LAST : 0);
+          QpHdr hh; hh.q = qv; hh.np = np; hh.total = (int)tv; hh.qn = qnv; hh.pad = 0; hh.qkey = qkv;
+          hh.flags = (first ? QP_F_FIRST : 0) | (last ? QP_F_LAST : 0);
           hdr[stage] = hh;
         }
         __syncwarp();
@@ -481,11 +531,14 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
             bulk_g2s(smem_u32(ring + (size_t)stage * QP_STAGE_BYTES + (size_t)k * QP_SLOT), reinterpret_cast<const void*>(pp & ~15ULL), bytes[r], smem_u32(bars + stage));
           }
         }
-        next_stage();
+        if (++stage == QP_STAGES) { stage = 0; phase ^= 1u; }
+        g = ng; base = nbase; gi1 = ngi1; d[0] = dn[0]; d[1] = dn[1];
       }
     }
     // no more queries: one empty END stage
     mbar_wait(smem_u32(bars + QP_STAGES + stage), phase ^ 1u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_post += __shfl_down_sync(FULL, n_post, o);
     if (lane == 0) {
       QpHdr hh; hh.q = a.nq; hh.np = 0; hh.total = 0; hh.qn = 0.f; hh.pad = 0; hh.qkey = 0; hh.flags = QP_F_END;
       hdr[stage] = hh;
@@ -498,6 +551,13 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
   // -------------------------------------------------- consumers
   const int cw = warp - 1, ctid = tid - 32;
   constexpr int CT = QP_NCW * 32;
+  const unsigned keys_s = smem_u32(keys), vals_s = smem_u32(vals);
+  if (ctid == 0) {               // two chunks of the hot-candidate buffer up front; a new one is reserved whenever one is taken
+    s_chunk_pos = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
+    s_chunk_end = s_chunk_pos + QP_CHUNK;
+    s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
+    s_out_n = 0u;
+  }
   int stage = 0; unsigned phase = 0; unsigned n_cand = 0;
   unsigned size = 256u, thr_fix = 0u, self = 0xffffffffu; bool scan_all = true; float qn = 0.f; long long qkey = 0; int q = 0;
   for (;;) {
@@ -542,55 +602,82 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
           slot[e] = __umulhi(cc[e] * 0x9E3779B1u, size);
         }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { old[e] = 0u; if (on[e]) old[e] = atomicCAS(keys + slot[e], 0u, cc[e] + 1u); }
+      for (int e = 0; e < 4; ++e) old[e] = atoms_cas_if(keys_s + slot[e] * 4u, cc[e] + 1u, on[e]);
+      bool coll = false;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (!on[e]) continue;
-        const unsigned k1 = cc[e] + 1u;
-        if (old[e] != 0u && old[e] != k1) {                   // occupied by another candidate: linear probing
-          unsigned sl_ = slot[e];
-          for (;;) {
-            if (++sl_ == size) sl_ = 0;
-            const unsigned o = atomicCAS(keys + sl_, 0u, k1);
-            if (o == 0u || o == k1) { old[e] = o; break; }
+      for (int e = 0; e < 4; ++e) coll |= on[e] && old[e] != 0u && old[e] != cc[e] + 1u;
+      if (coll) {                                              // a slot held by another candidate: linear probing (one branch for all four)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const unsigned k1 = cc[e] + 1u;
+          if (on[e] && old[e] != 0u && old[e] != k1) {
+            unsigned sl_ = slot[e];
+            for (;;) {
+              if (++sl_ == size) sl_ = 0;
+              const unsigned o = atomicCAS(keys + sl_, 0u, k1);
+              if (o == 0u || o == k1) { old[e] = o; break; }
+            }
+            slot[e] = sl_;
           }
-          slot[e] = sl_;
         }
-        if (!DUPKEYS) n_cand += old[e] == 0u;                 // (with caller keys: counted in the scan, same-key candidates do not count)
       }
+      unsigned prev[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        if (!on[e]) continue;
-        const unsigned prev = atomicAdd(vals + slot[e], contrib[e]);
-        if (!scan_all && prev < thr_fix && prev + contrib[e] >= thr_fix) {
-          const unsigned h = atomicAdd(&s_hot_n, 1u);
-          if (h < (unsigned)QM_HOT) hot[h] = (int)slot[e];
-        }
+        if (!DUPKEYS) n_cand += (unsigned)(on[e] && old[e] == 0u);      // (caller keys: counted in the scan; same-key candidates do not count)
+        prev[e] = atoms_add_if(vals_s + slot[e] * 4u, contrib[e], on[e]);
+      }
+      bool anyhot = false;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) anyhot |= on[e] && prev[e] < thr_fix && prev[e] + contrib[e] >= thr_fix;
+      if (anyhot && !scan_all) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (on[e] && prev[e] < thr_fix && prev[e] + contrib[e] >= thr_fix) {
+            const unsigned h = atomicAdd(&s_hot_n, 1u);
+            if (h < (unsigned)QM_HOT) hot[h] = (int)slot[e];
+          }
       }
     }
-    if (hh.flags & QP_F_LAST) {                                  // consumer-only epilogue of the query
-      auto test_emit = [&](const unsigned k, const unsigned vv) {
-        const long long c = (long long)k - 1;
-        if (DUPKEYS) { if (__ldg(a.c_key + c) == qkey) return; ++n_cand; }
-        const float est = __uint2float_ru(vv) * a.inv_scale;
-        const float ub = __fmul_ru(__ldg(a.row_ub + c), qn);
-        if (__fmaf_ru(est, a.band1, ub) >= a.thr) {
-          const unsigned long long o = atomicAdd(&a.counters[C_PF], 1ULL);
-          if (o < a.out_cap) { a.out_q[o] = q; a.out_c[o] = (int32_t)c; a.out_est[o] = est; }
-        }
-      };
+    if (hh.flags & QP_F_LAST) {
+      // ---- consumer-only epilogue.  No global round trip here: the candidates that crossed the coarse threshold go,
+      // with their final sums, to this CTA's chunk of the hot-candidate buffer; k_qm_filter applies the exact test.
       consumer_bar();
       const unsigned nh = s_hot_n;
-      if (scan_all || nh > (unsigned)QM_HOT) {
-        for (unsigned i = ctid; i < size; i += CT) { const unsigned k = keys[i]; if (k) test_emit(k, vals[i]); }
+      const bool full = scan_all || nh > (unsigned)QM_HOT;
+      if (full) {                                              // rare: every touched slot is written; make room for `size` entries
+        if (ctid == 0 && s_chunk_pos + size > s_chunk_end) {
+          s_chunk_pos = s_chunk_next; s_chunk_end = s_chunk_next + QP_CHUNK;
+          s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
+        }
+        consumer_bar();
+      }
+      const unsigned cpos = s_chunk_pos;
+      auto put = [&](const unsigned at, const unsigned k, const unsigned vv) {
+        const unsigned o = cpos + at;
+        if (o < a.hot_cap) { a.hot_q[o] = q; a.hot_c[o] = (int32_t)(k - 1u); a.hot_est[o] = __uint2float_ru(vv) * a.inv_scale; }
+      };
+      if (full) {
+        for (unsigned i = ctid; i < size; i += CT) {
+          const unsigned k = keys[i];
+          if (!k) continue;
+          if (DUPKEYS) { if (__ldg(a.c_key + (k - 1u)) == qkey) continue; ++n_cand; }
+          put(atomicAdd(&s_out_n, 1u), k, vals[i]);
+        }
       } else {
-        for (unsigned e = ctid; e < nh; e += CT) { const int s = hot[e]; test_emit(keys[s], vals[s]); }
+        for (unsigned e = ctid; e < nh; e += CT) { const int sl_ = hot[e]; put(e, keys[sl_], vals[sl_]); }
       }
       consumer_bar();
       for (unsigned i = ctid * 4; i < size; i += CT * 4) {
         *reinterpret_cast<uint4*>(keys + i) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(vals + i) = make_uint4(0, 0, 0, 0);
       }
-      if (ctid == 0) s_hot_n = 0u;
+      if (ctid == 0) {
+        s_chunk_pos += full ? s_out_n : nh; s_out_n = 0u; s_hot_n = 0u;
+        if (s_chunk_pos + (unsigned)QM_HOT > s_chunk_end) {    // the next query's hot list always fits
+          s_chunk_pos = s_chunk_next; s_chunk_end = s_chunk_next + QP_CHUNK;
+          s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
+        }
+      }
       consumer_bar();
     }
     if (++stage == QP_STAGES) { stage = 0; phase ^= 1u; }
@@ -599,6 +686,36 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nc += __shfl_down_sync(FULL, nc, o);
   if (lane == 0 && nc) atomicAdd(&a.counters[C_CANDS], nc);
+}
+
+
+// The exact candidate test of the pipelined kernel, moved out of its epilogue: one thread per entry of the hot-candidate
+// buffer (q = -1: never written),  estimate * (1 + guard band) + |q| * |c_unindexed| >= t,  survivors compacted into
+// the record list of the fp64 verify kernel (warp-aggregated).
+__global__ void k_qm_filter(const QmArgs a) {
+  const unsigned long long n = min(a.counters[C_HOTN], (unsigned long long)a.hot_cap);
+  const int lane = threadIdx.x & 31;
+  for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ULL; i0 < n; i0 += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long i = i0 + lane;
+    bool pass = false; int q = -1, c = 0; float est = 0.f;
+    if (i < n) {
+      q = a.hot_q[i];
+      if (q >= 0) {
+        c = a.hot_c[i]; est = a.hot_est[i];
+        const float ub = __fmul_ru(__ldg(a.row_ub + c), __ldg(a.q_nrm + q));
+        pass = __fmaf_ru(est, a.band1, ub) >= a.thr;
+      }
+    }
+    const unsigned bal = __ballot_sync(FULL, pass);
+    if (!bal) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&a.counters[C_PF], (unsigned long long)__popc(bal));
+    base = __shfl_sync(FULL, base, 0);
+    if (pass) {
+      const unsigned long long o = base + __popc(bal & ((1u << lane) - 1u));
+      if (o < a.out_cap) { a.out_q[o] = q; a.out_c[o] = c; a.out_est[o] = est; }
+    }
+  }
 }
 
 }  // namespace apss

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--n-index", type=int, default=0)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed batches (ncu --profile-from-start off)")
     ap.add_argument("variants", nargs="*", default=["mode=3"])
     args = ap.parse_args()
     cfg = dict(synth.CONFIGS[args.config])
@@ -59,19 +60,23 @@ def main():
             eng.insert_batch(*rows(lo, min(N, lo + B)), index_only=True)
         torch.cuda.synchronize()
         t_load = time.time() - t0
-        sc, dv, wl, pv, cu, pr = [], [], [], 0, 0, 0
+        sc, dv, wl, pv, cu, pr, pf = [], [], [], 0, 0, 0, 0
         for i in range(nb):
             r_in = rows(N + i * B, N + (i + 1) * B)
             torch.cuda.synchronize()
+            if args.profile_range and i == args.warmup:
+                torch.cuda.profiler.start()
             w0 = time.time()
             r = eng.insert_batch(*r_in)
             w1 = time.time()
             if i >= args.warmup:
                 sc.append(r.score_ms); dv.append(r.device_ms); wl.append((w1 - w0) * 1e3)
-                pv += r.postings_visited; cu += r.candidates_unique; pr += r.n_pairs
+                pv += r.postings_visited; cu += r.candidates_unique; pr += r.n_pairs; pf += r.n_prefilter
+        if args.profile_range:
+            torch.cuda.profiler.stop()
         st = eng.stats()
         rec = {"variant": var, "score_ms": sum(sc) / len(sc), "device_ms": sum(dv) / len(dv), "wall_ms": sum(wl) / len(wl),
-               "postings_per_step": pv / len(sc), "cands_per_step": cu / len(sc), "pairs": pr, "preload_s": t_load,
+               "postings_per_step": pv / len(sc), "cands_per_step": cu / len(sc), "pairs": pr, "prefilter_per_step": pf / len(sc), "preload_s": t_load,
                "segments_or_tiles": st["n_tiles"], "merges": st.get("segment_merges"), "alg_GBps": 8e-9 * pv / (sum(sc) * 1e-3) if sum(sc) else None}
         print(json.dumps(rec), flush=True)
         out.append(rec)
