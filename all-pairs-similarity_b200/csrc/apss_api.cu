@@ -800,6 +800,7 @@ static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, i
     CK(cudaMemsetAsync(h->hot_q.p, 0xff, sizeof(int32_t) * h->hot_q.cap, s));
     CK(cudaMemsetAsync(h->d_counters + C_HOTN, 0, sizeof(unsigned long long), s));
     QmArgs ap = a; ap.cap = std::min(a.cap, QP_CAP);
+    { const char* e = getenv("APSS_QM_DRY"); ap.dry = e ? atoi(e) : 0; }
     ap.hot_q = h->hot_q.p; ap.hot_c = h->hot_c.p; ap.hot_est = h->hot_est.p; ap.hot_cap = (unsigned)std::min<size_t>(h->hot_q.cap, 0xffff0000u);
     auto kern = h->custom_keys ? k_score_qm_pipe<true> : k_score_qm_pipe<false>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QP_SMEM));

@@ -168,6 +168,7 @@ struct QmArgs {
   int32_t* hot_q; int32_t* hot_c; float* hot_est; unsigned hot_cap;     // pipelined kernel: candidates that crossed the query's
                                  // coarse threshold, written in per-CTA chunks reserved on C_HOTN (q = -1: unused entry)
   int32_t from_list;             // k_score_qm: 0 = take every query from the cursor, 1 = take the deferred list
+  int32_t dry;                   // measurement only (APSS_QM_DRY): 1 = no table updates, 2 = no copies either
 };
 
 template <int NT>
@@ -521,12 +522,12 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
           hdr[stage] = hh;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(smem_u32(bars + stage), sum);
+        if (lane == 0) mbar_arrive_expect_tx(smem_u32(bars + stage), a.dry == 2 ? 0u : sum);
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const int k = lane + 32 * r;
-          if (k < np) {
+          if (k < np && a.dry != 2) {
             const unsigned long long pp = ((unsigned long long)d[r].y << 32) | d[r].x;
             bulk_g2s(smem_u32(ring + (size_t)stage * QP_STAGE_BYTES + (size_t)k * QP_SLOT), reinterpret_cast<const void*>(pp & ~15ULL), bytes[r], smem_u32(bars + stage));
           }
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
           const int e = 2 * r + u;
           cc[e] = u ? v[r].z : v[r].x;
           const float w = __uint_as_float(u ? v[r].w : v[r].y);
-          on[e] = jj[r] + u >= 0 && jj[r] + u < ln[r] && cc[e] != self;
+          on[e] = jj[r] + u >= 0 && jj[r] + u < ln[r] && cc[e] != self && !a.dry;
           contrib[e] = __float2uint_ru(__fmul_ru(w, ws[r]));
           slot[e] = __umulhi(cc[e] * 0x9E3779B1u, size);
         }
