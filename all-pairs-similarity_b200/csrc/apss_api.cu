@@ -9,6 +9,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -137,7 +141,10 @@ struct VmBuf {
 
 }  // namespace
 
+struct MultiState;
+
 struct apss_handle {
+  MultiState* multi = nullptr;   // n_devices > 1: this handle is the shard dispatcher over one engine per GPU (see the end of the file)
   apss_config cfg{};
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -344,14 +351,28 @@ static cudaError_t launch_cand(apss_handle* h, const CandArgs& a) {
 
 extern "C" int32_t apss_abi_version(void) { return APSS_ABI_VERSION; }
 
+static int32_t multi_create(const apss_config* cfg, apss_handle** out);
+static void multi_destroy(apss_handle* h);
+static int32_t multi_insert_batch(apss_handle* h, int32_t n, const int64_t* indptr, const int32_t* indices, const double* values,
+                                  const int64_t* ext_keys, const int32_t* first_dim, uint32_t flags, apss_batch_result* out);
+static int32_t multi_fetch_pairs(apss_handle* h, int32_t* q, int32_t* c, double* sim, int64_t capacity, int64_t* n_out);
+static int32_t multi_get_stats(apss_handle* h, apss_stats* out);
+static int32_t multi_fetch_status(apss_handle* h, uint8_t* status, int32_t capacity);
+static int32_t multi_freeze(apss_handle* h);
+static int32_t multi_set_next_id(apss_handle* h, int64_t next_id);
+
 extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   if (!cfg || !out || cfg->struct_size != (int32_t)sizeof(apss_config)) return APSS_E_INVALID;
   *out = nullptr;
+  if (cfg->n_devices < 0 || cfg->n_devices > APSS_MAX_DEVICES) return APSS_E_INVALID;
+  if (cfg->n_devices > 1) return multi_create(cfg, out);
   if (cfg->dim <= 0 || cfg->dim > (1 << 30) || !(cfg->index_threshold >= 0.0) || !(cfg->similarity_threshold == cfg->similarity_threshold) || (cfg->semantics != APSS_SEM_R1 && cfg->semantics != APSS_SEM_R0)) return APSS_E_INVALID;
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) { cudaGetLastError(); return APSS_E_NO_DEVICE; }
+  const int dev0 = cfg->n_devices == 1 ? cfg->device_ids[0] : cfg->device;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || dev0 < 0 || dev0 >= ndev) { cudaGetLastError(); return APSS_E_NO_DEVICE; }
   apss_handle* h = new apss_handle();
-  h->cfg = *cfg; h->cfg.max_weight = nullptr; h->device = cfg->device;
+  h->cfg = *cfg; h->cfg.max_weight = nullptr; h->device = cfg->n_devices == 1 ? cfg->device_ids[0] : cfg->device;
+  h->cfg.device = h->device;
   h->fwd_skip.device = h->row_ub.device = h->heavy.device = h->ifw_ptr.device = h->ifw.device = cfg->device;
   h->fwd_ptr.device = h->fwd_idx.device = h->fwd_val.device = h->gid.device = h->key.device = h->post.device = h->dir.device =
       h->tile_base.device = h->dn_cnt.device = h->dn_dim.device = h->dn_len.device = h->tile_cnt.device = h->dn_hash.device =
@@ -477,6 +498,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
 
 extern "C" void apss_destroy(apss_handle* h) {
   if (!h) return;
+  if (h->multi) { multi_destroy(h); return; }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->fwd_ptr.release(); h->fwd_idx.release(); h->fwd_val.release(); h->gid.release(); h->key.release();
@@ -935,6 +957,7 @@ static void rollback_batch(apss_handle* h, const BatchTxn& txn) {
 extern "C" int32_t apss_insert_batch(apss_handle* h, int32_t n, const int64_t* indptr, const int32_t* indices, const double* values,
                                      const int64_t* ext_keys, const int32_t* first_dim, uint32_t flags, apss_batch_result* out) {
   if (!h) return APSS_E_INVALID;
+  if (h->multi) return multi_insert_batch(h, n, indptr, indices, values, ext_keys, first_dim, flags, out);
   if (h->broken) return h->fail(APSS_E_STATE, "handle retired after a failed batch that could not be rolled back; destroy it");
   BatchTxn txn{h->n_local, h->nnz, h->n_post, h->ntiles, h->next_id, h->segs.size(), h->max_nnz_seen, h->max_sq, h->custom_keys};
   const int32_t rc = insert_batch_impl(h, txn, n, indptr, indices, values, ext_keys, first_dim, flags, out);
@@ -1156,6 +1179,7 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
 
 extern "C" int32_t apss_fetch_pairs(apss_handle* h, int32_t* q, int32_t* c, double* sim, int64_t capacity, int64_t* n_out) {
   if (!h) return APSS_E_INVALID;
+  if (h->multi) return multi_fetch_pairs(h, q, c, sim, capacity, n_out);
   if (h->last_n < 0) return h->fail(APSS_E_STATE, "no completed batch to fetch from");
   CK(cudaSetDevice(h->device));
   const int64_t m = std::min<int64_t>(h->last_pairs, capacity < 0 ? 0 : capacity);
@@ -1171,6 +1195,7 @@ extern "C" int32_t apss_fetch_pairs(apss_handle* h, int32_t* q, int32_t* c, doub
 
 extern "C" int32_t apss_pairs_device(apss_handle* h, const int32_t** q, const int32_t** c, const double** sim, int64_t* n) {
   if (!h) return APSS_E_INVALID;
+  if (h->multi) return h->fail(APSS_E_STATE, "apss_pairs_device: the pairs of a multi-device handle live on several GPUs; use apss_fetch_pairs");
   if (h->last_n < 0) return h->fail(APSS_E_STATE, "no completed batch");
   if (q) *q = h->out_q.p;
   if (c) *c = h->out_c.p;
@@ -1181,16 +1206,18 @@ extern "C" int32_t apss_pairs_device(apss_handle* h, const int32_t** q, const in
 
 extern "C" int32_t apss_fetch_status(apss_handle* h, uint8_t* status, int32_t capacity) {
   if (!h || !status) return APSS_E_INVALID;
+  if (h->multi) return multi_fetch_status(h, status, capacity);
   if (h->last_n < 0) return h->fail(APSS_E_STATE, "no completed batch");
   const int32_t m = std::min<int32_t>(capacity, (int32_t)h->last_status.size());
   if (m > 0) std::memcpy(status, h->last_status.data(), m);
   return APSS_OK;
 }
 
-extern "C" int32_t apss_freeze(apss_handle* h) { if (!h) return APSS_E_INVALID; h->frozen = true; return APSS_OK; }
+extern "C" int32_t apss_freeze(apss_handle* h) { if (!h) return APSS_E_INVALID; if (h->multi) return multi_freeze(h); h->frozen = true; return APSS_OK; }
 
 extern "C" int32_t apss_set_next_id(apss_handle* h, int64_t next_id) {
   if (!h) return APSS_E_INVALID;
+  if (h->multi) return multi_set_next_id(h, next_id);
   if (next_id < 0 || next_id > 0x7fffffffLL) return h->fail(APSS_E_INVALID, "next_id out of int32 range");
   h->next_id = next_id;
   return APSS_OK;
@@ -1198,6 +1225,7 @@ extern "C" int32_t apss_set_next_id(apss_handle* h, int64_t next_id) {
 
 extern "C" int32_t apss_get_stats(apss_handle* h, apss_stats* out) {
   if (!h || !out) return APSS_E_INVALID;
+  if (h->multi) return multi_get_stats(h, out);
   apss_stats s{};
   s.n_vectors = h->n_local; s.n_postings = h->n_post; s.n_tiles = h->prune_mode == 3 ? (int64_t)h->segs.size() : h->ntiles;   // pruning = 3: posting segments
   s.bytes_postings = h->n_post * 8; s.bytes_directory = s.n_tiles * ((int64_t)h->cfg.dim + 1) * 4;
@@ -1212,7 +1240,236 @@ extern "C" int32_t apss_get_stats(apss_handle* h, apss_stats* out) {
 }
 
 extern "C" const char* apss_last_error(apss_handle* h) { return h ? h->err.c_str() : "null handle"; }
-extern "C" void* apss_stream(apss_handle* h) { return h ? (void*)h->stream : nullptr; }
+// (multi-device handle: the stream of the first shard; every shard has its own)
+extern "C" void* apss_stream(apss_handle* h);
+
+
+// ================================================================================================ shard dispatch below the ABI
+//
+// apss_config.n_devices > 1 (replaces the remote router EPA:37-49,113-122): ONE handle owns several GPUs
+// in one process.  The index is partitioned by internal-id range, block-cyclic: the batch with number b is indexed by
+// shard b mod N (and scored there against itself: IWA:125-132), every other shard scores it query-only against its own
+// vectors, so every pair is found exactly once.  One worker thread per GPU drives that GPU's engine (the single-device
+// handle above); the calling thread only fans the batch out and merges the results:
+//   host batch    every worker copies it to its own GPU (N host-to-device copies in parallel, one PCIe link each);
+//   device batch  (APSS_BATCH_DEVICE_PTRS) staged once, then sent to the other GPUs with cudaMemcpyPeerAsync -- NVLink --
+//                 and each engine reads its own copy.
+// Pair lists stay on the shards until apss_fetch_pairs gathers them (candidate ids are global: the dispatcher owns the id
+// space through apss_set_next_id).  A failure of the indexing shard is rolled back by that engine; a failure of a
+// query-only shard after the owner has indexed retires the handle (the batch cannot be un-indexed from outside).
+struct MultiState {
+  std::vector<apss_handle*> sh;
+  std::vector<std::thread> th;
+  std::mutex mu; std::condition_variable cv_go, cv_done;
+  std::vector<std::function<void()>> job; std::vector<uint64_t> want, done; bool stop = false;
+  int64_t next_id = 0, batch_no = 0; bool frozen = false, broken = false;
+  std::vector<apss_batch_result> res; std::vector<int32_t> rc;
+  int32_t last_n = -1; int64_t last_pairs = 0; int owner_last = 0;
+  // staging of device-pointer batches on every shard's GPU
+  struct Stage { DevBuf<int64_t> ptr, key; DevBuf<int32_t> idx, first; DevBuf<double> val; };
+  std::vector<Stage> stage;
+
+  void worker(int w) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<void()> f;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_go.wait(lk, [&] { return stop || want[w] > seen; });
+        if (stop) return;
+        seen = want[w]; f = job[w];
+      }
+      f();
+      { std::lock_guard<std::mutex> lk(mu); done[w] = seen; }
+      cv_done.notify_all();
+    }
+  }
+  // run f(w) on every shard's thread and wait for all of them
+  void run_all(const std::function<void(int)>& f) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t w = 0; w < sh.size(); ++w) { job[w] = [f, w] { f((int)w); }; ++want[w]; }
+    }
+    cv_go.notify_all();
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { for (size_t w = 0; w < sh.size(); ++w) if (done[w] != want[w]) return false; return true; });
+  }
+};
+
+static void multi_destroy(apss_handle* h) {
+  MultiState* m = h->multi;
+  { std::lock_guard<std::mutex> lk(m->mu); m->stop = true; }
+  m->cv_go.notify_all();
+  for (auto& t : m->th) if (t.joinable()) t.join();
+  for (size_t w = 0; w < m->sh.size(); ++w) {
+    if (!m->sh[w]) continue;
+    cudaSetDevice(m->sh[w]->device);
+    if (w < m->stage.size()) { auto& g = m->stage[w]; g.ptr.release(); g.key.release(); g.idx.release(); g.first.release(); g.val.release(); }
+    apss_destroy(m->sh[w]);
+  }
+  delete m;
+  delete h;
+}
+
+static int32_t multi_create(const apss_config* cfg, apss_handle** out) {
+  const int N = cfg->n_devices;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return APSS_E_NO_DEVICE; }
+  for (int a = 0; a < N; ++a) {
+    if (cfg->device_ids[a] < 0 || cfg->device_ids[a] >= ndev) return APSS_E_NO_DEVICE;
+    // (APSS_TEST_ALLOW_DUP_DEVICES: several shards on one GPU, so that the dispatch logic can be tested on a one-GPU box)
+    for (int b = 0; b < a; ++b) if (cfg->device_ids[a] == cfg->device_ids[b] && !getenv("APSS_TEST_ALLOW_DUP_DEVICES")) return APSS_E_INVALID;
+  }
+  apss_handle* h = new apss_handle();
+  h->cfg = *cfg; h->cfg.max_weight = nullptr; h->device = cfg->device_ids[0];
+  MultiState* m = h->multi = new MultiState();
+  m->sh.assign(N, nullptr); m->stage.resize(N); m->job.resize(N); m->want.assign(N, 0); m->done.assign(N, 0);
+  m->res.resize(N); m->rc.assign(N, APSS_OK);
+  for (int w = 0; w < N; ++w) {
+    apss_config c = *cfg;
+    c.n_devices = 0; c.device = cfg->device_ids[w];
+    c.reserve_vectors = cfg->reserve_vectors > 0 ? cfg->reserve_vectors / N + (1 << 16) : 0;
+    c.reserve_nnz = cfg->reserve_nnz > 0 ? cfg->reserve_nnz / N + (1 << 22) : 0;
+    const int32_t rc = apss_create(&c, &m->sh[w]);
+    if (rc != APSS_OK) { multi_destroy(h); return rc; }
+  }
+  // peer access for the NVLink fan-out of device-resident batches (best effort: without it the copies are staged by the driver)
+  for (int a = 0; a < N; ++a) {
+    cudaSetDevice(cfg->device_ids[a]);
+    for (int b = 0; b < N; ++b) if (a != b) { int can = 0; cudaDeviceCanAccessPeer(&can, cfg->device_ids[a], cfg->device_ids[b]); if (can) cudaDeviceEnablePeerAccess(cfg->device_ids[b], 0); }
+  }
+  cudaGetLastError();
+  for (int w = 0; w < N; ++w) m->th.emplace_back([m, w] { m->worker(w); });
+  *out = h;
+  return APSS_OK;
+}
+
+static int32_t multi_insert_batch(apss_handle* h, int32_t n, const int64_t* indptr, const int32_t* indices, const double* values,
+                                  const int64_t* ext_keys, const int32_t* first_dim, uint32_t flags, apss_batch_result* out) {
+  MultiState* m = h->multi;
+  const int N = (int)m->sh.size();
+  if (m->broken) return h->fail(APSS_E_STATE, "handle retired after a failed batch that could not be rolled back; destroy it");
+  if (n < 0 || (n > 0 && (!indptr || (!indices && !values)))) return h->fail(APSS_E_INVALID, "null batch arrays");
+  const bool query_only = (flags & APSS_BATCH_QUERY_ONLY) || m->frozen;
+  const int owner = (int)(m->batch_no % N);
+  m->last_n = -1; m->last_pairs = 0;
+  // device-resident batch: one staged copy per GPU over NVLink, issued on the owning engine's stream by its worker
+  const bool dev_ptrs = (flags & APSS_BATCH_DEVICE_PTRS) != 0;
+  int src_dev = -1; int64_t nnz = 0;
+  if (dev_ptrs && n > 0) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, indptr) != cudaSuccess || at.type != cudaMemoryTypeDevice) { cudaGetLastError(); return h->fail(APSS_E_INVALID, "APSS_BATCH_DEVICE_PTRS: indptr is not a device pointer"); }
+    src_dev = at.device;
+    cudaSetDevice(src_dev);
+    if (cudaMemcpy(&nnz, indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return h->fail(APSS_E_CUDA, "cannot read indptr[n]"); }
+    if (nnz < 0 || nnz > 0x7fffff00LL) return h->fail(APSS_E_INVALID, "batch too large: at most 2^31 components per call");
+  }
+  m->run_all([&](int w) {
+    apss_handle* e = m->sh[w];
+    uint32_t f = flags;
+    if (w != owner || query_only) f |= APSS_BATCH_QUERY_ONLY;
+    if (w != owner) f &= ~(uint32_t)APSS_BATCH_INDEX_ONLY;
+    if ((flags & APSS_BATCH_INDEX_ONLY) && w != owner && !query_only) {        // bulk load: the other shards have nothing to do
+      m->res[w] = apss_batch_result{}; m->rc[w] = APSS_OK; return;
+    }
+    apss_set_next_id(e, m->next_id);                  // default keys and candidate ids are GLOBAL internal ids
+    const int64_t* p = indptr; const int32_t* ix = indices; const double* v = values; const int64_t* k = ext_keys; const int32_t* fd = first_dim;
+    if (dev_ptrs && n > 0 && e->device != src_dev) {
+      MultiState::Stage& g = m->stage[w];
+      cudaSetDevice(e->device);
+      cudaStream_t s = e->stream;
+      bool ok = g.ptr.reserve((size_t)n + 1, 0, s) == cudaSuccess && g.idx.reserve((size_t)std::max<int64_t>(nnz, 1), 0, s) == cudaSuccess &&
+                g.val.reserve((size_t)std::max<int64_t>(nnz, 1), 0, s) == cudaSuccess;
+      ok = ok && cudaMemcpyPeerAsync(g.ptr.p, e->device, indptr, src_dev, sizeof(int64_t) * ((size_t)n + 1), s) == cudaSuccess;
+      if (ok && nnz) ok = cudaMemcpyPeerAsync(g.idx.p, e->device, indices, src_dev, sizeof(int32_t) * (size_t)nnz, s) == cudaSuccess &&
+                          cudaMemcpyPeerAsync(g.val.p, e->device, values, src_dev, sizeof(double) * (size_t)nnz, s) == cudaSuccess;
+      if (ok && ext_keys) { ok = g.key.reserve((size_t)n, 0, s) == cudaSuccess && cudaMemcpyPeerAsync(g.key.p, e->device, ext_keys, src_dev, sizeof(int64_t) * (size_t)n, s) == cudaSuccess; k = g.key.p; }
+      if (ok && first_dim) { ok = g.first.reserve((size_t)n, 0, s) == cudaSuccess && cudaMemcpyPeerAsync(g.first.p, e->device, first_dim, src_dev, sizeof(int32_t) * (size_t)n, s) == cudaSuccess; fd = g.first.p; }
+      if (!ok) { cudaGetLastError(); m->rc[w] = e->fail(APSS_E_CUDA, "peer copy of the batch to device %d failed", e->device); return; }
+      p = g.ptr.p; ix = g.idx.p; v = g.val.p;
+    }
+    m->rc[w] = apss_insert_batch(e, n, p, ix, v, k, fd, f, &m->res[w]);
+  });
+  // ---- merge
+  int32_t rc = m->rc[owner];
+  int bad = rc != APSS_OK ? owner : -1;
+  for (int w = 0; w < N && rc == APSS_OK; ++w) if (m->rc[w] != APSS_OK) { rc = m->rc[w]; bad = w; }
+  if (rc != APSS_OK) {
+    h->err = std::string("shard on device ") + std::to_string(m->sh[bad]->device) + ": " + m->sh[bad]->err;
+    if (m->rc[owner] == APSS_OK && !query_only) {      // the owner has indexed a batch the caller is told has failed
+      m->broken = true;
+      h->err += " (the owning shard had already indexed the batch: this handle is retired, destroy it)";
+    }
+    return rc;
+  }
+  apss_batch_result r{};
+  r.id_base = m->next_id; r.n_vectors = n;
+  r.n_rejected = m->res[owner].n_rejected; r.n_empty = m->res[owner].n_empty; r.n_active = m->res[owner].n_active;
+  for (int w = 0; w < N; ++w) {
+    const apss_batch_result& x = m->res[w];
+    r.n_pairs += x.n_pairs; r.n_pairs_r1 += x.n_pairs_r1; r.n_prefilter += x.n_prefilter; r.postings_visited += x.postings_visited;
+    r.candidates_unique += x.candidates_unique; r.work_items += x.work_items; r.dense_postings += x.dense_postings; r.dense_fma += x.dense_fma;
+    r.score_ms = std::max(r.score_ms, x.score_ms); r.device_ms = std::max(r.device_ms, x.device_ms);
+  }
+  if (!query_only) { m->next_id += n; m->batch_no += 1; }
+  m->last_n = n; m->last_pairs = r.n_pairs; m->owner_last = owner;
+  if (out) *out = r;
+  return APSS_OK;
+}
+
+static int32_t multi_fetch_pairs(apss_handle* h, int32_t* q, int32_t* c, double* sim, int64_t capacity, int64_t* n_out) {
+  MultiState* m = h->multi;
+  if (m->last_n < 0) return h->fail(APSS_E_STATE, "no completed batch to fetch from");
+  const int N = (int)m->sh.size();
+  std::vector<int64_t> off(N + 1, 0);
+  for (int w = 0; w < N; ++w) off[w + 1] = off[w] + m->res[w].n_pairs;
+  const int64_t cap = capacity < 0 ? 0 : capacity;
+  std::vector<int32_t> rc(N, APSS_OK);
+  if (cap > 0 && (q || c || sim))
+    m->run_all([&](int w) {                             // every shard copies its slice straight into the caller's arrays
+      const int64_t lo = std::min(off[w], cap), hi = std::min(off[w + 1], cap);
+      if (hi <= lo) return;
+      int64_t got = 0;
+      rc[w] = apss_fetch_pairs(m->sh[w], q ? q + lo : nullptr, c ? c + lo : nullptr, sim ? sim + lo : nullptr, hi - lo, &got);
+    });
+  for (int w = 0; w < N; ++w) if (rc[w] != APSS_OK) { h->err = m->sh[w]->err; return rc[w]; }
+  if (n_out) *n_out = m->last_pairs;
+  return APSS_OK;
+}
+
+static int32_t multi_fetch_status(apss_handle* h, uint8_t* status, int32_t capacity) {
+  MultiState* m = h->multi;
+  if (m->last_n < 0) return h->fail(APSS_E_STATE, "no completed batch");
+  return apss_fetch_status(m->sh[m->owner_last], status, capacity);
+}
+
+static int32_t multi_freeze(apss_handle* h) { h->multi->frozen = true; for (apss_handle* e : h->multi->sh) apss_freeze(e); return APSS_OK; }
+
+static int32_t multi_set_next_id(apss_handle* h, int64_t next_id) {
+  if (next_id < 0 || next_id > 0x7fffffffLL) return h->fail(APSS_E_INVALID, "next_id out of int32 range");
+  h->multi->next_id = next_id;
+  return APSS_OK;
+}
+
+extern "C" void* apss_stream(apss_handle* h) { return !h ? nullptr : (h->multi ? (void*)h->multi->sh[0]->stream : (void*)h->stream); }
+
+static int32_t multi_get_stats(apss_handle* h, apss_stats* out) {
+  MultiState* m = h->multi;
+  apss_stats s{};
+  for (apss_handle* e : m->sh) {
+    apss_stats x{};
+    apss_get_stats(e, &x);
+    s.n_vectors += x.n_vectors; s.n_postings += x.n_postings; s.n_tiles += x.n_tiles; s.bytes_postings += x.bytes_postings;
+    s.bytes_directory += x.bytes_directory; s.bytes_forward += x.bytes_forward; s.tot_postings_visited += x.tot_postings_visited;
+    s.tot_candidates_unique += x.tot_candidates_unique; s.tot_pairs += x.tot_pairs; s.tot_prefilter += x.tot_prefilter;
+    s.score_launches += x.score_launches; s.kernel_launches += x.kernel_launches; s.tot_score_ms = std::max(s.tot_score_ms, x.tot_score_ms);
+    s.n_unindexed += x.n_unindexed; s.segment_merges += x.segment_merges; s.merged_postings += x.merged_postings;
+    s.tile_vectors = x.tile_vectors; s.warps_per_cta = x.warps_per_cta; s.sm_count = x.sm_count;
+  }
+  s.frozen = m->frozen; s.n_devices = (int32_t)m->sh.size();
+  *out = s;
+  return APSS_OK;
+}
 
 extern "C" int32_t apss_microbench_accumulators(int32_t device, int32_t mode, int32_t warps, int32_t iters, double* updates_per_sec) {
   if (!updates_per_sec || warps < 1 || warps > 32) return APSS_E_INVALID;

@@ -23,12 +23,14 @@ static int failures = 0;
 
 static SparkSparseVector V(std::vector<std::pair<int32_t, double>> e, int size = 64) { return SparkSparseVector::sparse(size, std::move(e)); }
 
+static std::vector<int> g_devices;      // GPUs behind the one engine the actor holds (shards below the C ABI); empty = GPU 0
+
 static Engine* make_engine(int dim, double t, double idx_thr, bool as_built, int pruning) {
 #ifdef USE_ORACLE_ENGINE
   (void)pruning;
   return new Engine(dim, t, idx_thr, as_built);
 #else
-  return new Engine(dim, t, idx_thr, 0, as_built ? APSS_SEM_R0 : APSS_SEM_R1, pruning);
+  return new Engine(dim, t, idx_thr, 0, as_built ? APSS_SEM_R0 : APSS_SEM_R1, pruning, g_devices);
 #endif
 }
 
@@ -179,12 +181,13 @@ static void formats() {
 
 int main(int argc, char** argv) {
   const int pruning = argc > 1 ? std::atoi(argv[1]) : 0;
+  for (int a = 2; a < argc; ++a) g_devices.push_back(std::atoi(argv[a]));      // e.g. "0 1 2 3": device_ids of the one handle
   formats();
   scenario(pruning);
   buffered_output_and_router();
   as_built_first_list_skip();
   index_data_and_data_packet(pruning);
   if (failures) { std::fprintf(stderr, "%d check(s) failed\n", failures); return 1; }
-  std::printf("actor scenario ok (pruning=%d)\n", pruning);
+  std::printf("actor scenario ok (pruning=%d, devices=%zu)\n", pruning, g_devices.empty() ? (size_t)1 : g_devices.size());
   return 0;
 }

@@ -59,14 +59,26 @@ def test_cpp_actor_against_the_oracle_double(tmp_path):
     assert "vector1 size: 32, vector2 size: 64" in r.stderr          # the swallowed exception is logged (IWA:135-137)
 
 
+def _device_lists():
+    import torch
+    out = [[], [0, 0]]                       # one GPU; two shards on GPU 0 (test hook: the dispatch logic on a one-GPU box)
+    if torch.cuda.is_available() and torch.cuda.device_count() >= 2:
+        out.append(list(range(torch.cuda.device_count())))
+    return out
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("pruning", [0, 2, 3])
 def test_cpp_actor_through_the_c_abi(tmp_path, pruning):
+    """the C++ actor holds ONE engine; with device_ids = {0..N-1} the shard dispatch happens below the C ABI"""
     import apss_b200
     lib = apss_b200.native.LIB_PATH
     assert os.path.exists(lib), "libapss_b200.so has not been built"
     dirs = _cuda_lib_dirs()
     exe = _build(tmp_path, "actor_gpu", lib, lib_dirs=dirs)
-    r = subprocess.run([exe, str(pruning)], capture_output=True, text=True, timeout=300, env=_env(dirs))
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert "actor scenario ok (pruning=%d)" % pruning in r.stdout
+    for devs in _device_lists():
+        env = _env(dirs)
+        env["APSS_TEST_ALLOW_DUP_DEVICES"] = "1"
+        r = subprocess.run([exe, str(pruning)] + [str(d) for d in devs], capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "actor scenario ok (pruning=%d, devices=%d)" % (pruning, max(1, len(devs))) in r.stdout

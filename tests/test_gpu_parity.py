@@ -695,3 +695,54 @@ def test_int32_bounds_of_ids_and_component_counts():
     assert e.value.code == -1 and "id space" in str(e.value)
     rg = g.insert_batch(*csr_from_dicts([A, dict(A)]))     # two still fit
     assert rg.id_base == (1 << 31) - 3 and g.stats()["n_vectors"] == 2
+
+
+# ---------------------------------------------------------------- shard dispatch below the C ABI
+
+def _device_sets():
+    import torch
+    sets = [("dup", [0, 0, 0])]                       # three shards on GPU 0 (test hook): the dispatch logic on a one-GPU box
+    if torch.cuda.device_count() >= 2:
+        sets.append(("real", list(range(min(torch.cuda.device_count(), 4)))))
+    return sets
+
+
+@pytest.mark.parametrize("pruning", [0, 3])
+def test_multi_device_handle_matches_the_oracle(pruning, monkeypatch):
+    """apss_config.n_devices > 1: ONE handle, the index sharded by id range (block-cyclic by batch) over several engines.
+    Pairs, similarities and the summed counters are those of a single index worker; ids stay global; keys, query-only
+    batches, freeze, bulk load and device-resident batches (NVLink peer fan-out) go through the same entry points."""
+    import torch
+    N, D, t = 6000, 1 << 12, 0.6
+    data = _synth(N, D, 30, seed=11)
+    keys = np.arange(N, dtype=np.int64); keys[3::9] = keys[2:-1:9]
+    n = native()
+    monkeypatch.setenv("APSS_TEST_ALLOW_DUP_DEVICES", "1")
+    for name, devs in _device_sets():
+        o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8, pruning=bool(pruning))
+        g = n.Index(D, t, pruning=pruning, devices=devs)
+        assert g.stats()["n_devices"] == len(devs)
+        # bulk load of the first 1000 vectors (one shard indexes, the others have nothing to do), then live batches
+        o.insert_batch(*csr_slice(data, 0, 1000), index_only=True); g.insert_batch(*csr_slice(data, 0, 1000), index_only=True)
+        for lo, hi, use_keys, on_dev in [(1000, 2000, False, False), (2000, 2007, False, True), (2007, 3500, True, False),
+                                         (3500, 3501, True, True), (3501, 5000, False, False)]:
+            csr = csr_slice(data, lo, hi)
+            ro = o.insert_batch(*csr, keys=keys[lo:hi] if use_keys else None)
+            args = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in csr] if on_dev else list(csr)
+            k = None if not use_keys else (torch.from_numpy(keys[lo:hi].copy()).cuda() if on_dev else keys[lo:hi])
+            rg = g.insert_batch(*args, ext_keys=k)
+            assert rg.id_base == ro.id_base == lo
+            assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+            if not pruning:
+                assert (rg.postings_visited, rg.candidates_unique) == (ro.postings_visited, ro.candidates_unique)
+            assert list(g.fetch_status(hi - lo)) == list(ro.status)
+        o.freeze(); g.freeze()
+        csr = csr_slice(data, 5000, 6000)
+        ro = o.insert_batch(*csr); rg = g.insert_batch(*csr)
+        assert_pairs_equal(gpu_pairs(g, rg), ro.pair_set())
+        st = g.stats()
+        assert st["n_vectors"] == 5000 and st["tot_pairs"] == o.totals()["pairs"] > 0
+        with pytest.raises(n.ApssError):                       # a malformed batch is refused by every shard, nothing changes
+            g.insert_batch(np.array([0, 2], np.int64), np.array([5, 5], np.int32), np.array([.5, .5]))
+        assert g.stats()["n_vectors"] == 5000
+        g.close()
