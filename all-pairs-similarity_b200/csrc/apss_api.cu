@@ -24,6 +24,16 @@ using namespace apss;
 
 namespace {
 
+// APSS_ALLOC_TRACE=1: every growth of a device buffer with its size and host time (growth stalls the caller)
+struct AllocTrace {
+  const char* what; size_t bytes; std::chrono::steady_clock::time_point t0; bool on;
+  AllocTrace(const char* w, size_t b) : what(w), bytes(b), t0(std::chrono::steady_clock::now()), on(getenv("APSS_ALLOC_TRACE") != nullptr) {}
+  ~AllocTrace() {
+    if (on) std::fprintf(stderr, "apss alloc: %s to %.1f MB took %.2f ms\n", what, bytes / 1e6,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -31,6 +41,7 @@ struct DevBuf {
   // grow to >= n elements, preserving the first `keep` elements
   cudaError_t reserve(size_t n, size_t keep, cudaStream_t s) {
     if (n <= cap) return cudaSuccess;
+    AllocTrace tr_("cudaMalloc", n * sizeof(T));
     size_t ncap = std::max(n, cap + cap / 2);
     ncap = (ncap + 255) & ~size_t(255);
     T* np = nullptr;
@@ -91,6 +102,7 @@ struct VmBuf {
 
   cudaError_t reserve(size_t n, size_t keep, cudaStream_t s) {
     if (n <= cap) return cudaSuccess;
+    AllocTrace tr_("vmm-map", n * sizeof(T));
     VmApi& api = vm_api();
     if (!api.ok || (p && !vmm)) {
       cudaError_t e = fallback.reserve(n, keep, s);
@@ -201,6 +213,7 @@ struct apss_handle {
   DevBuf<unsigned> sg_keys_in, sg_keys_out; DevBuf<unsigned long long> sg_vals_in;
   DevBuf<unsigned long long> qm_cnt, qm_off; DevBuf<QmItem> qm_items;
   int64_t merges = 0, merged_postings = 0;
+  int64_t merge_ratio = 8;   // an older segment more than this many times the newer ones together is left alone (APSS_QM_MERGE_RATIO)
   int qm_cap = QM_CAP, qm_nt = 1024; size_t qm_items_cap0 = 0; bool qm_pipe = true; DevBuf<int32_t> qm_deferred, hot_q, hot_c; DevBuf<float> hot_est;     // test hooks: APSS_QM_CAP, APSS_QM_ITEMS_CAP
   bool broken = false;       // a failure after the index was touched that could not be rolled back: every later call fails
   // query-block transposition (v2 kernel)
@@ -450,6 +463,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
       if (h->dir_pool.reserve((size_t)(QM_MAXSEG + 2) * ((size_t)cfg->dim + 1), 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
       for (int k = QM_MAXSEG + 1; k >= 0; --k) h->dir_free.push_back(k);
       { const char* e = getenv("APSS_QM_CAP"); if (e && atoi(e) >= 8 && atoi(e) <= QM_CAP) h->qm_cap = atoi(e); }
+      { const char* e = getenv("APSS_QM_MERGE_RATIO"); if (e && atoi(e) >= 1 && atoi(e) <= 1024) h->merge_ratio = atoi(e); }
       { const char* e = getenv("APSS_QM_NT"); if (e && atoi(e) == 512) h->qm_nt = 512; }
       { const char* e = getenv("APSS_QM_PIPE"); if (e && atoi(e) == 0) h->qm_pipe = false; }      // measurement / tests: ranged kernel only
       { const char* e = getenv("APSS_QM_ITEMS_CAP"); if (e && atoll(e) >= 1) h->qm_items_cap0 = (size_t)atoll(e); }
@@ -634,13 +648,16 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
   int dimbits = 1; while ((1LL << dimbits) < (int64_t)D + 1) ++dimbits;
   int tilebits = 1; while ((1LL << tilebits) < ntiles_aff + 1) ++tilebits;   // + the "not indexed" sentinel tile
   if (m > 0) {
-    CK(h->s_keys_in.reserve(m, 0, s)); CK(h->s_keys_out.reserve(m, 0, s)); CK(h->s_vals_in.reserve(m, 0, s));
+    // scratch sized for the most an append can touch (open tile + batch, longest vector seen): growing it later costs a
+    // cudaMalloc + cudaFree (tens of ms each with the shard's large VMM reservations mapped) in the middle of a live stream
+    const int64_t m_cap = std::max<int64_t>(m, (int64_t)(CR + n) * (int64_t)(h->max_nnz_seen + 8));
+    CK(h->s_keys_in.reserve(m_cap, 0, s)); CK(h->s_keys_out.reserve(m_cap, 0, s)); CK(h->s_vals_in.reserve(m_cap, 0, s));
     k_emit_postings<<<cdiv(m, 256), 256, 0, s>>>(nnz_lo, nnz_new, row_lo, n_new, h->fwd_ptr.p, h->fwd_idx.p, h->fwd_val.p,
                                                   h->prune ? h->fwd_skip.p : nullptr, ntiles_aff, CR, tile0, dimbits, h->s_keys_in.p, h->s_vals_in.p);
     CK(cudaGetLastError()); h->kernel_launches++;
     size_t tmp = 0;
     unsigned long long* vals_out = reinterpret_cast<unsigned long long*>(h->post.p + post_base);
-    if (h->algo == 3) { CK(h->s_vals_out.reserve(m, 0, s)); vals_out = h->s_vals_out.p; }
+    if (h->algo == 3) { CK(h->s_vals_out.reserve(m_cap, 0, s)); vals_out = h->s_vals_out.p; }
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->s_keys_in.p, h->s_keys_out.p, h->s_vals_in.p, vals_out, m, 0, dimbits + tilebits, s));
     CK(h->cub_tmp.reserve(tmp, 0, s));
     CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, h->s_keys_in.p, h->s_keys_out.p, h->s_vals_in.p, vals_out, m, 0, dimbits + tilebits, s));
@@ -783,7 +800,7 @@ static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, i
   SegList sl{}; sl.n = (int32_t)h->segs.size();
   for (int k = 0; k < sl.n; ++k) { sl.post[k] = h->seg_post(h->segs[k]); sl.dir[k] = h->seg_dir(h->segs[k]); }
   CK(h->qm_cnt.reserve((size_t)batch_nnz + 1, 0, s)); CK(h->qm_off.reserve((size_t)batch_nnz + 1, 0, s));
-  if (!h->qm_items.cap) CK(h->qm_items.reserve(h->qm_items_cap0 ? h->qm_items_cap0 : std::max<size_t>((size_t)batch_nnz * 2, (size_t)1 << 16), 0, s));
+  if (!h->qm_items.cap) CK(h->qm_items.reserve(h->qm_items_cap0 ? h->qm_items_cap0 : std::max<size_t>((size_t)batch_nnz * 4, (size_t)1 << 16), 0, s));
   k_qm_count<<<cdiv((int64_t)batch_nnz + 1, 256), 256, 0, s>>>(batch_nnz, h->q_dim.p, sl, h->qm_cnt.p);
   CK(cudaGetLastError());
   size_t tb = 0;
@@ -852,8 +869,9 @@ static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, i
 }
 
 // LSM policy: after a committed append, the youngest segments are merged while the next older one is at most
-// twice their sum (every posting is copied ~3 times over the life of the index; a query term meets
-// O(log #batches) lists).  Stream-ordered: the caller does not wait for it.
+// merge_ratio (8) times their sum: the sizes of neighbouring segments differ by more than 8x, so a query term meets
+// log_8(#batches) lists (3 at a million vectors); every posting is copied about (8/7) log_8(#batches) times by merges
+// that are streaming copies.  Stream-ordered: the caller does not wait for it.
 static int32_t merge_segments(apss_handle* h) {
   cudaStream_t s = h->stream;
   const int D = h->cfg.dim;
@@ -863,7 +881,7 @@ static int32_t merge_segments(apss_handle* h) {
   while (j < size) {
     const int64_t prev = h->segs[size - 1 - j].n_post;
     if (sum + prev > 0x7fff0000LL) break;                                  // directories are int32 per segment
-    if (prev > 2 * sum && size - j <= QM_MAXSEG - 8) break;
+    if (prev > h->merge_ratio * sum && size - j <= QM_MAXSEG - 8) break;
     sum += prev; ++j;
   }
   if (j < 2 || h->dir_free.empty()) return APSS_OK;
@@ -1146,7 +1164,7 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
     if (hot_short) { const size_t need = (size_t)h->h_counters[C_HOTN] * 2; CK(h->hot_q.reserve(need, 0, s)); CK(h->hot_c.reserve(need, 0, s)); CK(h->hot_est.reserve(need, 0, s)); }
     if (h->h_counters[C_PF] <= h->pf_q.cap && !items_short && !hot_short) break;
     if (attempt == 3) return h->fail(APSS_E_NOMEM, "pair / piece buffer overflow persisted");
-    if (items_short) CK(h->qm_items.reserve(items_need + items_need / 4 + 1024, 0, s));     // grow and replay
+    if (items_short) CK(h->qm_items.reserve(items_need + items_need / 2 + 1024, 0, s));     // grow and replay
     if (h->h_counters[C_PF] > h->pf_q.cap) {
       const size_t need = (size_t)h->h_counters[C_PF] + 1024;
       CK(h->pf_q.reserve(need, 0, s)); CK(h->pf_c.reserve(need, 0, s)); CK(h->pf_est.reserve(need, 0, s));

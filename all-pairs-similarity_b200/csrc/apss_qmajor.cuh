@@ -573,7 +573,9 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
       thr_fix = em > 0.f ? (unsigned)fminf(floorf(em * a.scale * 0.99999f), 4294967040.f) : 0u;
       scan_all = DUPKEYS || thr_fix == 0u;
     }
-    {
+    if (cw >= hh.np) {                                          // a short stage: nothing for this warp, just release it
+      if (lane == 0) mbar_arrive(smem_u32(bars + QP_STAGES + stage));
+    } else {
       uint4 v[2]; int jj[2], ln[2]; float ws[2];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
