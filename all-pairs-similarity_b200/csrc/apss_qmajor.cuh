@@ -573,7 +573,8 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
       thr_fix = em > 0.f ? (unsigned)fminf(floorf(em * a.scale * 0.99999f), 4294967040.f) : 0u;
       scan_all = DUPKEYS || thr_fix == 0u;
     }
-    if (cw >= hh.np) {                                          // a short stage: nothing for this warp, just release it
+    if (cw >= hh.np) {                                          // a short stage: nothing for this warp, just release it --
+      __syncwarp();                                             // once EVERY lane has read the header (the producer rewrites it)
       if (lane == 0) mbar_arrive(smem_u32(bars + QP_STAGES + stage));
     } else {
       uint4 v[2]; int jj[2], ln[2]; float ws[2];
@@ -691,6 +692,312 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
   if (lane == 0 && nc) atomicAdd(&a.counters[C_CANDS], nc);
 }
 
+
+// ------------------------------------------------------------------ the flat-stage variant (default)
+
+// k_score_qm_pipe gives every piece a fixed 512-byte slot and every consumer warp two slots per stage; with the short
+// lists of the young posting segments the slots are ~40 % full and the consumer loop -- which is instruction-issue bound
+// -- spends most of its slots on nothing.  Here the producer PACKS the pieces of a stage back to back (16-byte units, a
+// running offset from a warp prefix sum) and publishes a piece table (start unit, length, parity, weight) plus, per
+// 512-byte window, the first piece that reaches into it.  A consumer warp takes whole windows: lane = one 16-byte unit =
+// two postings, finds its piece with a short forward walk from the window's first piece, and every lane has work.
+static constexpr int QF_PPL = 3;                  // pieces per producer lane and stage
+static constexpr int QF_NP = 32 * QF_PPL;         // pieces per stage, at most
+static constexpr int QF_UNITS = 2 * QP_NCW * 32;  // 16-byte units per stage (two windows per consumer warp) = 31 744 B
+static constexpr int QF_STAGE_BYTES = QF_UNITS * 16;
+struct QfHdr { int q, np, flags, total; float qn; int units; long long qkey; };      // 32 B per stage
+static constexpr size_t QF_META = (size_t)(QF_NP + 1) * 8 + 64 + sizeof(QfHdr);     // piece table + window table + header
+static constexpr size_t QF_SMEM = (size_t)2 * QP_TBL * 4 + (size_t)QM_HOT * 4 + (size_t)QP_STAGES * QF_STAGE_BYTES +
+                                  (size_t)QP_STAGES * QF_META + (size_t)QP_STAGES * 16;
+
+template <bool DUPKEYS>
+__global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
+  extern __shared__ __align__(128) unsigned char qp_smem[];
+  unsigned* keys = reinterpret_cast<unsigned*>(qp_smem);
+  unsigned* vals = keys + QP_TBL;
+  int* hot = reinterpret_cast<int*>(vals + QP_TBL);
+  unsigned char* ring = reinterpret_cast<unsigned char*>(hot + QM_HOT);                  // QP_STAGES x QF_STAGE_BYTES, 128-byte aligned
+  unsigned char* metab = ring + (size_t)QP_STAGES * QF_STAGE_BYTES;                      // per stage: tab[QF_NP + 1] | first[64] | header
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(metab + (size_t)QP_STAGES * QF_META);
+  auto tab_of = [&](int st) { return reinterpret_cast<uint2*>(metab + (size_t)st * QF_META); };
+  auto first_of = [&](int st) { return metab + (size_t)st * QF_META + (size_t)(QF_NP + 1) * 8; };
+  auto hdr_of = [&](int st) { return reinterpret_cast<QfHdr*>(metab + (size_t)st * QF_META + (size_t)(QF_NP + 1) * 8 + 64); };
+  __shared__ unsigned s_hot_n, s_out_n, s_chunk_pos, s_chunk_end, s_chunk_next;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid * 4; i < 2 * QP_TBL; i += 1024 * 4) *reinterpret_cast<uint4*>(keys + i) = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    s_hot_n = 0u;
+    for (int s = 0; s < QP_STAGES; ++s) { mbar_init(smem_u32(bars + s), 1u); mbar_init(smem_u32(bars + QP_STAGES + s), (unsigned)QP_NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ------------------------------------------------ producer
+    int stage = 0; unsigned phase = 0; unsigned long long n_post = 0;
+    auto load_desc = [&](const long long base, const long long end, uint4 (&d)[QF_PPL]) {      // lane l: pieces 3l, 3l + 1, 3l + 2
+#pragma unroll
+      for (int r = 0; r < QF_PPL; ++r) {
+        const long long k = base + lane * QF_PPL + r;
+        d[r] = make_uint4(0, 0, 0, 0);
+        if (k < end) d[r] = __ldg(reinterpret_cast<const uint4*>(a.items + k));
+      }
+    };
+    for (;;) {
+      int qbase = 0;
+      if (lane == 0) qbase = (int)atomicAdd(&a.counters[C_WORK], (unsigned long long)QP_QG);
+      qbase = __shfl_sync(FULL, qbase, 0);
+      if (qbase >= a.nq) break;
+      // ---- one query per lane: the whole set-up chain in parallel
+      const int myq = qbase + lane;
+      long long my_i0 = 0, my_i1 = 0, my_total = 0, my_qkey = 0; float my_qn = 0.f; bool my_ok = false;
+      if (lane < QP_QG && myq < a.nq) {
+        const int t0 = __ldg(a.q_ptr + myq), t1 = __ldg(a.q_ptr + myq + 1);
+        if (t0 != t1) {
+          const unsigned long long o0 = __ldg(a.item_off + t0), o1 = __ldg(a.item_off + t1);
+          my_i0 = (long long)(o0 >> 36); my_i1 = min((long long)(o1 >> 36), a.item_cap);
+          my_total = (long long)((o1 & 0xfffffffffULL) - (o0 & 0xfffffffffULL));
+          my_ok = my_i0 < my_i1;
+          if (my_ok && my_total > a.cap) {                     // too long for one table pass: the ranged kernel takes it
+            const unsigned long long k = atomicAdd(&a.counters[C_HEAVY], 1ULL);
+            if (k < (unsigned long long)a.deferred_cap) a.deferred[k] = myq;
+            my_ok = false;
+          }
+          if (my_ok) {
+            n_post += (unsigned long long)my_total;
+            my_qn = __ldg(a.q_nrm + myq);
+            if (DUPKEYS) my_qkey = __ldg(a.q_key + myq);
+          }
+        }
+      }
+      unsigned okmask = __ballot_sync(FULL, my_ok);
+      if (!okmask) continue;
+      int g = __ffs(okmask) - 1;
+      long long base = __shfl_sync(FULL, my_i0, g), gi1 = __shfl_sync(FULL, my_i1, g);
+      uint4 d[QF_PPL];
+      load_desc(base, gi1, d);
+      while (g >= 0) {
+        // ---- pack: units per piece, running offsets, how many pieces fit the stage
+        unsigned un[QF_PPL], st[QF_PPL], lsum = 0;
+#pragma unroll
+        for (int r = 0; r < QF_PPL; ++r) {
+          un[r] = (base + lane * QF_PPL + r < gi1) ? ((((d[r].x >> 3) & 1u) + d[r].z + 1u) >> 1) : 0u;
+          lsum += un[r];
+        }
+        unsigned incl = lsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+        st[0] = incl - lsum;
+#pragma unroll
+        for (int r = 1; r < QF_PPL; ++r) st[r] = st[r - 1] + un[r - 1];
+        int fit = 0; unsigned endu = 0;
+#pragma unroll
+        for (int r = 0; r < QF_PPL; ++r) if (un[r] && st[r] + un[r] <= (unsigned)QF_UNITS) { ++fit; endu = st[r] + un[r]; }
+        int np = fit;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { np += __shfl_xor_sync(FULL, np, o); endu = max(endu, __shfl_xor_sync(FULL, endu, o)); }
+        const bool first = base == __shfl_sync(FULL, my_i0, g), last = base + np >= gi1;
+        // what comes next: the query's next stage, or the first stage of the group's next query
+        int ng = g; long long nbase = base + np, ngi1 = gi1;
+        if (last) {
+          okmask &= ~(1u << g);
+          ng = okmask ? __ffs(okmask) - 1 : -1;
+          const int src = ng >= 0 ? ng : 0;
+          nbase = __shfl_sync(FULL, my_i0, src); ngi1 = __shfl_sync(FULL, my_i1, src);
+        }
+        uint4 dn[QF_PPL];
+#pragma unroll
+        for (int r = 0; r < QF_PPL; ++r) dn[r] = make_uint4(0, 0, 0, 0);
+        if (ng >= 0) load_desc(nbase, ngi1, dn);
+        const int qv = qbase + g; const long long tv = __shfl_sync(FULL, my_total, g);
+        const float qnv = __shfl_sync(FULL, my_qn, g); const long long qkv = __shfl_sync(FULL, my_qkey, g);
+        // ---- fill the stage
+        mbar_wait(smem_u32(bars + QP_STAGES + stage), phase ^ 1u);          // the consumers have released this stage
+        uint2* tab = tab_of(stage); unsigned char* fw = first_of(stage);
+#pragma unroll
+        for (int r = 0; r < QF_PPL; ++r) {
+          const int k = lane * QF_PPL + r;
+          if (un[r] && st[r] + un[r] <= (unsigned)QF_UNITS) {
+            tab[k] = make_uint2(st[r] | (d[r].z << 16) | (((d[r].x >> 3) & 1u) << 24), d[r].w);
+            for (unsigned w = (st[r] + 31u) >> 5; (w << 5) < st[r] + un[r]; ++w) fw[w] = (unsigned char)k;      // windows that start inside this piece
+          }
+        }
+        if (lane == 0) {
+          tab[np] = make_uint2(0xffffu, 0u);                 // sentinel: starts beyond every unit
+          QfHdr hh; hh.q = qv; hh.np = np; hh.total = (int)tv; hh.qn = qnv; hh.units = (int)endu; hh.qkey = qkv;
+          hh.flags = (first ? QP_F_FIRST : 0) | (last ? QP_F_LAST : 0);
+          *hdr_of(stage) = hh;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(smem_u32(bars + stage), a.dry == 2 ? 0u : endu * 16u);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < QF_PPL; ++r)
+          if (un[r] && st[r] + un[r] <= (unsigned)QF_UNITS && a.dry != 2) {
+            const unsigned long long pp = ((unsigned long long)d[r].y << 32) | d[r].x;
+            bulk_g2s(smem_u32(ring + (size_t)stage * QF_STAGE_BYTES + (size_t)st[r] * 16), reinterpret_cast<const void*>(pp & ~15ULL), un[r] * 16u, smem_u32(bars + stage));
+          }
+        if (++stage == QP_STAGES) { stage = 0; phase ^= 1u; }
+        g = ng; base = nbase; gi1 = ngi1;
+#pragma unroll
+        for (int r = 0; r < QF_PPL; ++r) d[r] = dn[r];
+      }
+    }
+    // no more queries: one empty END stage
+    mbar_wait(smem_u32(bars + QP_STAGES + stage), phase ^ 1u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_post += __shfl_down_sync(FULL, n_post, o);
+    if (lane == 0) {
+      QfHdr hh; hh.q = a.nq; hh.np = 0; hh.total = 0; hh.qn = 0.f; hh.units = 0; hh.qkey = 0; hh.flags = QP_F_END;
+      *hdr_of(stage) = hh;
+      mbar_arrive(smem_u32(bars + stage));
+      if (n_post) atomicAdd(&a.counters[C_POSTINGS], n_post);
+    }
+    return;
+  }
+
+  // -------------------------------------------------- consumers
+  const int cw = warp - 1, ctid = tid - 32;
+  constexpr int CT = QP_NCW * 32;
+  const unsigned keys_s = smem_u32(keys), vals_s = smem_u32(vals);
+  if (ctid == 0) {               // two chunks of the hot-candidate buffer up front; a new one is reserved whenever one is taken
+    s_chunk_pos = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
+    s_chunk_end = s_chunk_pos + QP_CHUNK;
+    s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
+    s_out_n = 0u;
+  }
+  int stage = 0; unsigned phase = 0; unsigned n_cand = 0;
+  unsigned size = 256u, thr_fix = 0u, self = 0xffffffffu; bool scan_all = true; float qn = 0.f; long long qkey = 0; int q = 0;
+  for (;;) {
+    mbar_wait(smem_u32(bars + stage), phase);
+    const QfHdr hh = *hdr_of(stage);
+    if (hh.flags & QP_F_END) break;
+    if (hh.flags & QP_F_FIRST) {
+      q = hh.q; qn = hh.qn; qkey = hh.qkey;
+      size = (unsigned)min((long long)QP_TBL, max(256LL, (3LL * hh.total + 31) & ~31LL));
+      self = a.q_local_base >= 0 ? (unsigned)(a.q_local_base + q) : 0xffffffffu;
+      const float em = (a.thr - a.cu_max * qn * 1.000001f) / a.band1;
+      thr_fix = em > 0.f ? (unsigned)fminf(floorf(em * a.scale * 0.99999f), 4294967040.f) : 0u;
+      scan_all = DUPKEYS || thr_fix == 0u;
+    }
+    if (cw * 32 >= hh.units) {                                  // a short stage: no window for this warp, just release it --
+      __syncwarp();                                             // once EVERY lane has read the header (the producer rewrites it)
+      if (lane == 0) mbar_arrive(smem_u32(bars + QP_STAGES + stage));
+    } else {
+      const uint2* tab = tab_of(stage); const unsigned char* fw = first_of(stage);
+      uint4 v[2]; int jj[2], ln[2]; float ws[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const unsigned u = (unsigned)(cw + QP_NCW * r) * 32u + (unsigned)lane;       // my 16-byte unit of the stage
+        v[r] = make_uint4(0, 0, 0, 0); jj[r] = 0; ln[r] = 0; ws[r] = 0.f;
+        if (u < (unsigned)hh.units) {
+          int p = fw[cw + QP_NCW * r];
+          uint2 cur = tab[p], nxt = tab[p + 1];
+          while ((nxt.x & 0xffffu) <= u) { cur = nxt; ++p; nxt = tab[p + 1]; }       // forward walk: few pieces reach into one window
+          ln[r] = (int)((cur.x >> 16) & 0xffu); ws[r] = __uint_as_float(cur.y);
+          jj[r] = 2 * (int)(u - (cur.x & 0xffffu)) - (int)(cur.x >> 24);
+          v[r] = *reinterpret_cast<const uint4*>(ring + (size_t)stage * QF_STAGE_BYTES + (size_t)u * 16);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bars + QP_STAGES + stage));      // the postings are in registers: release the stage
+      unsigned cc[4], slot[4], contrib[4], old[4]; bool on[4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int e = 2 * r + u;
+          cc[e] = u ? v[r].z : v[r].x;
+          const float w = __uint_as_float(u ? v[r].w : v[r].y);
+          on[e] = jj[r] + u >= 0 && jj[r] + u < ln[r] && cc[e] != self && !a.dry;
+          contrib[e] = __float2uint_ru(__fmul_ru(w, ws[r]));
+          slot[e] = __umulhi(cc[e] * 0x9E3779B1u, size);
+        }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) old[e] = atoms_cas_if(keys_s + slot[e] * 4u, cc[e] + 1u, on[e]);
+      bool coll = false;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) coll |= on[e] && old[e] != 0u && old[e] != cc[e] + 1u;
+      if (coll) {                                              // a slot held by another candidate: linear probing (one branch for all four)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const unsigned k1 = cc[e] + 1u;
+          if (on[e] && old[e] != 0u && old[e] != k1) {
+            unsigned sl_ = slot[e];
+            for (;;) {
+              if (++sl_ == size) sl_ = 0;
+              const unsigned o = atomicCAS(keys + sl_, 0u, k1);
+              if (o == 0u || o == k1) { old[e] = o; break; }
+            }
+            slot[e] = sl_;
+          }
+        }
+      }
+      unsigned prev[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (!DUPKEYS) n_cand += (unsigned)(on[e] && old[e] == 0u);      // (caller keys: counted in the scan; same-key candidates do not count)
+        prev[e] = atoms_add_if(vals_s + slot[e] * 4u, contrib[e], on[e]);
+      }
+      bool anyhot = false;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) anyhot |= on[e] && prev[e] < thr_fix && prev[e] + contrib[e] >= thr_fix;
+      if (anyhot && !scan_all) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (on[e] && prev[e] < thr_fix && prev[e] + contrib[e] >= thr_fix) {
+            const unsigned h = atomicAdd(&s_hot_n, 1u);
+            if (h < (unsigned)QM_HOT) hot[h] = (int)slot[e];
+          }
+      }
+    }
+    if (hh.flags & QP_F_LAST) {
+      // ---- consumer-only epilogue (see k_score_qm_pipe): no global round trip
+      consumer_bar();
+      const unsigned nh = s_hot_n;
+      const bool full = scan_all || nh > (unsigned)QM_HOT;
+      if (full) {
+        if (ctid == 0 && s_chunk_pos + size > s_chunk_end) {
+          s_chunk_pos = s_chunk_next; s_chunk_end = s_chunk_next + QP_CHUNK;
+          s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
+        }
+        consumer_bar();
+      }
+      const unsigned cpos = s_chunk_pos;
+      auto put = [&](const unsigned at, const unsigned k, const unsigned vv) {
+        const unsigned o = cpos + at;
+        if (o < a.hot_cap) { a.hot_q[o] = q; a.hot_c[o] = (int32_t)(k - 1u); a.hot_est[o] = __uint2float_ru(vv) * a.inv_scale; }
+      };
+      if (full) {
+        for (unsigned i = ctid; i < size; i += CT) {
+          const unsigned k = keys[i];
+          if (!k) continue;
+          if (DUPKEYS) { if (__ldg(a.c_key + (k - 1u)) == qkey) continue; ++n_cand; }
+          put(atomicAdd(&s_out_n, 1u), k, vals[i]);
+        }
+      } else {
+        for (unsigned e = ctid; e < nh; e += CT) { const int sl_ = hot[e]; put(e, keys[sl_], vals[sl_]); }
+      }
+      consumer_bar();
+      for (unsigned i = ctid * 4; i < size; i += CT * 4) {
+        *reinterpret_cast<uint4*>(keys + i) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(vals + i) = make_uint4(0, 0, 0, 0);
+      }
+      if (ctid == 0) {
+        s_chunk_pos += full ? s_out_n : nh; s_out_n = 0u; s_hot_n = 0u;
+        if (s_chunk_pos + (unsigned)QM_HOT > s_chunk_end) {    // the next query's hot list always fits
+          s_chunk_pos = s_chunk_next; s_chunk_end = s_chunk_next + QP_CHUNK;
+          s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
+        }
+      }
+      consumer_bar();
+    }
+    if (++stage == QP_STAGES) { stage = 0; phase ^= 1u; }
+  }
+  unsigned long long nc = n_cand;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nc += __shfl_down_sync(FULL, nc, o);
+  if (lane == 0 && nc) atomicAdd(&a.counters[C_CANDS], nc);
+}
 
 // The exact candidate test of the pipelined kernel, moved out of its epilogue: one thread per entry of the hot-candidate
 // buffer (q = -1: never written),  estimate * (1 + guard band) + |q| * |c_unindexed| >= t,  survivors compacted into

@@ -389,6 +389,9 @@ def run_allpairs(cx, mode):
 
 def main():
     args = parse_args()
+    if os.environ.get("APSS_BENCH_WATCHDOG"):        # debugging aid: dump every thread's stack and exit after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["APSS_BENCH_WATCHDOG"]), exit=True)
     from apss_b200 import synth
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
