@@ -197,7 +197,7 @@ struct apss_handle {
   DevBuf<int32_t> qdir; VmBuf<int32_t> heavy;
   VmBuf<int64_t> ifw_ptr; VmBuf<uint2> ifw; DevBuf<int32_t> q_icnt, q_iptr;   // compact store of the indexed components
   DevBuf<int32_t> df; VmBuf<uint8_t> fwd_skip; VmBuf<float> row_ub;
-  DevBuf<uint8_t> q_skip; DevBuf<float> q_cu, q_nrm;
+  DevBuf<uint8_t> q_skip; DevBuf<float> q_cu, q_nrm, q_bkt; DevBuf<int32_t> q_dfmin; VmBuf<int32_t> row_dfmin;
   DevBuf<unsigned long long> pr_keys_in, pr_keys_out, pr_vals_in, pr_vals_out;
   int64_t tot_skipped = 0;
   // query-major scoring on the reduced index (prune_mode 3): LSM posting segments, oldest first
@@ -386,6 +386,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
   apss_handle* h = new apss_handle();
   h->cfg = *cfg; h->cfg.max_weight = nullptr; h->device = cfg->n_devices == 1 ? cfg->device_ids[0] : cfg->device;
   h->cfg.device = h->device;
+  h->row_dfmin.device = cfg->n_devices == 1 ? cfg->device_ids[0] : cfg->device;
   h->fwd_skip.device = h->row_ub.device = h->heavy.device = h->ifw_ptr.device = h->ifw.device = cfg->device;
   h->fwd_ptr.device = h->fwd_idx.device = h->fwd_val.device = h->gid.device = h->key.device = h->post.device = h->dir.device =
       h->tile_base.device = h->dn_cnt.device = h->dn_dim.device = h->dn_len.device = h->tile_cnt.device = h->dn_hash.device =
@@ -500,6 +501,7 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
                                h->seg_arena[1].reserve((size_t)cfg->reserve_nnz / 2, 0, h->stream) != cudaSuccess)) return bail(APSS_E_NOMEM);
   }
   if (cfg->reserve_vectors > 0 && h->prune && h->row_ub.reserve(cfg->reserve_vectors, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
+  if (cfg->reserve_vectors > 0 && h->prune_mode == 3 && h->row_dfmin.reserve(cfg->reserve_vectors, 0, h->stream) != cudaSuccess) return bail(APSS_E_NOMEM);
   {
     size_t np = cfg->reserve_pairs > 0 ? (size_t)cfg->reserve_pairs : (size_t)1 << 20;
     if (h->pf_q.reserve(np, 0, h->stream) != cudaSuccess || h->pf_c.reserve(np, 0, h->stream) != cudaSuccess || h->pf_est.reserve(np, 0, h->stream) != cudaSuccess ||
@@ -527,6 +529,7 @@ extern "C" void apss_destroy(apss_handle* h) {
   h->pf_q.release(); h->pf_c.release(); h->pf_est.release(); h->out_q.release(); h->out_c.release(); h->out_sim.release();
   h->qdir.release(); h->heavy.release(); h->ifw_ptr.release(); h->ifw.release(); h->q_icnt.release(); h->q_iptr.release();
   h->df.release(); h->fwd_skip.release(); h->row_ub.release(); h->q_skip.release(); h->q_cu.release(); h->q_nrm.release();
+  h->q_bkt.release(); h->q_dfmin.release(); h->row_dfmin.release();
   h->pr_keys_in.release(); h->pr_keys_out.release(); h->pr_vals_in.release(); h->pr_vals_out.release();
   h->segs.clear(); h->seg_arena[0].release(); h->seg_arena[1].release(); h->dir_pool.release();
   h->sg_keys_in.release(); h->sg_keys_out.release(); h->sg_vals_in.release(); h->qm_cnt.release(); h->qm_off.release(); h->qm_items.release(); h->qm_deferred.release(); h->hot_q.release(); h->hot_c.release(); h->hot_est.release();
@@ -547,7 +550,7 @@ extern "C" void apss_destroy(apss_handle* h) {
 // (see k_prune_mark).  Fills q_skip[batch_nnz] and q_cu[n]; the document frequencies include this batch.
 static int32_t prune_select(apss_handle* h, int32_t n, int32_t batch_nnz) {
   cudaStream_t s = h->stream;
-  CK(h->q_skip.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_cu.reserve(n, 0, s));
+  CK(h->q_skip.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_cu.reserve(n, 0, s)); CK(h->q_dfmin.reserve(n, 0, s));
   CK(h->q_icnt.reserve(n + 1, 0, s)); CK(h->q_iptr.reserve(n + 1, 0, s));
   CK(h->pr_keys_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_keys_out.reserve(std::max(batch_nnz, 1), 0, s));
   CK(h->pr_vals_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_vals_out.reserve(std::max(batch_nnz, 1), 0, s));
@@ -563,7 +566,8 @@ static int32_t prune_select(apss_handle* h, int32_t n, int32_t batch_nnz) {
     CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->pr_keys_in.p, h->pr_keys_out.p, h->pr_vals_in.p, h->pr_vals_out.p, batch_nnz, 0, 31 + rowbits, s));
     h->kernel_launches += 4;
   }
-  k_prune_mark<<<cdiv(((int64_t)n + 1) * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_val.p, h->pr_vals_out.p, h->prune_lim, h->q_skip.p, h->q_cu.p, h->q_icnt.p, h->d_counters);
+  k_prune_mark<<<cdiv(((int64_t)n + 1) * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_val.p, h->pr_vals_out.p, h->pr_keys_out.p, h->prune_lim, h->q_skip.p, h->q_cu.p, h->q_icnt.p,
+                                                                h->q_dfmin.p, h->d_counters);
   CK(cudaGetLastError()); h->kernel_launches++;
   if (h->prune_mode == 2) {
     size_t tb = 0;
@@ -594,6 +598,10 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
     CK(h->fwd_skip.reserve(std::max<int64_t>(nnz_new, 1), nnz_old, s)); CK(h->row_ub.reserve(n_new, n_old, s));
     if (batch_nnz) CK(cudaMemcpyAsync(h->fwd_skip.p + nnz_old, h->q_skip.p, (size_t)batch_nnz, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(h->row_ub.p + n_old, h->q_cu.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    if (h->prune_mode == 3) {
+      CK(h->row_dfmin.reserve(n_new, n_old, s));
+      CK(cudaMemcpyAsync(h->row_dfmin.p + n_old, h->q_dfmin.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    }
   }
   if (h->prune_mode == 3) {     // query-major scoring: the batch becomes one new posting segment (merged after the call)
     if (batch_nnz) {
@@ -808,6 +816,9 @@ static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, i
   CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, h->qm_cnt.p, h->qm_off.p, batch_nnz + 1, s));
   CK(h->cub_tmp.reserve(tb, 0, s));
   CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tb, h->qm_cnt.p, h->qm_off.p, batch_nnz + 1, s));
+  CK(h->q_bkt.reserve((size_t)n * 32, 0, s));
+  k_qm_qnorms<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->q_w.p, h->df.p, h->q_bkt.p);
+  CK(cudaGetLastError());
   QmArgs a{};
   {   // u32 fixed point: every dot product is <= the largest squared norm (Cauchy-Schwarz)
     const int Fc = std::max(-100, std::min(100, (int)std::floor(std::log2(2147483648.0 / (std::max(h->max_sq, 1e-300) * (1.0 + 1e-6))))));
@@ -817,6 +828,7 @@ static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, i
   CK(cudaGetLastError());
   a.q_ptr = h->q_ptr.p; a.item_off = h->qm_off.p; a.items = h->qm_items.p; a.item_cap = (long long)h->qm_items.cap;
   a.q_nrm = h->q_nrm.p; a.q_key = h->custom_keys ? d_qkey : nullptr; a.row_ub = h->row_ub.p; a.c_key = h->key.p;
+  a.row_dfmin = h->row_dfmin.p; a.q_bkt = h->q_bkt.p;
   a.n_rows = h->n_local; a.q_local_base = q_local_base; a.nq = n;
   a.thr = (float)t; if ((double)a.thr > t) a.thr = std::nextafterf(a.thr, -INFINITY);
   a.band1 = (float)(1.0 + (double)(h->max_nnz_seen + 8) * std::ldexp(1.0, -22));

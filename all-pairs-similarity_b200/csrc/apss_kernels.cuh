@@ -170,9 +170,11 @@ __global__ void k_rank_keys(int n, const int32_t* __restrict__ q_ptr, const int3
 // one warp per vector: walk its components in rank order, fp64 running sum of squares (separate multiply and
 // add, like the oracle; 32 components loaded at a time, the sum chained through them in lane order), mark the
 // prefix, record |c_U| rounded up and the number of indexed components
+// dfmin[v]: the smallest document frequency among the components left out (the last one of the prefix, the ranking
+// being by descending frequency); INT_MAX when nothing was left out.  Used by the query-major kernels' candidate test.
 __global__ void k_prune_mark(int n, const int32_t* __restrict__ q_ptr, const double* __restrict__ q_val,
-                             const unsigned long long* __restrict__ ranked, double lim,
-                             uint8_t* __restrict__ skip, float* __restrict__ cu, int32_t* __restrict__ icnt,
+                             const unsigned long long* __restrict__ ranked, const unsigned long long* __restrict__ ranked_keys, double lim,
+                             uint8_t* __restrict__ skip, float* __restrict__ cu, int32_t* __restrict__ icnt, int32_t* __restrict__ dfmin,
                              unsigned long long* counters) {
   const int v = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
@@ -201,6 +203,7 @@ __global__ void k_prune_mark(int n, const int32_t* __restrict__ q_ptr, const dou
   if (k > a) atomicAdd(&counters[C_SKIPPED], (unsigned long long)(k - a));
   cu[v] = s > 0.0 ? __double2float_ru(sqrt(s) * (1.0 + 1e-9)) : 0.f;
   icnt[v] = b - k;
+  if (dfmin) dfmin[v] = k > a ? (int32_t)(0x7fffffffLL - (long long)(ranked_keys[k - 1] & 0x7fffffffULL)) : 0x7fffffff;
 }
 
 // compact forward store of the INDEXED components only, (dim, fp32 weight), for the candidate-major kernel:
