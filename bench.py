@@ -531,8 +531,18 @@ def main():
         pr = run_leg(cx, args.pruned_mode, profile=args.profile_range and args.profile_leg == "pruned")
     jobs = []
     if not args.no_allpairs and not shard_gen:
+        # the job's data set is G(N, ...) exactly -- independent of --steps / --warmup, so its pair total and hash are
+        # comparable across runs, modes and --gpus N (the IDF depends on how many rows are generated)
+        job_data = synth.generate(N, D, cfg["nnz_mean"], s=cfg["s"], seed=cfg["seed"], device=dev)
+
+        def job_rows(lo, hi):
+            b = job_data.rows(lo, hi)
+            return b.indptr.contiguous(), b.indices.contiguous(), b.values.contiguous()
+
+        cx.dev_rows, cx.total_nnz = job_rows, job_data.nnz
         for m in ([main_mode] if (args.no_pruned_leg or args.prune) else [0, args.pruned_mode]):
             jobs.append(run_allpairs(cx, m))
+        del job_data
     sampler.stop()
     if world > 1:        # every collective is done: rank 0 goes on alone with the CPU-side checks
         dist.barrier()
