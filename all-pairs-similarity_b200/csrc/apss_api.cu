@@ -214,7 +214,7 @@ struct apss_handle {
   DevBuf<unsigned long long> qm_cnt, qm_off; DevBuf<QmItem> qm_items;
   int64_t merges = 0, merged_postings = 0;
   int64_t merge_ratio = 8;   // an older segment more than this many times the newer ones together is left alone (APSS_QM_MERGE_RATIO)
-  int qm_cap = QM_CAP, qm_nt = 1024; size_t qm_items_cap0 = 0; bool qm_pipe = true, qm_flat = true; DevBuf<int32_t> qm_deferred, hot_q, hot_c; DevBuf<float> hot_est;     // test hooks: APSS_QM_CAP, APSS_QM_ITEMS_CAP
+  int qm_cap = QM_CAP, qm_nt = 1024; size_t qm_items_cap0 = 0; bool qm_pipe = true; DevBuf<int32_t> qm_deferred, hot_q, hot_c; DevBuf<float> hot_est;     // test hooks: APSS_QM_CAP, APSS_QM_ITEMS_CAP
   bool broken = false;       // a failure after the index was touched that could not be rolled back: every later call fails
   // query-block transposition (v2 kernel)
   DevBuf<unsigned long long> bt_keys_in, bt_keys_out, bt_vals_in, bt_vals_out, ud_key; DevBuf<int32_t> bt_flags, bt_pos, ud_dim, ud_start, bd_ptr;
@@ -466,7 +466,6 @@ extern "C" int32_t apss_create(const apss_config* cfg, apss_handle** out) {
       { const char* e = getenv("APSS_QM_CAP"); if (e && atoi(e) >= 8 && atoi(e) <= QM_CAP) h->qm_cap = atoi(e); }
       { const char* e = getenv("APSS_QM_MERGE_RATIO"); if (e && atoi(e) >= 1 && atoi(e) <= 1024) h->merge_ratio = atoi(e); }
       { const char* e = getenv("APSS_QM_NT"); if (e && atoi(e) == 512) h->qm_nt = 512; }
-      { const char* e = getenv("APSS_QM_FLAT"); if (e && atoi(e) == 0) h->qm_flat = false; }      // measurement: fixed-slot ring instead of the packed one
       { const char* e = getenv("APSS_QM_PIPE"); if (e && atoi(e) == 0) h->qm_pipe = false; }      // measurement / tests: ranged kernel only
       { const char* e = getenv("APSS_QM_ITEMS_CAP"); if (e && atoll(e) >= 1) h->qm_items_cap0 = (size_t)atoll(e); }
     }
@@ -607,7 +606,7 @@ static int32_t index_append(apss_handle* h, int32_t n, int32_t batch_nnz, const 
     if (batch_nnz) {
       if ((int)h->segs.size() >= QM_MAXSEG || h->dir_free.empty()) return h->fail(APSS_E_STATE, "too many posting segments");
       apss_handle::Seg sg; sg.row_lo = n_old; sg.row_hi = n_new;
-      sg.cap_post = (int64_t)batch_nnz + 64;      // the sort writes the un-indexed components behind the postings; + one window of read slack
+      sg.cap_post = (int64_t)batch_nnz + 64;      // the sort writes the un-indexed components behind the postings; + read slack
       if (!h->segs.empty()) { const apss_handle::Seg& b = h->segs.back(); sg.off = (b.off + b.n_post + 64 + 31) & ~(int64_t)31; }
       CK(h->seg_arena[0].reserve((size_t)(sg.off + sg.cap_post), 0, s));
       CK(h->sg_keys_in.reserve(batch_nnz, 0, s)); CK(h->sg_keys_out.reserve(batch_nnz, 0, s)); CK(h->sg_vals_in.reserve(batch_nnz, 0, s));
@@ -854,14 +853,10 @@ static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, i
     QmArgs ap = a; ap.cap = std::min(a.cap, QP_CAP);
     { const char* e = getenv("APSS_QM_DRY"); ap.dry = e ? atoi(e) : 0; }
     ap.hot_q = h->hot_q.p; ap.hot_c = h->hot_c.p; ap.hot_est = h->hot_est.p; ap.hot_cap = (unsigned)std::min<size_t>(h->hot_q.cap, 0xffff0000u);
-    if (h->qm_flat) {
+    {
       auto kern = h->custom_keys ? k_score_qm_flat<true> : k_score_qm_flat<false>;
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QF_SMEM));
       kern<<<h->sm_count, 1024, QF_SMEM, s>>>(ap);
-    } else {
-      auto kern = h->custom_keys ? k_score_qm_pipe<true> : k_score_qm_pipe<false>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QP_SMEM));
-      kern<<<h->sm_count, 1024, QP_SMEM, s>>>(ap);
     }
     CK(cudaGetLastError());
     k_qm_filter<<<h->sm_count * 8, 256, 0, s>>>(ap);

@@ -103,14 +103,16 @@ __global__ void k_merge_copy(int src, int n_post, int D, const MergeSrc m, const
 
 // ------------------------------------------------------------------ per batch: the pieces of every query
 
-// A piece is at most one 128-bit load per lane: it never crosses a 1 KB-aligned window of 64 postings counted from the
-// 16-byte pair its list starts in.  A list [a, b) that starts on the upper half of a pair (a odd; segment buffers are
-// 256-byte aligned) gets a first piece of <= 63 postings, every other piece starts on a pair boundary and has <= 64.
+// A piece is a run of <= QM_PMAX postings of one list that starts on a 16-byte pair boundary (except the first piece
+// of a list that starts on the upper half of a pair; segment buffers are 256-byte aligned): ONE bulk copy moves it.
+// The bulk-copy engine handles a small request in about as many cycles as a large one (measured: ~80 cycles per
+// request per SM), so pieces are as long as the stage allows, not one warp-load long.
+static constexpr int QM_PMAX = 1024;
 __device__ __forceinline__ int qm_pieces(int a, int b) {
   const int len = b - a;
   if (len <= 0) return 0;
-  const int first = min(len, 64 - (a & 1));
-  return 1 + (len - first + 63) / 64;
+  const int first = min(len, QM_PMAX - (a & 1));
+  return 1 + (len - first + QM_PMAX - 1) / QM_PMAX;
 }
 
 // thread per query term: (pieces << 36 | postings) of its lists over all segments; ONE 64-bit scan then yields both
@@ -140,7 +142,7 @@ __global__ void k_qm_emit(int nnz, const int32_t* __restrict__ q_dim, const floa
   for (int s = 0; s < sl.n; ++s) {
     const int a = __ldg(sl.dir[s] + d), b = __ldg(sl.dir[s] + d + 1);
     for (int p = a; p < b; ++o) {
-      const int len = min(b - p, 64 - (p & 1));
+      const int len = min(b - p, QM_PMAX - (p & 1));
       if (o < cap) { QmItem it; it.post = (unsigned long long)(sl.post[s] + p); it.len = len; it.wqs = wqs; items[o] = it; }
       p += len;
     }
@@ -170,7 +172,8 @@ struct QmArgs {
   int32_t* hot_q; int32_t* hot_c; float* hot_est; unsigned hot_cap;     // pipelined kernel: candidates that crossed the query's
                                  // coarse threshold, written in per-CTA chunks reserved on C_HOTN (q = -1: unused entry)
   int32_t from_list;             // k_score_qm: 0 = take every query from the cursor, 1 = take the deferred list
-  int32_t dry;                   // measurement only (APSS_QM_DRY): 1 = no table updates, 2 = no copies either
+  int32_t dry;                   // measurement only (APSS_QM_DRY, bits): 1 = no table updates, 2 = no copies, 4 = L2 prefetch of the
+                                 // next stage's pieces while the producer waits (measured: slower -- it doubles the bulk requests)
 };
 
 // ---- the candidate test.  dot(q, c) = dot(q, c_indexed) + dot(q, c_unindexed), and by Cauchy-Schwarz on the un-indexed
@@ -226,8 +229,6 @@ __device__ __forceinline__ long long qm_block_sum(long long v, long long* red, i
   return s;
 }
 
-static constexpr int QM_G = 4;            // pieces a warp keeps in flight (independent 128-bit loads per lane)
-
 template <int NT, int TBL, bool DUPKEYS>
 __global__ void __launch_bounds__(NT, 2048 / NT / 2 * 1) k_score_qm(const QmArgs a) {
   extern __shared__ __align__(16) unsigned qm_smem[];
@@ -275,69 +276,46 @@ __global__ void __launch_bounds__(NT, 2048 / NT / 2 * 1) k_score_qm(const QmArgs
     const int per = (int)((i1 - i0 + NW - 1) / NW);
     const long long w_lo = i0 + (long long)warp * per, w_hi = min(i1, w_lo + per);
 
-    // one pass: candidates with lo <= id < hi (ranged) or all of them; count_only: how many entries the range holds
+    // one pass: candidates with lo <= id < hi (ranged) or all of them; count_only: how many entries the range holds.
+    // A warp takes its pieces one after the other and streams each in 1 KB chunks (two postings per lane, 128-bit loads).
     auto walk = [&](const bool ranged, const bool count_only, const unsigned lo, const unsigned hi, const unsigned size) -> long long {
       long long cnt = 0;
-      for (long long base = w_lo; base < w_hi; base += 32) {
-        const int nd = (int)min(32LL, w_hi - base);
-        uint4 desc = make_uint4(0, 0, 0, 0);
-        if (lane < nd) desc = __ldg(reinterpret_cast<const uint4*>(a.items + base + lane));      // one descriptor per lane
-        for (int g = 0; g < nd; g += QM_G) {
-          uint4 v[QM_G]; int jj[QM_G]; int ln[QM_G]; float ws[QM_G];
+      for (long long i = w_lo; i < w_hi; ++i) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(a.items + i));          // same address on every lane
+        const unsigned long long pp = ((unsigned long long)raw.y << 32) | raw.x;
+        const int len = (int)raw.z; const float wqs = __uint_as_float(raw.w);
+        const int odd = (int)((pp >> 3) & 1ULL);                                       // the piece starts on the upper half of a 16-byte pair
+        const uint4* p4 = reinterpret_cast<const uint4*>(pp - 8ULL * odd);
+        for (int j0 = -odd; j0 < len; j0 += 64) {
+          const int j = j0 + 2 * lane;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (j + 1 >= 0 && j < len) v = ld_stream4(p4 + ((j + odd) >> 1));
+          unsigned cc[2], slot[2], contrib[2]; bool on[2];
 #pragma unroll
-          for (int k = 0; k < QM_G; ++k) {                     // QM_G independent loads in flight
-            const int src = min(g + k, 31);
-            const unsigned plo = __shfl_sync(FULL, desc.x, src), phi = __shfl_sync(FULL, desc.y, src);
-            ln[k] = (g + k < nd) ? (int)__shfl_sync(FULL, desc.z, src) : 0;
-            ws[k] = __uint_as_float(__shfl_sync(FULL, desc.w, src));
-            const unsigned long long pp = ((unsigned long long)phi << 32) | plo;
-            const int odd = (int)((pp >> 3) & 1ULL);           // the list starts on the upper half of a 16-byte pair
-            jj[k] = 2 * lane - odd;
-            v[k] = make_uint4(0, 0, 0, 0);
-            if (jj[k] + 1 >= 0 && jj[k] < ln[k]) v[k] = ld_stream4(reinterpret_cast<const uint4*>(pp - 8ULL * odd) + lane);
+          for (int u = 0; u < 2; ++u) {
+            cc[u] = u ? v.z : v.x;
+            const float w = __uint_as_float(u ? v.w : v.y);
+            on[u] = j + u >= 0 && j + u < len && cc[u] != self;
+            if (ranged) on[u] = on[u] && cc[u] >= lo && cc[u] < hi;
+            contrib[u] = __float2uint_ru(__fmul_ru(w, wqs));
+            slot[u] = __umulhi(cc[u] * 0x9E3779B1u, size);
           }
-          unsigned cc[2 * QM_G], slot[2 * QM_G], contrib[2 * QM_G], old[2 * QM_G]; bool on[2 * QM_G];
+          if (count_only) { cnt += (int)on[0] + (int)on[1]; continue; }
 #pragma unroll
-          for (int k = 0; k < QM_G; ++k)
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int e = 2 * k + u;
-              cc[e] = u ? v[k].z : v[k].x;
-              const float w = __uint_as_float(u ? v[k].w : v[k].y);
-              on[e] = jj[k] + u >= 0 && jj[k] + u < ln[k] && cc[e] != self;
-              if (ranged) on[e] = on[e] && cc[e] >= lo && cc[e] < hi;
-              contrib[e] = __float2uint_ru(__fmul_ru(w, ws[k]));
-              slot[e] = __umulhi(cc[e] * 0x9E3779B1u, size);
+          for (int u = 0; u < 2; ++u) {
+            if (!on[u]) continue;
+            const unsigned k1 = cc[u] + 1u;
+            unsigned sl_ = slot[u];
+            for (;;) {
+              const unsigned o = atomicCAS(keys + sl_, 0u, k1);
+              if (o == 0u) { ++n_cand; break; }
+              if (o == k1) break;
+              if (++sl_ == size) sl_ = 0;
             }
-          if (count_only) {
-#pragma unroll
-            for (int e = 0; e < 2 * QM_G; ++e) cnt += on[e];
-            continue;
-          }
-#pragma unroll
-          for (int e = 0; e < 2 * QM_G; ++e) { old[e] = 0u; if (on[e]) old[e] = atomicCAS(keys + slot[e], 0u, cc[e] + 1u); }
-#pragma unroll
-          for (int e = 0; e < 2 * QM_G; ++e) {
-            if (!on[e]) continue;
-            const unsigned k1 = cc[e] + 1u;
-            if (old[e] != 0u && old[e] != k1) {               // occupied by another candidate: linear probing
-              unsigned sl_ = slot[e];
-              for (;;) {
-                if (++sl_ == size) sl_ = 0;
-                const unsigned o = atomicCAS(keys + sl_, 0u, k1);
-                if (o == 0u || o == k1) { old[e] = o; break; }
-              }
-              slot[e] = sl_;
-            }
-            n_cand += old[e] == 0u;
-          }
-#pragma unroll
-          for (int e = 0; e < 2 * QM_G; ++e) {
-            if (!on[e]) continue;
-            const unsigned prev = atomicAdd(vals + slot[e], contrib[e]);
-            if (!scan_all && prev < thr_fix && prev + contrib[e] >= thr_fix) {
+            const unsigned prev = atomicAdd(vals + sl_, contrib[u]);
+            if (!scan_all && prev < thr_fix && prev + contrib[u] >= thr_fix) {
               const unsigned h = atomicAdd(&s_hot_n, 1u);
-              if (h < (unsigned)QM_HOT) hot[h] = (int)slot[e];
+              if (h < (unsigned)QM_HOT) hot[h] = (int)sl_;
             }
           }
         }
@@ -399,27 +377,15 @@ __global__ void __launch_bounds__(NT, 2048 / NT / 2 * 1) k_score_qm(const QmArgs
 // ------------------------------------------------------------------ the pipelined kernel (bulk-async producer / consumers)
 
 // k_score_qm above pays a chain of dependent global round trips per query (cursor -> q_ptr -> offsets -> piece
-// descriptors -> postings) with the whole CTA in lock step.  Here one PRODUCER warp runs ahead of the 31 CONSUMER
-// warps: it walks the queries, and for every stage of the ring it (a) loads up to QP_SP piece descriptors, (b) posts
-// the stage's byte count on the stage's mbarrier (arrive.expect_tx) and (c) issues one cp.async.bulk per piece -- the
-// 16-byte aligned window of <= 512 B holding the piece -- straight into the stage's shared-memory slots.  Consumers
-// wait on the full barrier, read their pieces with one LDS.128 per lane, accumulate into the hash table exactly as
-// k_score_qm does, and release the stage through the empty barrier.  A query's last stage triggers the consumer-only
-// epilogue (hot list, clear) behind a named barrier while the producer is already staging the next query.  Queries
-// whose lists exceed one table pass are appended to the deferred list for k_score_qm's ranged passes.
+// descriptors -> postings) with the whole CTA in lock step.  In k_score_qm_flat (below) one PRODUCER warp runs ahead of
+// 31 CONSUMER warps through a two-stage shared-memory ring guarded by mbarrier full / empty pairs; the postings arrive by
+// cp.async.bulk (TMA bulk copy), the consumers only ever touch shared memory.
 static constexpr int QP_NCW = 31;                 // consumer warps
-static constexpr int QP_SP = 2 * QP_NCW;          // pieces per stage (two per consumer warp)
 static constexpr int QP_STAGES = 2;
 static constexpr int QP_QG = 8;                   // queries whose set-up chain the producer runs at once (one per lane)
-static constexpr int QP_SLOT = 512;               // bytes per piece slot
-static constexpr int QP_STAGE_BYTES = QP_SP * QP_SLOT;
 static constexpr int QP_TBL = 19712;              // table slots: 232448 - ring - hot list - metadata, in 8-byte slots
 static constexpr int QP_CAP = 10752;              // entries per query handled here (load factor <= 0.55)
 static constexpr int QP_F_FIRST = 1, QP_F_LAST = 2, QP_F_END = 4;
-
-struct QpHdr { int q, np, flags, total; float qn; int pad; long long qkey; };      // 32 B per stage
-static constexpr size_t QP_SMEM = (size_t)2 * QP_TBL * 4 + (size_t)QM_HOT * 4 + (size_t)QP_STAGES * QP_STAGE_BYTES +
-                                  (size_t)QP_STAGES * QP_SP * 8 + (size_t)QP_STAGES * sizeof(QpHdr) + (size_t)QP_STAGES * 16;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -440,6 +406,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "bra QP_WAIT_%=;\n\t"
       "QP_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -459,286 +428,11 @@ static constexpr unsigned QP_CHUNK = 32768;        // entries of the hot-candida
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(QP_NCW * 32) : "memory"); }
 
-template <bool DUPKEYS>
-__global__ void __launch_bounds__(1024, 1) k_score_qm_pipe(const QmArgs a) {
-  extern __shared__ __align__(128) unsigned char qp_smem[];
-  unsigned* keys = reinterpret_cast<unsigned*>(qp_smem);
-  unsigned* vals = keys + QP_TBL;
-  int* hot = reinterpret_cast<int*>(vals + QP_TBL);
-  unsigned char* ring = reinterpret_cast<unsigned char*>(hot + QM_HOT);                  // QP_STAGES x QP_STAGE_BYTES, 128-byte aligned
-  uint2* meta = reinterpret_cast<uint2*>(ring + (size_t)QP_STAGES * QP_STAGE_BYTES);     // per piece: (len | odd << 16, weight bits)
-  QpHdr* hdr = reinterpret_cast<QpHdr*>(meta + QP_STAGES * QP_SP);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(hdr + QP_STAGES);    // full[QP_STAGES], empty[QP_STAGES]
-  __shared__ unsigned s_hot_n, s_out_n, s_chunk_pos, s_chunk_end, s_chunk_next;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid * 4; i < 2 * QP_TBL; i += 1024 * 4) *reinterpret_cast<uint4*>(keys + i) = make_uint4(0, 0, 0, 0);
-  if (tid == 0) {
-    s_hot_n = 0u;
-    for (int s = 0; s < QP_STAGES; ++s) { mbar_init(smem_u32(bars + s), 1u); mbar_init(smem_u32(bars + QP_STAGES + s), (unsigned)QP_NCW); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == 0) {
-    // ------------------------------------------------ producer
-    // Two latencies are kept off the critical path: (1) the per-query chain cursor -> q_ptr -> offsets -> norm is run
-    // for QP_QG queries at once, one query per lane; (2) the piece descriptors of stage s + 1 are loaded before stage s
-    // is filled, so the only waits left are the ring's own empty barriers.
-    int stage = 0; unsigned phase = 0; unsigned long long n_post = 0;
-    auto load_desc = [&](const long long base, const int np, uint4 (&d)[2]) {
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int k = lane + 32 * r;
-        d[r] = make_uint4(0, 0, 0, 0);
-        if (k < np) d[r] = __ldg(reinterpret_cast<const uint4*>(a.items + base + k));
-      }
-    };
-    for (;;) {
-      int qbase = 0;
-      if (lane == 0) qbase = (int)atomicAdd(&a.counters[C_WORK], (unsigned long long)QP_QG);
-      qbase = __shfl_sync(FULL, qbase, 0);
-      if (qbase >= a.nq) break;
-      // ---- one query per lane: the whole set-up chain in parallel
-      const int myq = qbase + lane;
-      long long my_i0 = 0, my_i1 = 0, my_total = 0, my_qkey = 0; float my_qn = 0.f; bool my_ok = false;
-      if (lane < QP_QG && myq < a.nq) {
-        const int t0 = __ldg(a.q_ptr + myq), t1 = __ldg(a.q_ptr + myq + 1);
-        if (t0 != t1) {
-          const unsigned long long o0 = __ldg(a.item_off + t0), o1 = __ldg(a.item_off + t1);
-          my_i0 = (long long)(o0 >> 36); my_i1 = min((long long)(o1 >> 36), a.item_cap);
-          my_total = (long long)((o1 & 0xfffffffffULL) - (o0 & 0xfffffffffULL));
-          my_ok = my_i0 < my_i1;
-          if (my_ok && my_total > a.cap) {                     // too long for one table pass: the ranged kernel takes it
-            const unsigned long long k = atomicAdd(&a.counters[C_HEAVY], 1ULL);
-            if (k < (unsigned long long)a.deferred_cap) a.deferred[k] = myq;
-            my_ok = false;
-          }
-          if (my_ok) {
-            n_post += (unsigned long long)my_total;
-            my_qn = __ldg(a.q_nrm + myq);
-            if (DUPKEYS) my_qkey = __ldg(a.q_key + myq);
-          }
-        }
-      }
-      unsigned okmask = __ballot_sync(FULL, my_ok);
-      if (!okmask) continue;
-      // ---- the group's stages in order, descriptors one stage ahead
-      int g = __ffs(okmask) - 1;
-      long long base = __shfl_sync(FULL, my_i0, g), gi1 = __shfl_sync(FULL, my_i1, g);
-      uint4 d[2];
-      load_desc(base, (int)min((long long)QP_SP, gi1 - base), d);
-      while (g >= 0) {
-        const int np = (int)min((long long)QP_SP, gi1 - base);
-        const bool first = base == __shfl_sync(FULL, my_i0, g), last = base + QP_SP >= gi1;
-        // what comes next: the query's next stage, or the first stage of the group's next query
-        int ng = g; long long nbase = base + QP_SP, ngi1 = gi1;
-        if (last) {
-          okmask &= ~(1u << g);
-          ng = okmask ? __ffs(okmask) - 1 : -1;
-          const int src = ng >= 0 ? ng : 0;
-          nbase = __shfl_sync(FULL, my_i0, src); ngi1 = __shfl_sync(FULL, my_i1, src);
-        }
-        uint4 dn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (ng >= 0) load_desc(nbase, (int)min((long long)QP_SP, ngi1 - nbase), dn);
-        // ---- fill this stage
-        unsigned bytes[2], sum = 0;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          bytes[r] = (lane + 32 * r < np) ? (((((d[r].x >> 3) & 1u) + d[r].z) * 8u + 15u) & ~15u) : 0u;
-          sum += bytes[r];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-        const int qv = qbase + g; const long long tv = __shfl_sync(FULL, my_total, g);
-        const float qnv = __shfl_sync(FULL, my_qn, g); const long long qkv = __shfl_sync(FULL, my_qkey, g);
-        mbar_wait(smem_u32(bars + QP_STAGES + stage), phase ^ 1u);          // the consumers have released this stage
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int k = lane + 32 * r;
-          if (k < np) meta[stage * QP_SP + k] = make_uint2(d[r].z | (((d[r].x >> 3) & 1u) << 16), d[r].w);
-        }
-        if (lane == 0) {
-          QpHdr hh; hh.q = qv; hh.np = np; hh.total = (int)tv; hh.qn = qnv; hh.pad = 0; hh.qkey = qkv;
-          hh.flags = (first ? QP_F_FIRST : 0) | (last ? QP_F_LAST : 0);
-          hdr[stage] = hh;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(smem_u32(bars + stage), a.dry == 2 ? 0u : sum);
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int k = lane + 32 * r;
-          if (k < np && a.dry != 2) {
-            const unsigned long long pp = ((unsigned long long)d[r].y << 32) | d[r].x;
-            bulk_g2s(smem_u32(ring + (size_t)stage * QP_STAGE_BYTES + (size_t)k * QP_SLOT), reinterpret_cast<const void*>(pp & ~15ULL), bytes[r], smem_u32(bars + stage));
-          }
-        }
-        if (++stage == QP_STAGES) { stage = 0; phase ^= 1u; }
-        g = ng; base = nbase; gi1 = ngi1; d[0] = dn[0]; d[1] = dn[1];
-      }
-    }
-    // no more queries: one empty END stage
-    mbar_wait(smem_u32(bars + QP_STAGES + stage), phase ^ 1u);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n_post += __shfl_down_sync(FULL, n_post, o);
-    if (lane == 0) {
-      QpHdr hh; hh.q = a.nq; hh.np = 0; hh.total = 0; hh.qn = 0.f; hh.pad = 0; hh.qkey = 0; hh.flags = QP_F_END;
-      hdr[stage] = hh;
-      mbar_arrive(smem_u32(bars + stage));
-      if (n_post) atomicAdd(&a.counters[C_POSTINGS], n_post);
-    }
-    return;
-  }
-
-  // -------------------------------------------------- consumers
-  const int cw = warp - 1, ctid = tid - 32;
-  constexpr int CT = QP_NCW * 32;
-  const unsigned keys_s = smem_u32(keys), vals_s = smem_u32(vals);
-  if (ctid == 0) {               // two chunks of the hot-candidate buffer up front; a new one is reserved whenever one is taken
-    s_chunk_pos = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
-    s_chunk_end = s_chunk_pos + QP_CHUNK;
-    s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
-    s_out_n = 0u;
-  }
-  int stage = 0; unsigned phase = 0; unsigned n_cand = 0;
-  unsigned size = 256u, thr_fix = 0u, self = 0xffffffffu; bool scan_all = true; float qn = 0.f; long long qkey = 0; int q = 0;
-  for (;;) {
-    mbar_wait(smem_u32(bars + stage), phase);
-    const QpHdr hh = hdr[stage];
-    if (hh.flags & QP_F_END) break;
-    if (hh.flags & QP_F_FIRST) {
-      q = hh.q; qn = hh.qn; qkey = hh.qkey;
-      size = (unsigned)min((long long)QP_TBL, max(256LL, (3LL * hh.total + 31) & ~31LL));
-      self = a.q_local_base >= 0 ? (unsigned)(a.q_local_base + q) : 0xffffffffu;
-      const float em = (a.thr - a.cu_max * qn * 1.000001f) / a.band1;
-      thr_fix = em > 0.f ? (unsigned)fminf(floorf(em * a.scale * 0.99999f), 4294967040.f) : 0u;
-      scan_all = DUPKEYS || thr_fix == 0u;
-    }
-    if (cw >= hh.np) {                                          // a short stage: nothing for this warp, just release it --
-      __syncwarp();                                             // once EVERY lane has read the header (the producer rewrites it)
-      if (lane == 0) mbar_arrive(smem_u32(bars + QP_STAGES + stage));
-    } else {
-      uint4 v[2]; int jj[2], ln[2]; float ws[2];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int k = cw + QP_NCW * r;
-        v[r] = make_uint4(0, 0, 0, 0); jj[r] = 0; ln[r] = 0; ws[r] = 0.f;
-        if (k < hh.np) {
-          const uint2 m = meta[stage * QP_SP + k];
-          const int odd = (int)(m.x >> 16);
-          ln[r] = (int)(m.x & 0xffffu); ws[r] = __uint_as_float(m.y);
-          jj[r] = 2 * lane - odd;
-          if (jj[r] + 1 >= 0 && jj[r] < ln[r])
-            v[r] = *reinterpret_cast<const uint4*>(ring + (size_t)stage * QP_STAGE_BYTES + (size_t)k * QP_SLOT + (size_t)lane * 16);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(bars + QP_STAGES + stage));      // the postings are in registers: release the stage
-      unsigned cc[4], slot[4], contrib[4], old[4]; bool on[4];
-#pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int e = 2 * r + u;
-          cc[e] = u ? v[r].z : v[r].x;
-          const float w = __uint_as_float(u ? v[r].w : v[r].y);
-          on[e] = jj[r] + u >= 0 && jj[r] + u < ln[r] && cc[e] != self && !a.dry;
-          contrib[e] = __float2uint_ru(__fmul_ru(w, ws[r]));
-          slot[e] = __umulhi(cc[e] * 0x9E3779B1u, size);
-        }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) old[e] = atoms_cas_if(keys_s + slot[e] * 4u, cc[e] + 1u, on[e]);
-      bool coll = false;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) coll |= on[e] && old[e] != 0u && old[e] != cc[e] + 1u;
-      if (coll) {                                              // a slot held by another candidate: linear probing (one branch for all four)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const unsigned k1 = cc[e] + 1u;
-          if (on[e] && old[e] != 0u && old[e] != k1) {
-            unsigned sl_ = slot[e];
-            for (;;) {
-              if (++sl_ == size) sl_ = 0;
-              const unsigned o = atomicCAS(keys + sl_, 0u, k1);
-              if (o == 0u || o == k1) { old[e] = o; break; }
-            }
-            slot[e] = sl_;
-          }
-        }
-      }
-      unsigned prev[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (!DUPKEYS) n_cand += (unsigned)(on[e] && old[e] == 0u);      // (caller keys: counted in the scan; same-key candidates do not count)
-        prev[e] = atoms_add_if(vals_s + slot[e] * 4u, contrib[e], on[e]);
-      }
-      bool anyhot = false;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) anyhot |= on[e] && prev[e] < thr_fix && prev[e] + contrib[e] >= thr_fix;
-      if (anyhot && !scan_all) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (on[e] && prev[e] < thr_fix && prev[e] + contrib[e] >= thr_fix) {
-            const unsigned h = atomicAdd(&s_hot_n, 1u);
-            if (h < (unsigned)QM_HOT) hot[h] = (int)slot[e];
-          }
-      }
-    }
-    if (hh.flags & QP_F_LAST) {
-      // ---- consumer-only epilogue.  No global round trip here: the candidates that crossed the coarse threshold go,
-      // with their final sums, to this CTA's chunk of the hot-candidate buffer; k_qm_filter applies the exact test.
-      consumer_bar();
-      const unsigned nh = s_hot_n;
-      const bool full = scan_all || nh > (unsigned)QM_HOT;
-      if (full) {                                              // rare: every touched slot is written; make room for `size` entries
-        if (ctid == 0 && s_chunk_pos + size > s_chunk_end) {
-          s_chunk_pos = s_chunk_next; s_chunk_end = s_chunk_next + QP_CHUNK;
-          s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
-        }
-        consumer_bar();
-      }
-      const unsigned cpos = s_chunk_pos;
-      auto put = [&](const unsigned at, const unsigned k, const unsigned vv) {
-        const unsigned o = cpos + at;
-        if (o < a.hot_cap) { a.hot_q[o] = q; a.hot_c[o] = (int32_t)(k - 1u); a.hot_est[o] = __uint2float_ru(vv) * a.inv_scale; }
-      };
-      if (full) {
-        for (unsigned i = ctid; i < size; i += CT) {
-          const unsigned k = keys[i];
-          if (!k) continue;
-          if (DUPKEYS) { if (__ldg(a.c_key + (k - 1u)) == qkey) continue; ++n_cand; }
-          put(atomicAdd(&s_out_n, 1u), k, vals[i]);
-        }
-      } else {
-        for (unsigned e = ctid; e < nh; e += CT) { const int sl_ = hot[e]; put(e, keys[sl_], vals[sl_]); }
-      }
-      consumer_bar();
-      for (unsigned i = ctid * 4; i < size; i += CT * 4) {
-        *reinterpret_cast<uint4*>(keys + i) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(vals + i) = make_uint4(0, 0, 0, 0);
-      }
-      if (ctid == 0) {
-        s_chunk_pos += full ? s_out_n : nh; s_out_n = 0u; s_hot_n = 0u;
-        if (s_chunk_pos + (unsigned)QM_HOT > s_chunk_end) {    // the next query's hot list always fits
-          s_chunk_pos = s_chunk_next; s_chunk_end = s_chunk_next + QP_CHUNK;
-          s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
-        }
-      }
-      consumer_bar();
-    }
-    if (++stage == QP_STAGES) { stage = 0; phase ^= 1u; }
-  }
-  unsigned long long nc = n_cand;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) nc += __shfl_down_sync(FULL, nc, o);
-  if (lane == 0 && nc) atomicAdd(&a.counters[C_CANDS], nc);
-}
-
-
 // ------------------------------------------------------------------ the flat-stage variant (default)
 
-// k_score_qm_pipe gives every piece a fixed 512-byte slot and every consumer warp two slots per stage; with the short
-// lists of the young posting segments the slots are ~40 % full and the consumer loop -- which is instruction-issue bound
-// -- spends most of its slots on nothing.  Here the producer PACKS the pieces of a stage back to back (16-byte units, a
+// A first version gave every piece a fixed 512-byte slot and every consumer warp two slots per stage; with the short
+// lists of the young posting segments the slots were ~40 % full and the consumer loop spent most of its issue slots on
+// nothing.  Here the producer PACKS the pieces of a stage back to back (16-byte units, a
 // running offset from a warp prefix sum) and publishes a piece table (start unit, length, parity, weight) plus, per
 // 512-byte window, the first piece that reaches into it.  A consumer warp takes whole windows: lane = one 16-byte unit =
 // two postings, finds its piece with a short forward walk from the window's first piece, and every lane has work.
@@ -852,6 +546,12 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
         if (ng >= 0) load_desc(nbase, ngi1, dn);
         const int qv = qbase + g; const long long tv = __shfl_sync(FULL, my_total, g);
         const float qnv = __shfl_sync(FULL, my_qn, g); const long long qkv = __shfl_sync(FULL, my_qkey, g);
+        // the stage's postings start their way from HBM to L2 now, while the producer waits for a ring slot
+        if ((a.dry & 6) == 4)
+#pragma unroll
+          for (int r = 0; r < QF_PPL; ++r)
+            if (un[r] && st[r] + un[r] <= (unsigned)QF_UNITS)
+              bulk_prefetch_l2(reinterpret_cast<const void*>((((unsigned long long)d[r].y << 32) | d[r].x) & ~15ULL), un[r] * 16u);
         // ---- fill the stage
         mbar_wait(smem_u32(bars + QP_STAGES + stage), phase ^ 1u);          // the consumers have released this stage
         uint2* tab = tab_of(stage); unsigned char* fw = first_of(stage);
@@ -859,22 +559,22 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
         for (int r = 0; r < QF_PPL; ++r) {
           const int k = lane * QF_PPL + r;
           if (un[r] && st[r] + un[r] <= (unsigned)QF_UNITS) {
-            tab[k] = make_uint2(st[r] | (d[r].z << 16) | (((d[r].x >> 3) & 1u) << 24), d[r].w);
+            tab[k] = make_uint2(st[r] | (d[r].z << 12) | (((d[r].x >> 3) & 1u) << 24), d[r].w);
             for (unsigned w = (st[r] + 31u) >> 5; (w << 5) < st[r] + un[r]; ++w) fw[w] = (unsigned char)k;      // windows that start inside this piece
           }
         }
         if (lane == 0) {
-          tab[np] = make_uint2(0xffffu, 0u);                 // sentinel: starts beyond every unit
+          tab[np] = make_uint2(0xfffu, 0u);                  // sentinel: starts beyond every unit
           QfHdr hh; hh.q = qv; hh.np = np; hh.total = (int)tv; hh.qn = qnv; hh.units = (int)endu; hh.qkey = qkv;
           hh.flags = (first ? QP_F_FIRST : 0) | (last ? QP_F_LAST : 0);
           *hdr_of(stage) = hh;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(smem_u32(bars + stage), a.dry == 2 ? 0u : endu * 16u);
+        if (lane == 0) mbar_arrive_expect_tx(smem_u32(bars + stage), (a.dry & 2) ? 0u : endu * 16u);
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < QF_PPL; ++r)
-          if (un[r] && st[r] + un[r] <= (unsigned)QF_UNITS && a.dry != 2) {
+          if (un[r] && st[r] + un[r] <= (unsigned)QF_UNITS && !(a.dry & 2)) {
             const unsigned long long pp = ((unsigned long long)d[r].y << 32) | d[r].x;
             bulk_g2s(smem_u32(ring + (size_t)stage * QF_STAGE_BYTES + (size_t)st[r] * 16), reinterpret_cast<const void*>(pp & ~15ULL), un[r] * 16u, smem_u32(bars + stage));
           }
@@ -934,9 +634,9 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
         if (u < (unsigned)hh.units) {
           int p = fw[cw + QP_NCW * r];
           uint2 cur = tab[p], nxt = tab[p + 1];
-          while ((nxt.x & 0xffffu) <= u) { cur = nxt; ++p; nxt = tab[p + 1]; }       // forward walk: few pieces reach into one window
-          ln[r] = (int)((cur.x >> 16) & 0xffu); ws[r] = __uint_as_float(cur.y);
-          jj[r] = 2 * (int)(u - (cur.x & 0xffffu)) - (int)(cur.x >> 24);
+          while ((nxt.x & 0xfffu) <= u) { cur = nxt; ++p; nxt = tab[p + 1]; }        // forward walk: few pieces reach into one window
+          ln[r] = (int)((cur.x >> 12) & 0xfffu); ws[r] = __uint_as_float(cur.y);
+          jj[r] = 2 * (int)(u - (cur.x & 0xfffu)) - (int)(cur.x >> 24);
           v[r] = *reinterpret_cast<const uint4*>(ring + (size_t)stage * QF_STAGE_BYTES + (size_t)u * 16);
         }
       }
@@ -950,7 +650,7 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
           const int e = 2 * r + u;
           cc[e] = u ? v[r].z : v[r].x;
           const float w = __uint_as_float(u ? v[r].w : v[r].y);
-          on[e] = jj[r] + u >= 0 && jj[r] + u < ln[r] && cc[e] != self && !a.dry;
+          on[e] = jj[r] + u >= 0 && jj[r] + u < ln[r] && cc[e] != self && !(a.dry & 3);
           contrib[e] = __float2uint_ru(__fmul_ru(w, ws[r]));
           slot[e] = __umulhi(cc[e] * 0x9E3779B1u, size);
         }
@@ -993,7 +693,8 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
       }
     }
     if (hh.flags & QP_F_LAST) {
-      // ---- consumer-only epilogue (see k_score_qm_pipe): no global round trip
+      // ---- consumer-only epilogue.  No global round trip here: the candidates that crossed the coarse threshold go,
+      // with their final sums, to this CTA's chunk of the hot-candidate buffer; k_qm_filter applies the exact test.
       consumer_bar();
       const unsigned nh = s_hot_n;
       const bool full = scan_all || nh > (unsigned)QM_HOT;

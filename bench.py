@@ -555,7 +555,7 @@ def main():
     windows = [main_leg["window"], main_leg["window_e2e"]] + ([pr["window"], pr["window_e2e"]] if pr else []) + [j["window"] for j in jobs]
     kname = {1: "apss::k_score", 2: "apss::k_score_blk"}.get((args.variant >> 16) & 0xff, "apss::k_score_dense")
     if main_mode:
-        kname = {3: "apss::k_score_qm_pipe", 2: "apss::k_score_cand", 1: "apss::k_score_dense<pruned>"}[main_mode]
+        kname = {3: "apss::k_score_qm_flat", 2: "apss::k_score_cand", 1: "apss::k_score_dense<pruned>"}[main_mode]
     own_config = world == 1 and args.config == "C3" and not args.n_index and not args.batch
     line = {
         "metric": METRIC, "value": tot["cands"] / dt_value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -614,9 +614,9 @@ def main():
     if pr is not None:
         p_tot, dt_pr, st2 = pr["tot"], pr["dt_value"], pr["stats"]
         ps = p_tot["score_ms"] * 1e-3
-        tr = committed_traffic("apss::k_score_qm_pipe") if own_config else None
+        tr = committed_traffic("apss::k_score_qm_flat") if own_config else None
         line["pruned"] = {
-            "kernel": "apss::k_score_qm_pipe (query-major posting-list traversal of the reduced index; bulk-async producer + 31 consumer warps)"
+            "kernel": "apss::k_score_qm_flat (query-major posting-list traversal of the reduced index; bulk-async producer + 31 consumer warps)"
                       if args.pruned_mode == 3 else "apss::k_score_cand (candidate-major, reduced index)",
             "ms_per_step": dt_pr / K * 1e3, "pairs_per_sec": p_tot["pairs"] / dt_pr,
             "pairset_hash": "%016x" % p_tot["hash"],
