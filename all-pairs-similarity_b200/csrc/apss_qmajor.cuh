@@ -656,10 +656,21 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
         }
 #pragma unroll
       for (int e = 0; e < 4; ++e) old[e] = atoms_cas_if(keys_s + slot[e] * 4u, cc[e] + 1u, on[e]);
+      // second choice, still straight-line: a slot held by another candidate sends the key to an independent second hash
+      // before any probing loop -- the divergent loops below (the warp waits for its slowest lane) become rare and short
+      bool c2[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        c2[e] = on[e] && old[e] != 0u && old[e] != cc[e] + 1u && !(a.dry & 8);      // (dry bit 8: measurement, no second choice)
+        const unsigned s2 = __umulhi((cc[e] ^ 0x5bd1e995u) * 0x85EBCA6Bu, size);
+        if (c2[e]) slot[e] = s2;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const unsigned o2 = atoms_cas_if(keys_s + slot[e] * 4u, cc[e] + 1u, c2[e]); if (c2[e]) old[e] = o2; }
       bool coll = false;
 #pragma unroll
       for (int e = 0; e < 4; ++e) coll |= on[e] && old[e] != 0u && old[e] != cc[e] + 1u;
-      if (coll) {                                              // a slot held by another candidate: linear probing (one branch for all four)
+      if (coll) {                                              // both taken: linear probing from the second slot (one branch for all four)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const unsigned k1 = cc[e] + 1u;

@@ -50,11 +50,6 @@ def main():
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         eng = native.Index(D, t, pruning=mode, reserve_vectors=N + nb * B + B, reserve_nnz=int(data.nnz * 1.05))
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
         t0 = time.time()
         for lo in range(0, N, B):
             eng.insert_batch(*rows(lo, min(N, lo + B)), index_only=True)
@@ -81,6 +76,11 @@ def main():
         print(json.dumps(rec), flush=True)
         out.append(rec)
         eng.close()
+        for k, v in old.items():          # the variant's environment stays in force for its whole run (some knobs are read per call)
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     return out
 
 
