@@ -384,7 +384,7 @@ static constexpr int QP_NCW = 31;                 // consumer warps
 static constexpr int QP_STAGES = 2;
 static constexpr int QP_QG = 8;                   // queries whose set-up chain the producer runs at once (one per lane)
 static constexpr int QP_TBL = 19712;              // table slots: 232448 - ring - hot list - metadata, in 8-byte slots
-static constexpr int QP_CAP = 10752;              // entries per query handled here (load factor <= 0.55)
+static constexpr int QP_CAP = 13568;              // entries per query handled here (load factor <= 0.69: two-choice hashing keeps probes short)
 static constexpr int QP_F_FIRST = 1, QP_F_LAST = 2, QP_F_END = 4;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
