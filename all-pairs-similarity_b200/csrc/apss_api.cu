@@ -42,7 +42,10 @@ struct DevBuf {
   cudaError_t reserve(size_t n, size_t keep, cudaStream_t s) {
     if (n <= cap) return cudaSuccess;
     AllocTrace tr_("cudaMalloc", n * sizeof(T));
-    size_t ncap = std::max(n, cap + cap / 2);
+    // 25 % head-room on every (re)allocation: per-batch scratch is sized by the batch, batches differ by a few percent, and a
+    // cudaMalloc + cudaFree pair costs tens of milliseconds here (large VMM reservations mapped) -- a dozen buffers growing in
+    // the same call was a 0.5 s stall in the middle of a live stream
+    size_t ncap = std::max(n + n / 4, cap + cap / 2);
     ncap = (ncap + 255) & ~size_t(255);
     T* np = nullptr;
     cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
