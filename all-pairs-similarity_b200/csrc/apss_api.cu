@@ -554,23 +554,33 @@ static int32_t prune_select(apss_handle* h, int32_t n, int32_t batch_nnz) {
   cudaStream_t s = h->stream;
   CK(h->q_skip.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->q_cu.reserve(n, 0, s)); CK(h->q_dfmin.reserve(n, 0, s));
   CK(h->q_icnt.reserve(n + 1, 0, s)); CK(h->q_iptr.reserve(n + 1, 0, s));
-  CK(h->pr_keys_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_keys_out.reserve(std::max(batch_nnz, 1), 0, s));
-  CK(h->pr_vals_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_vals_out.reserve(std::max(batch_nnz, 1), 0, s));
+  // ranking inside a warp when every vector of the batch is short enough (C_MAXNNZ: read back after the prefilter)
+  const bool local_rank = (int64_t)h->h_counters[C_MAXNNZ] <= PRL_MAX && !getenv("APSS_PRUNE_GLOBAL_SORT");
   if (batch_nnz) {
     k_df_update<<<cdiv(batch_nnz, 256), 256, 0, s>>>(batch_nnz, h->q_dim.p, h->df.p, 1);
-    CK(cudaGetLastError());
-    k_rank_keys<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->df.p, h->pr_keys_in.p, h->pr_vals_in.p);
-    CK(cudaGetLastError());
-    int rowbits = 1; while ((1LL << rowbits) < n) ++rowbits;
-    size_t tb = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->pr_keys_in.p, h->pr_keys_out.p, h->pr_vals_in.p, h->pr_vals_out.p, batch_nnz, 0, 31 + rowbits, s));
-    CK(h->cub_tmp.reserve(tb, 0, s));
-    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->pr_keys_in.p, h->pr_keys_out.p, h->pr_vals_in.p, h->pr_vals_out.p, batch_nnz, 0, 31 + rowbits, s));
-    h->kernel_launches += 4;
+    CK(cudaGetLastError()); h->kernel_launches++;
   }
-  k_prune_mark<<<cdiv(((int64_t)n + 1) * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_val.p, h->pr_vals_out.p, h->pr_keys_out.p, h->prune_lim, h->q_skip.p, h->q_cu.p, h->q_icnt.p,
-                                                                h->q_dfmin.p, h->d_counters);
-  CK(cudaGetLastError()); h->kernel_launches++;
+  if (local_rank) {
+    k_prune_rank_mark<<<cdiv((int64_t)n + 1, PRL_WARPS), PRL_WARPS * 32, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->q_val.p, h->df.p, h->prune_lim, h->q_skip.p, h->q_cu.p,
+                                                                               h->q_icnt.p, h->q_dfmin.p, h->d_counters);
+    CK(cudaGetLastError()); h->kernel_launches++;
+  } else {
+    CK(h->pr_keys_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_keys_out.reserve(std::max(batch_nnz, 1), 0, s));
+    CK(h->pr_vals_in.reserve(std::max(batch_nnz, 1), 0, s)); CK(h->pr_vals_out.reserve(std::max(batch_nnz, 1), 0, s));
+    if (batch_nnz) {
+      k_rank_keys<<<cdiv((int64_t)n * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_dim.p, h->df.p, h->pr_keys_in.p, h->pr_vals_in.p);
+      CK(cudaGetLastError());
+      int rowbits = 1; while ((1LL << rowbits) < n) ++rowbits;
+      size_t tb = 0;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->pr_keys_in.p, h->pr_keys_out.p, h->pr_vals_in.p, h->pr_vals_out.p, batch_nnz, 0, 31 + rowbits, s));
+      CK(h->cub_tmp.reserve(tb, 0, s));
+      CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tb, h->pr_keys_in.p, h->pr_keys_out.p, h->pr_vals_in.p, h->pr_vals_out.p, batch_nnz, 0, 31 + rowbits, s));
+      h->kernel_launches += 3;
+    }
+    k_prune_mark<<<cdiv(((int64_t)n + 1) * 32, 256), 256, 0, s>>>(n, h->q_ptr.p, h->q_val.p, h->pr_vals_out.p, h->pr_keys_out.p, h->prune_lim, h->q_skip.p, h->q_cu.p, h->q_icnt.p,
+                                                                  h->q_dfmin.p, h->d_counters);
+    CK(cudaGetLastError()); h->kernel_launches++;
+  }
   if (h->prune_mode == 2) {
     size_t tb = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, h->q_icnt.p, h->q_iptr.p, n + 1, s));

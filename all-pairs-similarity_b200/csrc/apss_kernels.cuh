@@ -206,6 +206,61 @@ __global__ void k_prune_mark(int n, const int32_t* __restrict__ q_ptr, const dou
   if (dfmin) dfmin[v] = k > a ? (int32_t)(0x7fffffffLL - (long long)(ranked_keys[k - 1] & 0x7fffffffULL)) : 0x7fffffff;
 }
 
+// k_rank_keys + the radix sort + k_prune_mark in one launch, for batches whose longest vector has <= PRL_MAX components
+// (the usual case; longer ones take the global sort above).  One warp per vector: the ranking keys
+// ((0x7fffffff - df) << 32 | position) go to shared memory, every component's rank is the number of smaller keys
+// (positions are distinct, so the keys are; ascending position = ascending dim, the stable sort's tie order), the
+// positions are scattered into rank order and the walk of k_prune_mark follows, arithmetic and order unchanged.
+static constexpr int PRL_MAX = 512;       // components per vector the in-warp ranking takes
+static constexpr int PRL_WARPS = 8;
+__global__ void __launch_bounds__(PRL_WARPS * 32) k_prune_rank_mark(int n, const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim,
+                                  const double* __restrict__ q_val, const int32_t* __restrict__ df, double lim,
+                                  uint8_t* __restrict__ skip, float* __restrict__ cu, int32_t* __restrict__ icnt,
+                                  int32_t* __restrict__ dfmin, unsigned long long* counters) {
+  __shared__ unsigned long long s_key[PRL_WARPS][PRL_MAX];
+  __shared__ unsigned short s_ord[PRL_WARPS][PRL_MAX];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.x * PRL_WARPS + w;
+  if (v > n) return;
+  if (v == n) { if (lane == 0) icnt[n] = 0; return; }
+  const int a = q_ptr[v], b = q_ptr[v + 1], m = b - a;
+  DBG_ASSERT(m <= PRL_MAX);
+  unsigned long long* key = s_key[w]; unsigned short* ord = s_ord[w];
+  for (int i = lane; i < m; i += 32)
+    key[i] = ((unsigned long long)(unsigned)(0x7fffffff - __ldg(df + __ldg(q_dim + a + i))) << 32) | (unsigned)i;
+  __syncwarp();
+  for (int i = lane; i < m; i += 32) {
+    const unsigned long long ki = key[i];
+    int r = 0;
+    for (int j = 0; j < m; ++j) r += key[j] < ki;          // same j in every lane: shared-memory broadcast
+    ord[r] = (unsigned short)i;
+  }
+  __syncwarp();
+  double s = 0.0; int k = 0; bool open = true;             // k: first rank that stays indexed
+  for (int p0 = 0; p0 < m; p0 += 32) {
+    const int p = p0 + lane;
+    const int pos = p < m ? a + (int)ord[p] : -1;
+    const double x = p < m ? q_val[pos] : 0.0;
+    const double xx = __dmul_rn(x, x);
+    int nskip = 0;
+    if (open) {
+      const int cntl = min(32, m - p0);
+      for (int j = 0; j < cntl; ++j) {
+        const double s2 = __dadd_rn(s, __shfl_sync(FULL, xx, j));
+        if (!(s2 <= lim)) { open = false; break; }
+        s = s2; ++nskip;
+      }
+      k = p0 + nskip;
+    }
+    if (p < m) skip[pos] = lane < nskip ? 1 : 0;
+  }
+  if (lane) return;
+  if (k > 0) atomicAdd(&counters[C_SKIPPED], (unsigned long long)k);
+  cu[v] = s > 0.0 ? __double2float_ru(sqrt(s) * (1.0 + 1e-9)) : 0.f;
+  icnt[v] = m - k;
+  if (dfmin) dfmin[v] = k > 0 ? (int32_t)(0x7fffffffLL - (long long)(key[ord[k - 1]] >> 32)) : 0x7fffffff;
+}
+
 // compact forward store of the INDEXED components only, (dim, fp32 weight), for the candidate-major kernel:
 // appended behind the current end, which lives on the device in ifw_ptr[n_old]
 __global__ void k_ifw_append(int n, int64_t n_old, const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_dim,
@@ -928,7 +983,12 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
   constexpr int NT = WARPS * 32;
   const int nwords = QB * RW;
   for (int i = tid * 4; i < nwords; i += NT * 4) *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
-  unsigned long long n_post = 0, n_cand = 0, n_dpost = 0, n_dfma = 0;
+  // tallies: 32-bit per thread and item, summed per warp into shared 64-bit totals at the top of every item
+  // (keeps four 64-bit counters out of the register file for the whole kernel)
+  __shared__ unsigned long long s_tal[4];
+  if (tid < 4) s_tal[tid] = 0ULL;
+  unsigned n_post = 0, n_cand = 0, n_dpost = 0;
+  __syncthreads();
 #ifdef APSS_PHASE_TIMERS
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tc = clock64();
 #define PHASE_MARK(k) do { if (tid == 0) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; } } while (0)
@@ -939,6 +999,17 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
   const unsigned thr_hi = thr_lo << 16;      // high half >= thr  <=>  word >= thr << 16
 
   for (;;) {
+    {
+      unsigned long long tp = n_post, tc_ = n_cand, td = n_dpost;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        tp += __shfl_down_sync(FULL, tp, o);
+        tc_ += __shfl_down_sync(FULL, tc_, o);
+        td += __shfl_down_sync(FULL, td, o);
+      }
+      if (lane == 0) { if (tp) atomicAdd(&s_tal[0], tp); if (tc_) atomicAdd(&s_tal[1], tc_); if (td) atomicAdd(&s_tal[2], td); }
+      n_post = 0; n_cand = 0; n_dpost = 0;
+    }
     __syncthreads();
     PHASE_MARK(5);
     if (tid == 0) { s_item = atomicAdd(&a.counters[C_WORK], 1ULL); s_nseg = 0; s_segvalid = a.seg_cap - (a.seg_cap * 3 >> 3); s_nshort = 0; s_shortvalid = a.seg_cap * 3 >> 3; s_ndense = 0; s_next = 0; s_next2 = 0; }
@@ -972,7 +1043,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
           const int k = atomicAdd(&s_ndense, 1);
           DBG_ASSERT(k < KD && slot < ndt && nr >= 1 && nr <= QB);
           dl[k] = make_int4(slot, rs, nr, 0);
-          const unsigned long long dp = (unsigned long long)(unsigned)__ldg(dt.len + (size_t)tile * KD + slot) * (unsigned)nr;
+          const unsigned dp = (unsigned)__ldg(dt.len + (size_t)tile * KD + slot) * (unsigned)nr;
           n_post += dp; n_dpost += dp;
         } else {
           s = __ldg(dirt + d); e = __ldg(dirt + d + 1);
@@ -980,7 +1051,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
         }
       }
       const int len = e - s;
-      n_post += (unsigned long long)(unsigned)len * (unsigned)nr;
+      n_post += (unsigned)len * (unsigned)nr;
       if (len > 0 && len <= SPLIT) rw0 = __ldg(b.bt + rs);
       bool coop = false;                      // segment queue full: walk it here, warp-cooperatively
       if (len > SPLIT) {
@@ -1046,7 +1117,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
     __syncthreads();
     // ---- phase D: dense dims by FFMA, thread = COLS adjacent candidates x QB rows
     if (nd) {
-      if (tid == 0) n_dfma += (unsigned long long)((nd + 3) & ~3) * (unsigned long long)QB * (unsigned long long)CR;
+      if (tid == 0) s_tal[3] += (unsigned long long)((nd + 3) & ~3) * (unsigned long long)QB * (unsigned long long)CR;
       const float* __restrict__ wbase = dt.w + (size_t)tile * KD * CR;
       for (int cb = tid * COLS; cb < CR; cb += NT * COLS) {
         float av[COLS][QB];
@@ -1210,14 +1281,13 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) k_score_dens
       PHASE_MARK(4);
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    n_post += __shfl_down_sync(FULL, n_post, o);
-    n_cand += __shfl_down_sync(FULL, n_cand, o);
-    n_dpost += __shfl_down_sync(FULL, n_dpost, o);
+  // the loop flushed every thread's tallies before the break; the barrier at its top ordered them before this read
+  if (tid == 0) {
+    if (s_tal[0]) atomicAdd(&a.counters[C_POSTINGS], s_tal[0]);
+    if (s_tal[1]) atomicAdd(&a.counters[C_CANDS], s_tal[1]);
+    if (s_tal[2]) atomicAdd(&a.counters[C_DENSE_POST], s_tal[2]);
+    if (s_tal[3]) atomicAdd(&a.counters[C_DENSE_FMA], s_tal[3]);
   }
-  if (lane == 0) { atomicAdd(&a.counters[C_POSTINGS], n_post); atomicAdd(&a.counters[C_CANDS], n_cand); if (n_dpost) atomicAdd(&a.counters[C_DENSE_POST], n_dpost); }
-  if (tid == 0 && n_dfma) atomicAdd(&a.counters[C_DENSE_FMA], n_dfma);
 #ifdef APSS_PHASE_TIMERS
   if (tid == 0) { for (int k = 0; k < 8; ++k) atomicAdd(&a.counters[C_PHASE + k], (unsigned long long)ph[k]); }
 #endif

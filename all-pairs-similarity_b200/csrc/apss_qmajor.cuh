@@ -667,21 +667,25 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) { const unsigned o2 = atoms_cas_if(keys_s + slot[e] * 4u, cc[e] + 1u, c2[e]); if (c2[e]) old[e] = o2; }
-      bool coll = false;
+      // both taken: linear probing from the second slot.  ONE loop for the (rarely more than one) keys a lane still has
+      // to place -- four loops, one per register slot, each kept the whole warp for a lane or two
+      unsigned pend = 0u;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) coll |= on[e] && old[e] != 0u && old[e] != cc[e] + 1u;
-      if (coll) {                                              // both taken: linear probing from the second slot (one branch for all four)
+      for (int e = 0; e < 4; ++e) pend |= (on[e] && old[e] != 0u && old[e] != cc[e] + 1u) ? (1u << e) : 0u;
+      if (pend) {
+        auto pick = [&](const unsigned (&x)[4], const int e) { return e == 0 ? x[0] : e == 1 ? x[1] : e == 2 ? x[2] : x[3]; };
+        int e = __ffs((int)pend) - 1;
+        unsigned k1 = pick(cc, e) + 1u, sl_ = pick(slot, e);
+        for (;;) {
+          if (++sl_ == size) sl_ = 0;
+          const unsigned o = atomicCAS(keys + sl_, 0u, k1);
+          if (o == 0u || o == k1) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const unsigned k1 = cc[e] + 1u;
-          if (on[e] && old[e] != 0u && old[e] != k1) {
-            unsigned sl_ = slot[e];
-            for (;;) {
-              if (++sl_ == size) sl_ = 0;
-              const unsigned o = atomicCAS(keys + sl_, 0u, k1);
-              if (o == 0u || o == k1) { old[e] = o; break; }
-            }
-            slot[e] = sl_;
+            for (int r = 0; r < 4; ++r) if (r == e) { old[r] = o; slot[r] = sl_; }
+            pend &= pend - 1u;
+            if (!pend) break;
+            e = __ffs((int)pend) - 1;
+            k1 = pick(cc, e) + 1u; sl_ = pick(slot, e);
           }
         }
       }

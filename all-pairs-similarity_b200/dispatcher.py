@@ -125,6 +125,13 @@ class ShardDispatcher:
             self.batch_no += 1
 
         t2 = time.perf_counter()
+        if self.world == 1:
+            # single rank: nothing to exchange -- one device-to-host fetch through the C ABI, no torch temporaries
+            # (candidate ids are global already: the engine's next_id was set above)
+            qn, cn, sn = self.engine.fetch_pairs()
+            if self.timing is not None:
+                self.timing["bcast"] += t1 - t0; self.timing["score"] += t2 - t1; self.timing["gather"] += time.perf_counter() - t2; self.timing["calls"] += 1
+            return DispatchResult(id_base, owner, res.n_pairs, res.postings_visited, res.candidates_unique, qn, cn, sn, res)
         # 3. pair lists to rank 0.  One all_gather of a fixed-size slot per rank carries the counters AND up to
         #    PAIR_SLOT pairs (sim fp64 | q int32 | c int32), so the usual batch needs a single collective; only when a
         #    rank reports more pairs than fit is a second, exactly sized gather issued.
