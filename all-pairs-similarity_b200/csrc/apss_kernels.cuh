@@ -902,12 +902,58 @@ __device__ __forceinline__ void lane_walk(unsigned* acc, const uint2* __restrict
 // load -> FFMA -> shift -> red.shared chains -- and each register slot is refilled with the NEXT piece's
 // chunk as soon as it has been consumed.  Chunks past the end of the piece are skipped warp-uniformly;
 // only the last chunk is predicated per lane.  dir = +1 / -1: the queue grows up / down from `segs`.
+// predicated streaming load: ONE instruction under a predicate, no branch / convergence barrier around it
+__device__ __forceinline__ uint2 ld_stream_if(const uint2* p, bool on) {
+  uint2 r = make_uint2(0u, 0u);
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];\n\t}"
+      : "+r"(r.x), "+r"(r.y) : "l"(p), "r"((unsigned)on));
+  return r;
+}
+
+__device__ __forceinline__ void red_shared(unsigned saddr, unsigned val) {
+  asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(saddr), "r"(val) : "memory");
+}
+
+// One piece through its NCH register slots.  WHOLE: the piece fills every slot of every lane (most queued pieces are
+// cuts of exactly 32 * NCH postings) -- the reductions carry no predicate, so there is no branch / convergence barrier
+// around them (ptxas turns a predicated ATOMS into BSSY / BRA / BSYNC); otherwise a chunk is skipped warp-uniformly when
+// the piece ends before it and only its last chunk is predicated per lane.  TWO: the dimension is in two rows of the
+// block.  The refill loads are single predicated instructions and the compiler hoists them to the top.
+template <int NCH, bool WHOLE, bool TWO>
+__device__ __forceinline__ void piece_slots(uint2 (&pn)[NCH], const uint2* __restrict__ pt, const int4 S, const int4 Sn, int lane,
+                                            unsigned base0, unsigned base1, float ws0, float ws1, int CR) {
+  const int left = S.y - S.x - lane;                          // chunk u holds one of my postings iff left > 32 u
+  const int len = S.y - S.x;
+#pragma unroll
+  for (int u = 0; u < NCH; ++u) {
+    const uint2 pp = pn[u];
+    const int pnx = Sn.x + lane + 32 * u;
+    pn[u] = ld_stream_if(pt + pnx, pnx < Sn.y);              // refill the slot with the next piece's chunk
+    const float wc = __uint_as_float(pp.y);
+    const unsigned w4 = (pp.x >> 1) << 2, sh = (pp.x & 1u) << 4;
+    if (WHOLE) {
+      DBG_ASSERT(pp.x < (unsigned)CR);
+      red_shared(base0 + w4, fx_contrib(ws0, wc) << sh);
+      if (TWO) red_shared(base1 + w4, fx_contrib(ws1, wc) << sh);
+    } else if (len > 32 * u) {                                // warp-uniform
+      const bool ok = left > 32 * u;
+      DBG_ASSERT(!ok || pp.x < (unsigned)CR);
+      red_shared_if(base0 + w4, fx_contrib(ws0, wc) << sh, ok);
+      if (TWO) red_shared_if(base1 + w4, fx_contrib(ws1, wc) << sh, ok);
+    }
+  }
+}
+
+// Rows beyond the second -- rare for a sparse dimension in a 16-query block -- are applied in a separate loop BEFORE the
+// slots are refilled.
 template <int NCH>
 __device__ __forceinline__ void process_pieces(unsigned* acc, const int4* segs, int dir, int nseg, int* next,
                                                const uint2* __restrict__ pt, const uint2* __restrict__ bt, int lane, int CR) {
   const unsigned acc_s = (unsigned)__cvta_generic_to_shared(acc);
-  int k = 0;
-  if (lane == 0) k = atomicAdd(next, 1);
+  // the queue cursor is read one piece ahead of its use: lane 0 holds the raw ticket, the broadcast (which waits for
+  // the atomic) happens an iteration later, so the atomic's latency is off the piece -> descriptor -> load chain
+  int k = 0, kraw = 0;
+  if (lane == 0) { k = atomicAdd(next, 1); kraw = atomicAdd(next, 1); }
   k = __shfl_sync(FULL, k, 0);
   int4 S = make_int4(0, 0, 0, 0); uint2 rw = make_uint2(0, 0); uint2 pn[NCH];
   if (k < nseg) {
@@ -917,12 +963,11 @@ __device__ __forceinline__ void process_pieces(unsigned* acc, const int4* segs, 
 #pragma unroll
   for (int u = 0; u < NCH; ++u) {
     const int p = S.x + lane + 32 * u;
-    pn[u] = make_uint2(0u, 0u);
-    if (p < S.y) pn[u] = ld_stream(pt + p);
+    pn[u] = ld_stream_if(pt + p, p < S.y);
   }
   while (k < nseg) {
-    if (lane == 0) k = atomicAdd(next, 1);
-    k = __shfl_sync(FULL, k, 0);
+    k = __shfl_sync(FULL, kraw, 0);
+    if (lane == 0) kraw = atomicAdd(next, 1);
     int4 Sn = make_int4(0, 0, 0, 0); uint2 rwn = make_uint2(0, 0);
     if (k < nseg) {
       Sn = segs[dir * k];
@@ -931,25 +976,23 @@ __device__ __forceinline__ void process_pieces(unsigned* acc, const int4* segs, 
     const unsigned ro0 = __shfl_sync(FULL, rw.x, 0), ro1 = __shfl_sync(FULL, rw.x, 1);
     const float ws0 = __uint_as_float(__shfl_sync(FULL, rw.y, 0)), ws1 = __uint_as_float(__shfl_sync(FULL, rw.y, 1));
     const unsigned base0 = acc_s + (ro0 << 2), base1 = acc_s + (ro1 << 2);
-    const bool two = S.w > 1;
+    if (S.w > 2) {                                            // warp-uniform, rare
+      const int left = S.y - S.x - lane;
+      for (int r = 2; r < S.w; ++r) {
+        const unsigned bs = acc_s + (__shfl_sync(FULL, rw.x, r) << 2);
+        const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
 #pragma unroll
-    for (int u = 0; u < NCH; ++u) {
-      const uint2 pp = pn[u];
-      const int pnx = Sn.x + lane + 32 * u;
-      if (pnx < Sn.y) pn[u] = ld_stream(pt + pnx);           // refill the slot with the next piece's chunk
-      if (S.x + 32 * u < S.y) {                               // warp-uniform: chunk u exists in this piece
-        const bool ok = S.x + lane + 32 * u < S.y;           // only the last chunk is partial
-        DBG_ASSERT(!ok || pp.x < (unsigned)CR);
-        const float wc = __uint_as_float(pp.y);
-        const unsigned w4 = (pp.x >> 1) << 2, sh = (pp.x & 1u) << 4;
-        red_shared_if(base0 + w4, fx_contrib(ws0, wc) << sh, ok);
-        if (two) red_shared_if(base1 + w4, fx_contrib(ws1, wc) << sh, ok);     // warp-uniform branch
-        for (int r = 2; r < S.w; ++r) {
-          const unsigned ro = __shfl_sync(FULL, rw.x, r);
-          const float ws = __uint_as_float(__shfl_sync(FULL, rw.y, r));
-          red_shared_if(acc_s + (ro << 2) + w4, fx_contrib(ws, wc) << sh, ok);
-        }
+        for (int u = 0; u < NCH; ++u)
+          red_shared_if(bs + ((pn[u].x >> 1) << 2), fx_contrib(ws, __uint_as_float(pn[u].y)) << ((pn[u].x & 1u) << 4), left > 32 * u);
       }
+    }
+    const bool whole = S.y - S.x == 32 * NCH, two = S.w > 1;   // warp-uniform
+    if (whole) {
+      if (two) piece_slots<NCH, true, true>(pn, pt, S, Sn, lane, base0, base1, ws0, ws1, CR);
+      else piece_slots<NCH, true, false>(pn, pt, S, Sn, lane, base0, base1, ws0, ws1, CR);
+    } else {
+      if (two) piece_slots<NCH, false, true>(pn, pt, S, Sn, lane, base0, base1, ws0, ws1, CR);
+      else piece_slots<NCH, false, false>(pn, pt, S, Sn, lane, base0, base1, ws0, ws1, CR);
     }
     S = Sn; rw = rwn;
   }
