@@ -217,7 +217,7 @@ struct apss_handle {
   DevBuf<unsigned long long> qm_cnt, qm_off; DevBuf<QmItem> qm_items;
   int64_t merges = 0, merged_postings = 0;
   int64_t merge_ratio = 8;   // an older segment more than this many times the newer ones together is left alone (APSS_QM_MERGE_RATIO)
-  int qm_cap = QM_CAP, qm_nt = 1024; size_t qm_items_cap0 = 0; bool qm_pipe = true; DevBuf<int32_t> qm_deferred, hot_q, hot_c; DevBuf<float> hot_est;     // test hooks: APSS_QM_CAP, APSS_QM_ITEMS_CAP
+  int qm_cap = QM_CAP, qm_nt = 1024; size_t qm_items_cap0 = 0; bool qm_pipe = true; DevBuf<int32_t> qm_deferred, hot_q, hot_c; DevBuf<float> hot_est; DevBuf<unsigned> hot_used;     // test hooks: APSS_QM_CAP, APSS_QM_ITEMS_CAP
   bool broken = false;       // a failure after the index was touched that could not be rolled back: every later call fails
   // query-block transposition (v2 kernel)
   DevBuf<unsigned long long> bt_keys_in, bt_keys_out, bt_vals_in, bt_vals_out, ud_key; DevBuf<int32_t> bt_flags, bt_pos, ud_dim, ud_start, bd_ptr;
@@ -534,7 +534,7 @@ extern "C" void apss_destroy(apss_handle* h) {
   h->q_bkt.release(); h->q_dfmin.release(); h->row_dfmin.release();
   h->pr_keys_in.release(); h->pr_keys_out.release(); h->pr_vals_in.release(); h->pr_vals_out.release();
   h->segs.clear(); h->seg_arena[0].release(); h->seg_arena[1].release(); h->dir_pool.release();
-  h->sg_keys_in.release(); h->sg_keys_out.release(); h->sg_vals_in.release(); h->qm_cnt.release(); h->qm_off.release(); h->qm_items.release(); h->qm_deferred.release(); h->hot_q.release(); h->hot_c.release(); h->hot_est.release();
+  h->sg_keys_in.release(); h->sg_keys_out.release(); h->sg_vals_in.release(); h->qm_cnt.release(); h->qm_off.release(); h->qm_items.release(); h->qm_deferred.release(); h->hot_q.release(); h->hot_c.release(); h->hot_est.release(); h->hot_used.release();
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->h_total) cudaFreeHost(h->h_total);
@@ -858,21 +858,25 @@ static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, i
     // producer / consumer kernel for the queries that fit one table pass; the others land on the deferred list.  Its hot
     // candidates go to a chunked buffer (q = -1 marks unused entries), k_qm_filter applies the exact test afterwards.
     if (!h->hot_q.cap) {
-      const size_t c0 = std::max<size_t>((size_t)h->sm_count * 4 * QP_CHUNK, (size_t)1 << 22);
+      size_t c0 = std::max<size_t>((size_t)h->sm_count * 4 * QP_CHUNK, (size_t)1 << 22);
+      { const char* e = getenv("APSS_QM_HOT_CAP"); if (e && atoll(e) >= 1) c0 = (size_t)atoll(e); }      // test hook: forces the grow-and-replay path
       CK(h->hot_q.reserve(c0, 0, s)); CK(h->hot_c.reserve(c0, 0, s)); CK(h->hot_est.reserve(c0, 0, s));
     }
-    CK(cudaMemsetAsync(h->hot_q.p, 0xff, sizeof(int32_t) * h->hot_q.cap, s));
+    const size_t n_chunks = std::min<size_t>(h->hot_q.cap, 0xffff0000u) / QP_CHUNK;       // whole chunks only
+    CK(h->hot_used.reserve(n_chunks, 0, s));
+    CK(cudaMemsetAsync(h->hot_used.p, 0, sizeof(unsigned) * n_chunks, s));     // the chunk directory, not the buffer, is cleared
     CK(cudaMemsetAsync(h->d_counters + C_HOTN, 0, sizeof(unsigned long long), s));
     QmArgs ap = a; ap.cap = std::min(a.cap, QP_CAP);
     { const char* e = getenv("APSS_QM_DRY"); ap.dry = e ? atoi(e) : 0; }
-    ap.hot_q = h->hot_q.p; ap.hot_c = h->hot_c.p; ap.hot_est = h->hot_est.p; ap.hot_cap = (unsigned)std::min<size_t>(h->hot_q.cap, 0xffff0000u);
+    ap.hot_q = h->hot_q.p; ap.hot_c = h->hot_c.p; ap.hot_est = h->hot_est.p; ap.hot_cap = (unsigned)(n_chunks * QP_CHUNK);
+    ap.hot_used = h->hot_used.p; ap.n_chunks = (unsigned)n_chunks;
     {
       auto kern = h->custom_keys ? k_score_qm_flat<true> : k_score_qm_flat<false>;
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QF_SMEM));
       kern<<<h->sm_count, 1024, QF_SMEM, s>>>(ap);
     }
     CK(cudaGetLastError());
-    k_qm_filter<<<h->sm_count * 8, 256, 0, s>>>(ap);
+    k_qm_filter<<<(unsigned)(n_chunks * QF_PARTS), 256, 0, s>>>(ap);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_counters + C_HOTN, h->d_counters + C_HOTN, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     a.from_list = 1; h->kernel_launches += 2;
@@ -1187,7 +1191,7 @@ static int32_t insert_batch_impl(apss_handle* h, BatchTxn& txn, int32_t n, const
     hmark(5);    // all done
     const size_t items_need = h->prune_mode == 3 ? (size_t)(h->h_counters[C_ITEMS] >> 36) : 0;
     const bool items_short = items_need > h->qm_items.cap;
-    const bool hot_short = h->prune_mode == 3 && h->qm_pipe && (size_t)h->h_counters[C_HOTN] > h->hot_q.cap;
+    const bool hot_short = h->prune_mode == 3 && h->qm_pipe && (size_t)h->h_counters[C_HOTN] > std::min<size_t>(h->hot_q.cap, 0xffff0000u) / QP_CHUNK * QP_CHUNK;
     if (hot_short) { const size_t need = (size_t)h->h_counters[C_HOTN] * 2; CK(h->hot_q.reserve(need, 0, s)); CK(h->hot_c.reserve(need, 0, s)); CK(h->hot_est.reserve(need, 0, s)); }
     if (h->h_counters[C_PF] <= h->pf_q.cap && !items_short && !hot_short) break;
     if (attempt == 3) return h->fail(APSS_E_NOMEM, "pair / piece buffer overflow persisted");

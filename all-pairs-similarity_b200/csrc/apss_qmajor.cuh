@@ -169,6 +169,7 @@ struct QmArgs {
   int32_t* out_q; int32_t* out_c; float* out_est; unsigned long long out_cap;
   unsigned long long* counters;
   int32_t* deferred; int32_t deferred_cap;   // queries the pipelined kernel left to the ranged kernel (count in C_HEAVY)
+  unsigned* hot_used; unsigned n_chunks;    // entries written per QP_CHUNK-sized chunk of the hot-candidate buffer (zeroed by the host)
   int32_t* hot_q; int32_t* hot_c; float* hot_est; unsigned hot_cap;     // pipelined kernel: candidates that crossed the query's
                                  // coarse threshold, written in per-CTA chunks reserved on C_HOTN (q = -1: unused entry)
   int32_t from_list;             // k_score_qm: 0 = take every query from the cursor, 1 = take the deferred list
@@ -607,6 +608,17 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
     s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
     s_out_n = 0u;
   }
+  // (consumer thread 0 only) close the current chunk -- its fill goes to the chunk directory k_qm_filter reads -- and
+  // move to the one reserved ahead
+  auto close_chunk = [&]() {
+    const unsigned c0 = s_chunk_end - QP_CHUNK, ci = c0 / QP_CHUNK;
+    if (ci < a.n_chunks) a.hot_used[ci] = s_chunk_pos - c0;
+  };
+  auto next_chunk = [&]() {
+    close_chunk();
+    s_chunk_pos = s_chunk_next; s_chunk_end = s_chunk_next + QP_CHUNK;
+    s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
+  };
   int stage = 0; unsigned phase = 0; unsigned n_cand = 0;
   unsigned size = 256u, thr_fix = 0u, self = 0xffffffffu; bool scan_all = true; float qn = 0.f; long long qkey = 0; int q = 0;
   for (;;) {
@@ -714,10 +726,7 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
       const unsigned nh = s_hot_n;
       const bool full = scan_all || nh > (unsigned)QM_HOT;
       if (full) {
-        if (ctid == 0 && s_chunk_pos + size > s_chunk_end) {
-          s_chunk_pos = s_chunk_next; s_chunk_end = s_chunk_next + QP_CHUNK;
-          s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
-        }
+        if (ctid == 0 && s_chunk_pos + size > s_chunk_end) next_chunk();
         consumer_bar();
       }
       const unsigned cpos = s_chunk_pos;
@@ -741,15 +750,13 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
       }
       if (ctid == 0) {
         s_chunk_pos += full ? s_out_n : nh; s_out_n = 0u; s_hot_n = 0u;
-        if (s_chunk_pos + (unsigned)QM_HOT > s_chunk_end) {    // the next query's hot list always fits
-          s_chunk_pos = s_chunk_next; s_chunk_end = s_chunk_next + QP_CHUNK;
-          s_chunk_next = (unsigned)atomicAdd(&a.counters[C_HOTN], (unsigned long long)QP_CHUNK);
-        }
+        if (s_chunk_pos + (unsigned)QM_HOT > s_chunk_end) next_chunk();    // the next query's hot list always fits
       }
       consumer_bar();
     }
     if (++stage == QP_STAGES) { stage = 0; phase ^= 1u; }
   }
+  if (ctid == 0) close_chunk();          // (every epilogue ended with a consumer barrier: s_chunk_pos is final)
   unsigned long long nc = n_cand;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nc += __shfl_down_sync(FULL, nc, o);
@@ -759,18 +766,23 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
 // The exact candidate test of the pipelined kernel, moved out of its epilogue: one thread per entry of the hot-candidate
 // buffer (q = -1: never written),  estimate * (1 + guard band) + |q| * |c_unindexed| >= t,  survivors compacted into
 // the record list of the fp64 verify kernel (warp-aggregated).
+static constexpr int QF_PARTS = 8;          // blocks per chunk
 __global__ void k_qm_filter(const QmArgs a) {
-  const unsigned long long n = min(a.counters[C_HOTN], (unsigned long long)a.hot_cap);
+  // blockIdx.x = chunk * QF_PARTS + part; the chunk directory says how many entries the scoring kernel wrote there
+  const unsigned ci = blockIdx.x / QF_PARTS, part = blockIdx.x % QF_PARTS;
+  if (ci >= a.n_chunks) return;
+  const unsigned used = min(a.hot_used[ci], (unsigned)QP_CHUNK);
+  constexpr unsigned PER = QP_CHUNK / QF_PARTS;
+  const unsigned lo = part * PER, hi = min(used, lo + PER);
   const int lane = threadIdx.x & 31;
-  for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ULL; i0 < n; i0 += (unsigned long long)gridDim.x * blockDim.x) {
-    const unsigned long long i = i0 + lane;
+  const unsigned long long base0 = (unsigned long long)ci * QP_CHUNK;
+  for (unsigned e0 = lo + (threadIdx.x & ~31u); e0 < hi; e0 += blockDim.x) {
+    const unsigned e = e0 + lane;
     bool pass = false; int q = -1, c = 0; float est = 0.f;
-    if (i < n) {
-      q = a.hot_q[i];
-      if (q >= 0) {
-        c = a.hot_c[i]; est = a.hot_est[i];
-        pass = qm_candidate_passes(a, q, c, est);
-      }
+    if (e < hi) {
+      const unsigned long long i = base0 + e;
+      q = a.hot_q[i]; c = a.hot_c[i]; est = a.hot_est[i];
+      pass = qm_candidate_passes(a, q, c, est);
     }
     const unsigned bal = __ballot_sync(FULL, pass);
     if (!bal) continue;

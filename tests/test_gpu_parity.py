@@ -527,8 +527,8 @@ def test_pruned_c2_shape(mode):
     assert o.totals()["pairs"] > 0 and tp * 20 < tf
 
 
-@pytest.mark.parametrize("cap,items_cap", [(0, 0), (64, 0), (700, 50), (8, 1)])
-def test_query_major_ranged_passes_merges_and_piece_replay(cap, items_cap, monkeypatch):
+@pytest.mark.parametrize("cap,items_cap,hot_cap", [(0, 0, 0), (64, 0, 0), (700, 50, 0), (8, 1, 0), (0, 0, 70000)])
+def test_query_major_ranged_passes_merges_and_piece_replay(cap, items_cap, hot_cap, monkeypatch):
     """pruning = 3: a dimension shared by every vector (too heavy to stay out of the index) gives every query a list as
     long as the index: with the per-pass capacity lowered (APSS_QM_CAP) the query is scored in candidate-id ranges sized
     by the counting walk (halved until they fit); a tiny piece buffer (APSS_QM_ITEMS_CAP) forces the grow-and-replay
@@ -547,6 +547,8 @@ def test_query_major_ranged_passes_merges_and_piece_replay(cap, items_cap, monke
         monkeypatch.setenv("APSS_QM_CAP", str(cap))
     if items_cap:
         monkeypatch.setenv("APSS_QM_ITEMS_CAP", str(items_cap))
+    if hot_cap:      # two chunks of the hot-candidate buffer for 148 CTAs: the first call overflows, grows and replays
+        monkeypatch.setenv("APSS_QM_HOT_CAP", str(hot_cap))
     n = native()
     for use_keys in (False, True):
         o = orc.Oracle(D, t, algo=orc.ALGO_FAST, threads=8, pruning=True)
