@@ -80,6 +80,7 @@ class GpuIndexingWorkerActor:
         sem = str(conf_get(conf, "cpslab.allpair.gpu.semantics", "R1")).upper()
         self.as_built = sem == "R0"
         self.replyTo = replyTo
+        self.now_ms = lambda: int(time.time() * 1000)     # System.currentTimeMillis (a virtual clock in protocol tests)
         self.writeBuffer: Dict[str, Dict[str, float]] = {}
         self.stopUpdateIndex = False
         self._ids: List[str] = []                 # internal id -> caller's String id
@@ -104,7 +105,7 @@ class GpuIndexingWorkerActor:
             self._handle_batch(list(msg.vectors), skip_admit=False)
         elif isinstance(msg, IOTicket) or msg is IOTicket:
             if self.writeBuffer:                                               # IWA:139-142
-                self._reply(SimilarityOutput(dict(self.writeBuffer), int(time.time() * 1000)))
+                self._reply(SimilarityOutput(dict(self.writeBuffer), self.now_ms()))
                 self.writeBuffer = {}
         elif isinstance(msg, ReceiveTimeout) or msg is ReceiveTimeout:
             self.stopUpdateIndex = True                                        # IWA:143-144
@@ -121,7 +122,7 @@ class GpuIndexingWorkerActor:
             out = self.query_and_index(vectors, skip_admit, firsts)
             if self.replyTo is not None:                                       # IWA:128
                 if self.outputWritingDuration <= 0:                            # IWA:129-130
-                    self._reply(SimilarityOutput(out, int(time.time() * 1000)))
+                    self._reply(SimilarityOutput(out, self.now_ms()))
                 else:                                                          # IWA:131-132, 113-120
                     for q, sims in out.items():
                         for c, s in sims.items():
