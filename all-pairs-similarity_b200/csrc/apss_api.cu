@@ -868,6 +868,7 @@ static int32_t score_query_major(apss_handle* h, int32_t n, int32_t batch_nnz, i
     CK(cudaMemsetAsync(h->d_counters + C_HOTN, 0, sizeof(unsigned long long), s));
     QmArgs ap = a; ap.cap = std::min(a.cap, QP_CAP);
     { const char* e = getenv("APSS_QM_DRY"); ap.dry = e ? atoi(e) : 0; }
+    { const char* e = getenv("APSS_QM_SIZEF"); ap.sizef = e && atoi(e) >= 3 ? atoi(e) : 6; }
     ap.hot_q = h->hot_q.p; ap.hot_c = h->hot_c.p; ap.hot_est = h->hot_est.p; ap.hot_cap = (unsigned)(n_chunks * QP_CHUNK);
     ap.hot_used = h->hot_used.p; ap.n_chunks = (unsigned)n_chunks;
     {

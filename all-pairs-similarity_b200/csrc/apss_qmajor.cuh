@@ -173,6 +173,7 @@ struct QmArgs {
   int32_t* hot_q; int32_t* hot_c; float* hot_est; unsigned hot_cap;     // pipelined kernel: candidates that crossed the query's
                                  // coarse threshold, written in per-CTA chunks reserved on C_HOTN (q = -1: unused entry)
   int32_t from_list;             // k_score_qm: 0 = take every query from the cursor, 1 = take the deferred list
+  int32_t sizef;                 // pipelined kernel: table slots per list entry, in halves (6 = 3.0: load factor <= 1/3 where the table allows)
   int32_t dry;                   // measurement only (APSS_QM_DRY, bits): 1 = no table updates, 2 = no copies, 4 = L2 prefetch of the
                                  // next stage's pieces while the producer waits (measured: slower -- it doubles the bulk requests)
 };
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(1024, 1) k_score_qm_flat(const QmArgs a) {
     if (hh.flags & QP_F_END) break;
     if (hh.flags & QP_F_FIRST) {
       q = hh.q; qn = hh.qn; qkey = hh.qkey;
-      size = (unsigned)min((long long)QP_TBL, max(256LL, (3LL * hh.total + 31) & ~31LL));
+      size = (unsigned)min((long long)QP_TBL, max(256LL, ((long long)a.sizef * hh.total / 2 + 31) & ~31LL));
       self = a.q_local_base >= 0 ? (unsigned)(a.q_local_base + q) : 0xffffffffu;
       const float em = (a.thr - a.cu_max * qn * 1.000001f) / a.band1;
       thr_fix = em > 0.f ? (unsigned)fminf(floorf(em * a.scale * 0.99999f), 4294967040.f) : 0u;
