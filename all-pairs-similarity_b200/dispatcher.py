@@ -53,6 +53,7 @@ class ShardDispatcher:
         self.next_id = 0
         self.batch_no = 0
         self.frozen = False
+        self._payload = None     # broadcast buffer, grow-only
         # APSS_DISPATCH_TIMING=1: wall-clock per phase (broadcast, local scoring, gather), summed over the calls
         import os
         self.timing = {"bcast": 0.0, "score": 0.0, "gather": 0.0, "calls": 0} if os.environ.get("APSS_DISPATCH_TIMING") else None
@@ -97,10 +98,15 @@ class ShardDispatcher:
             self._bcast(hdr)
             n, nnz = (int(x) for x in hdr.tolist())
             b0, b1 = 8 * (n + 1), 8 * (n + 1) + 8 * nnz
+            # the payload lives in ONE grow-only buffer per rank (25 % head-room): a fresh tensor per batch means a
+            # cudaMalloc whenever a batch is a little larger than every one before, and with the shard's large
+            # reservations mapped that call takes tens of milliseconds -- in the middle of a stream of 16 ms steps
+            nbytes = b1 + 4 * nnz
+            if self._payload is None or self._payload.numel() < nbytes:
+                self._payload = torch.empty(nbytes + nbytes // 4 + 4096, dtype=torch.uint8, device=dev)
+            payload = self._payload[:nbytes]
             if self.rank == 0:
-                payload = torch.cat([indptr.view(torch.uint8), values.view(torch.uint8), indices.view(torch.uint8)])
-            else:
-                payload = torch.empty(b1 + 4 * nnz, dtype=torch.uint8, device=dev)
+                payload[:b0].copy_(indptr.view(torch.uint8)); payload[b0:b1].copy_(values.view(torch.uint8)); payload[b1:].copy_(indices.view(torch.uint8))
             self._bcast(payload)
             if self.rank != 0:
                 indptr = payload[:b0].view(torch.int64)

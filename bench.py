@@ -91,14 +91,43 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons DURING the timed region (the B200_PROFILING.md clocks line), every 100 ms.
+    Read through NVML in-process (what nvidia-smi itself reads): a polling `nvidia-smi -lms` child stalls the driver for
+    ~1 s at start-up and now and then for tens of ms per poll on a multi-GPU box -- inside a stream of 16 ms steps.
+    Falls back to the nvidia-smi loop when the NVML binding is missing.  Rows: (time, "sm,max,power,hw,hwth,swth,swcap")."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self._stop = gpu_index, [], None, False
+
+    def _nvml_loop(self, nv, hdl):
+        bits = [getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = nv.nvmlDeviceGetMaxClockInfo(hdl, nv.NVML_CLOCK_SM)
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(hdl, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(hdl) / 1000.0
+                r = int(get_reasons(hdl))
+                self.rows.append((time.time(), "%d, %d, %.2f, %s" % (sm, mx, pw, ", ".join("Active" if r & b else "Not Active" for b in bits))))
+            except Exception:      # noqa: BLE001
+                pass
+            time.sleep(0.1)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists ordinals
+            vis = [x for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip().isdigit()]
+            idx = int(vis[self.gpu]) if self.gpu < len(vis) else self.gpu
+            hdl = nv.nvmlDeviceGetHandleByIndex(idx)
+            threading.Thread(target=self._nvml_loop, args=(nv, hdl), daemon=True).start()
+            return
+        except Exception:      # noqa: BLE001
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -112,6 +141,7 @@ class ClockSampler:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self):
+        self._stop = True
         if self.proc:
             self.proc.terminate()
             try:
