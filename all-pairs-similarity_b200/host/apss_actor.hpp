@@ -304,10 +304,13 @@ class GpuIndexingWorkerActor {
   std::map<std::string, std::map<std::string, double>> writeBuffer;          // IWA:28
   apss_batch_result last_result{};
 
- private:
-  static int64_t now_ms() {
+  // System.currentTimeMillis; protocol tests put a virtual clock here (apss_loadgen.hpp)
+  std::function<int64_t()> now_ms = [] {
     return (int64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
-  }
+  };
+  void setReplyTo(Reply r) { replyTo_ = std::move(r); }          // outputActor (IWA:44), resolved after construction
+
+ private:
   void reply(const OutMessage& m) { if (replyTo_) replyTo_(m); }
   void handle_batch(const std::vector<IdVector>& vectors, bool skip_admit, const std::vector<int32_t>* firsts = nullptr) {
     try {                                                                    // IWA:124

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "apss_actor.hpp"
+#include "apss_loadgen.hpp"
 #ifdef USE_ORACLE_ENGINE
 #include "oracle_engine.hpp"
 using Engine = OracleEngine;
@@ -179,6 +180,48 @@ static void formats() {
   CHECK(threw);
 }
 
+// The reference's latency experiment (benchmark/LoadGenerator.scala:15-173) on a virtual clock: two runners, warm-up,
+// StartTest after the parent's ReceiveTimeout, every runner restarting its ids at 1, response time = outputMoment - StartTime
+// (immediate output: 0 ms; output buffered for 25 ms: the wait for the next flush).  Same checks as tests/test_loadgen.py.
+static void loadgen_protocol(int pruning, long long output_io_ms) {
+  const int D = 32, total = 4, kids = 2, nvid = 6;
+  Config conf{{"cpslab.allpair.similarityThreshold", "0.3"}, {"cpslab.allpair.outputIODuration", std::to_string(output_io_ms)},
+              {"cpslab.allpair.vectorDim", std::to_string(D)}, {"cpslab.allpair.indexThreshold", "0.0"},
+              {"cpslab.allpair.benchmark.expDuration", "500"}, {"cpslab.allpair.benchmark.writeBatchingDuration", "10"},
+              {"cpslab.allpair.benchmark.totalMessageCount", std::to_string(total)}, {"cpslab.allpair.benchmark.childrenNum", std::to_string(kids)}};
+  std::vector<IdVector> videos;
+  for (int i = 0; i < nvid; ++i)       // three shared dimensions: every pair of videos is similar; NOT normalised (the runner does it)
+    videos.push_back({"v" + std::to_string(i), SparkSparseVector(D, {0, 1, 2, 3 + i % 3, 8 + i}, {1.0 + 0.1 * i, 1.5, 0.7 + 0.05 * i, 1.1, 0.9})});
+  Engine* eng = make_engine(D, 0.3, 0.0, false, pruning);
+  GpuIndexingWorkerActor<Engine> w(conf, *eng, nullptr);
+  EventLoop loop(true, 1000000);
+  std::vector<std::pair<int64_t, std::string>> seen; std::vector<std::string> lines;
+  const auto rep = run_experiment(conf, videos, w, loop, true, [&](const std::string& ln) { lines.push_back(ln); },
+                                  [&](int64_t at, const VectorIOMsg& m) { seen.push_back({at, m.vectors[0].first}); });
+  // warm-up: runner i counts from i * total (LG:22) until msgCount > videos.size (LG:63-66), one vector per 10 ms tick
+  std::vector<int> warm_ids, test_ids; std::vector<int64_t> test_at;
+  for (const auto& [at, id] : seen) { if (at < 1000500) warm_ids.push_back(std::stoi(id)); else { test_ids.push_back(std::stoi(id)); test_at.push_back(at); } }
+  std::vector<int> want_warm;
+  for (int i = 1; i <= nvid + 1; ++i) want_warm.push_back(i);
+  for (int i = total + 1; i <= nvid + 1; ++i) want_warm.push_back(i);
+  std::sort(warm_ids.begin(), warm_ids.end()); std::sort(want_warm.begin(), want_warm.end());
+  CHECK(warm_ids == want_warm);
+  CHECK(seen.size() >= 4 && seen[0].first == 1000000 && seen[1].first == 1000000 && seen[2].first == 1000010 && seen[3].first == 1000010);
+  // test phase: every runner restarts at 1 (LG:79) -- the same ids from all children, as built
+  std::vector<int> want_test;
+  for (int k = 0; k < kids; ++k) for (int i = 1; i <= total + 1; ++i) want_test.push_back(i);
+  std::sort(test_ids.begin(), test_ids.end()); std::sort(want_test.begin(), want_test.end());
+  CHECK(test_ids == want_test);
+  CHECK(!test_at.empty() && test_at[0] >= 1000500 && test_at.size() >= 4 && test_at[1] == test_at[0] && test_at[2] == test_at[0] + 10);
+  CHECK(w.stopUpdateIndex);                                               // the worker's own ReceiveTimeout froze the index (IWA:143-144)
+  CHECK(rep.messages >= 1 && rep.with_both == rep.messages && rep.min >= 0 && rep.min <= rep.average && rep.average <= rep.max);
+  if (output_io_ms <= 0) CHECK(rep.max == 0);                             // answered inside the tick
+  else CHECK(rep.max > 0 && rep.max <= output_io_ms);                     // the wait for the worker's next IOTicket
+  CHECK(rep.line.rfind("LoadGenerator stopped with " + std::to_string(rep.messages) + " messages, average response time", 0) == 0);
+  CHECK(!lines.empty() && lines[0].find(" lasting Time:") != std::string::npos);
+  delete eng;
+}
+
 int main(int argc, char** argv) {
   const int pruning = argc > 1 ? std::atoi(argv[1]) : 0;
   for (int a = 2; a < argc; ++a) g_devices.push_back(std::atoi(argv[a]));      // e.g. "0 1 2 3": device_ids of the one handle
@@ -187,6 +230,8 @@ int main(int argc, char** argv) {
   buffered_output_and_router();
   as_built_first_list_skip();
   index_data_and_data_packet(pruning);
+  loadgen_protocol(pruning, 0);
+  loadgen_protocol(pruning, 25);
   if (failures) { std::fprintf(stderr, "%d check(s) failed\n", failures); return 1; }
   std::printf("actor scenario ok (pruning=%d, devices=%zu)\n", pruning, g_devices.empty() ? (size_t)1 : g_devices.size());
   return 0;
