@@ -40,12 +40,15 @@ def _worker(rank, world, port, N, D, t, B, ret, pair_slot=0):
             for q, c, s in zip(r.q, r.c, r.sim):
                 got[(int(r.id_base + q), int(c))] = float(s)
             assert r.n_pairs == len(r.q)
-    # frozen: a query-only batch is scored on every shard and indexed nowhere
+    # frozen: a query-only batch is scored on every shard and indexed nowhere (2.5x the size of the earlier batches:
+    # the grow-only broadcast buffer is re-allocated on every rank, then a small batch re-uses it)
     disp.freeze()
-    r = disp.insert_batch(*(csr_slice(data, 0, 50) if rank == 0 else (None, None, None)))
+    r = disp.insert_batch(*(csr_slice(data, 0, 500) if rank == 0 else (None, None, None)))
+    r2 = disp.insert_batch(*(csr_slice(data, 0, 50) if rank == 0 else (None, None, None)))
     if rank == 0:
         ret["pairs"] = got; ret["tot"] = tot
         ret["frozen_pairs"] = {(int(q), int(c)) for q, c in zip(r.q, r.c)}
+        ret["frozen_pairs_small"] = {(int(q), int(c)) for q, c in zip(r2.q, r2.c)}
         ret["next_id"] = disp.next_id
     dist.destroy_process_group()
 
@@ -66,6 +69,8 @@ def test_dispatcher_world2_matches_single_oracle(pair_slot):
             want.update(r.pair_set()); tot[0] += r.postings_visited; tot[1] += r.candidates_unique
     assert dict(ret["pairs"]) == want and len(want) > 0           # bit-exact, every pair exactly once
     assert list(ret["tot"]) == tot
-    rq = o.insert_batch(*csr_slice(data, 0, 50), query_only=True)
-    assert ret["frozen_pairs"] == {(int(q), int(c)) for q, c in zip(rq.q, rq.c)}
+    rq = o.insert_batch(*csr_slice(data, 0, 500), query_only=True)
+    assert ret["frozen_pairs"] == {(int(q), int(c)) for q, c in zip(rq.q, rq.c)} and len(rq.q) > 0
+    rq2 = o.insert_batch(*csr_slice(data, 0, 50), query_only=True)
+    assert ret["frozen_pairs_small"] == {(int(q), int(c)) for q, c in zip(rq2.q, rq2.c)}
     assert ret["next_id"] == N
