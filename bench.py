@@ -28,6 +28,9 @@ One JSON line on rank 0:
   cpu_baseline  the oracle's restatement of the reference algorithm (cpu_ref, `value`) and the accumulator algorithm
                 (cpu_opt) on this box's host cores, same index, bounded query samples.
 --impl reference times the CPU path as its own arm on the same config (rank 0 only).
+Timed regions: the step's input batches are cut out of the generated matrix BEFORE the clock starts (resident in HBM);
+every step fetches its pairs to the host inside the region; the order-independent pair hash is computed after it.
+`clocks`: SM clock / power / throttle reasons every 100 ms during the timed regions, read through in-process NVML.
 """
 from __future__ import annotations
 
